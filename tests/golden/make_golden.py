@@ -81,6 +81,7 @@ def run_case(spec, solver, dtype, iw, n_batch=None, traces=True, tag=None):
     q_prec = np.ones((B, P), np.float64)
     p_mu = np.zeros(P, np.float64)
     p_prec = np.ones(P, np.float64)
+    p_sigma = np.ones(P, np.float64)
     g_mu = np.zeros((B, P), np.float64)
     g_prec = np.zeros((B, P), np.float64)
     per_individual = np.zeros(P, np.int32)
@@ -100,6 +101,7 @@ def run_case(spec, solver, dtype, iw, n_batch=None, traces=True, tag=None):
         q_prec[:, k] = prec
         p_mu[k] = float(pd_.mu)
         p_prec[k] = float(pd_.prec)
+        p_sigma[k] = float(pd_.sigma)
         gm = d.mu.grad
         gp = d.prec.grad
         if gm is not None:
@@ -117,6 +119,7 @@ def run_case(spec, solver, dtype, iw, n_batch=None, traces=True, tag=None):
         "devices": np.asarray(batch.devices).astype(np.int32),
         "u": _np(captured["u"]).astype(fdt),
         "q_mu": q_mu.astype(fdt), "q_prec": q_prec.astype(fdt), "p_mu": p_mu.astype(fdt), "p_prec": p_prec.astype(fdt),
+        "p_sigma": p_sigma.astype(fdt),
         "theta": np.stack([_np(theta.samples[n]) for n in names]).astype(fdt),  # clipped, unconditioned [P,B,IW]
         "log_p_by_species": _np(log_p_by_species).astype(fdt),
         "log_p_theta": _np(log_p_theta).astype(fdt), "log_q_theta": _np(log_q_theta).astype(fdt),
