@@ -1,0 +1,181 @@
+/*
+ * vihds_b200.h -- C ABI of libvihds_b200.so: the B200-native batched ODE-integration + ELBO engine that replaces the
+ * hot path of microsoft/vi-hds.
+ *
+ * The reference has no FFI: its boundary is the Python plugin surface.  Each entry point below
+ * names the reference interface (file:line under /root/reference) whose work it takes over; INTEGRATION.md shows the
+ * ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer in the *_io structs is a DEVICE pointer owned by the caller (PyTorch's allocator in practice);
+ *    the library allocates nothing persistent and keeps no global mutable state; calls are asynchronous on `stream`
+ *    (a cudaStream_t passed as void*; NULL = legacy default stream) and re-entrant;
+ *  - host-side descriptors (vh_problem, slot maps, the io structs themselves) are read during the call only;
+ *  - return value: 0 on success, a negative vh_status otherwise; vh_last_error() gives a thread-local message;
+ *  - dtype: VH_F32 or VH_F64 (data.dtype, vihds/config.py:164-178); all floating-point buffers of one call share it;
+ *  - trajectory index n = b * IW + i  (b individual, i importance sample), N = B * IW.
+ *
+ * Device layouts (chosen for coalescing across trajectories; the reference itself returns x_states as a permuted,
+ * time-major view, vihds/ode.py:82):
+ *    u          [N][P]        as produced by BaseVAE.sample_u (vihds/vae.py:22-24), row-major
+ *    q_mu,q_prec[B][P]        encoder output per individual (global parameters repeated over B)
+ *    theta      [P][N]        clipped samples, one contiguous [B,IW] plane per parameter
+ *    extra      [E][N]        per-trajectory inputs that are not sampled (conditioned aR/aS, or all of theta in
+ *                             vh_simulate)
+ *    x_states   [T][S][N]     S = species + dynamic-precision states;   x_predict [T][4][N]
+ *    observations [B][4][T]   as in the reference batch (vihds/training.py:47-68)
+ *    logp_by_species [N][4];  logp_theta, logq_theta [N]
+ */
+#ifndef VIHDS_B200_H
+#define VIHDS_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VH_ABI_VERSION 1
+
+enum vh_status {
+  VH_OK = 0,
+  VH_ERR_INVALID = -1,     /* bad argument / unsupported combination */
+  VH_ERR_UNSUPPORTED = -2, /* e.g. adaptive solvers (dopri5/8): no fixed-step kernel, and no CPU fallback */
+  VH_ERR_CUDA = -3         /* a CUDA runtime call failed */
+};
+
+enum vh_dtype { VH_F32 = 0, VH_F64 = 1 };
+
+/* models.LOOKUP keys (models/__init__.py:19-35) that have a kernel */
+enum vh_model {
+  VH_MODEL_DR_CONSTANT = 0,               /* models/dr_constant.py:114-160, version 1 */
+  VH_MODEL_DR_CONSTANT_V2 = 1,            /* models/dr_constant.py:163-166 */
+  VH_MODEL_DR_CONSTANT_PRECISIONS = 2,    /* models/dr_constant.py:169-209 (NeuralPrecisions states) */
+  VH_MODEL_DR_CONSTANT_PRECISIONS_V2 = 3, /* models/dr_constant.py:212-215 */
+  VH_MODEL_RELAY_CONSTANT = 4,            /* models/relay_constant.py:137-196 */
+  VH_MODEL_RELAY_CONSTANT_PRECISIONS = 5, /* models/relay_constant.py:199-263 */
+  VH_MODEL_DR_BLACKBOX = 6,               /* models/dr_blackbox.py:61-125 */
+  VH_MODEL_COUNT = 7
+};
+
+/* params.solver values (vihds/ode.py:75-81) */
+enum vh_solver {
+  VH_SOLVER_EULER = 0,         /* torchdiffeq fixed-grid euler */
+  VH_SOLVER_MIDPOINT = 1,      /* torchdiffeq fixed-grid midpoint (spec default, vihds/config.py:59) */
+  VH_SOLVER_RK4 = 2,           /* torchdiffeq 0.1 "rk4" = 3/8 rule */
+  VH_SOLVER_MODEULER = 3,      /* vihds/solvers.py:9-17: Heun with CONSTANT h = times[1]-times[0] */
+  VH_SOLVER_MODEULERWHILE = 4, /* vihds/solvers.py:20-41: Heun with per-step h */
+  VH_SOLVER_COUNT = 5
+};
+
+enum vh_kind { VH_KIND_CONSTANT = 0, VH_KIND_NORMAL = 1, VH_KIND_LOGNORMAL = 2 };
+
+#define VH_MAX_SLOTS 64
+#define VH_SLOT_UNUSED (-1000000)
+
+typedef struct vh_problem {
+  int model;  /* vh_model */
+  int solver; /* vh_solver */
+  int dtype;  /* vh_dtype */
+  int B, IW, T;
+  int P; /* sampled parameters = columns of u (0 in vh_simulate) */
+  int C; /* treatments per individual (2: C6, C12) */
+  int D; /* device one-hot width (used by the black-box model only) */
+  int E; /* rows of `extra` */
+  int n_hidden; /* NeuralPrecisions hidden width (0 = single linear layer), black-box: precision-net hidden width */
+  int n_hidden_states; /* black-box NeuralStates hidden width */
+  int n_latent; /* black-box latent species */
+  int n_z, n_x, n_y; /* black-box latent-parameter counts */
+  /* slot_src[s]: where model slot s (see vh_slot_name) takes its value from:
+   *   >= 0  column of u / theta;   -1-e  row e of `extra`;   VH_SLOT_UNUSED  not provided (value 0). */
+  int slot_src[VH_MAX_SLOTS];
+} vh_problem;
+
+/* Forward: replaces, in ONE launch, q.sample + p.clip (vihds/distributions.py:119-142, :76-85), Decoder.forward
+ * (vihds/decoders.py:28-45 -> OdeModel.simulate vihds/ode.py:66-82, expand_precisions, observe), and the per-sample
+ * terms of Training.cost (vihds/training.py:130-136: log_prob_observations :24-44, q.log_prob, p.log_prob). */
+typedef struct vh_fwd_io {
+  const void* times;        /* [T] */
+  const void* u;            /* [N][P]  (NULL iff P == 0) */
+  const void* q_mu;         /* [B][P] */
+  const void* q_prec;       /* [B][P] */
+  const void* p_mu;         /* [P] prior mean */
+  const void* p_prec;       /* [P] prior precision */
+  const void* clip_lo;      /* [P] lower clip bound (prior mu - 4 sigma, exp'd for LogNormal); -inf = unclipped */
+  const void* clip_hi;      /* [P] */
+  const int* kind;          /* [P] vh_kind */
+  const void* extra;        /* [E][N] or NULL */
+  const void* treatments;   /* [B][C] log1p-transformed inputs (vihds/datasets.py:87) */
+  const void* dev_1hot;     /* [B][D] or NULL (black-box only) */
+  const void* observations; /* [B][4][T] or NULL (then no log-likelihood is accumulated) */
+  const void* weights;      /* flat decoder weights (layout: vh_weight_layout) or NULL */
+  void* theta;              /* out [P][N] or NULL */
+  void* x_states;           /* out [T][S][N] or NULL */
+  void* x_predict;          /* out [T][4][N] or NULL */
+  void* logp_by_species;    /* out [N][4] or NULL */
+  void* logp_theta;         /* out [N] or NULL */
+  void* logq_theta;         /* out [N] or NULL */
+} vh_fwd_io;
+
+/* Backward (discrete adjoint of the exact stepper; what autograd's replay of the unrolled solve computes in the
+ * reference, vihds/training.py:334).  Re-reads the x_states trace written by the forward call as its checkpoint. */
+typedef struct vh_bwd_io {
+  vh_fwd_io fwd;                 /* the forward call's inputs and its x_states output (x_predict/log* unused) */
+  const void* g_logp_by_species; /* [N][4] upstream gradients, any may be NULL (= zero) */
+  const void* g_logp_theta;      /* [N] */
+  const void* g_logq_theta;      /* [N] */
+  const void* g_theta;           /* [P][N] */
+  const void* g_x_states;        /* [T][S][N] */
+  const void* g_x_predict;       /* [T][4][N] */
+  void* d_q_mu;                  /* out [B][P], OVERWRITTEN (zeroed by the call, then accumulated) or NULL */
+  void* d_q_prec;                /* out [B][P] */
+  void* d_extra;                 /* out [E][N] or NULL */
+  void* d_weights;               /* out flat, same layout as weights (zeroed by the call) or NULL */
+} vh_bwd_io;
+
+int vh_abi_version(void);
+const char* vh_last_error(void);
+
+/* registry helpers: the Python side builds slot maps from names, never from hard-coded indices */
+int vh_model_id(const char* lookup_key);  /* models.LOOKUP key -> vh_model, or VH_ERR_UNSUPPORTED */
+int vh_solver_id(const char* name);       /* params.solver -> vh_solver, VH_ERR_UNSUPPORTED for adaptive solvers */
+int vh_num_slots(int model);
+const char* vh_slot_name(int model, int slot); /* theta attribute name the RHS reads (e.g. "KGR_76") */
+int vh_num_species(int model);                 /* OdeModel.n_species */
+int vh_state_width(const vh_problem* p);       /* S = species + dynamic-precision states */
+size_t vh_num_weights(const vh_problem* p);    /* length of the flat weight vector (0 for constant-precision models) */
+
+int vh_elbo_terms_fwd(const vh_problem* p, const vh_fwd_io* io, void* stream);
+int vh_elbo_terms_bwd(const vh_problem* p, const vh_bwd_io* io, void* stream);
+
+/* Narrow seam: OdeModel.simulate (vihds/ode.py:66-82) alone -- theta supplied by the caller as `extra` rows
+ * (P == 0); same kernels, no sampling / log-prob work.  x_states [T][S][N]. */
+int vh_simulate(const vh_problem* p, const vh_fwd_io* io, void* stream);
+int vh_simulate_bwd(const vh_problem* p, const vh_bwd_io* io, void* stream);
+
+/* IWAE reduction (vihds/training.py:134-148): log_w = sum_species logp + logp_theta - logq_theta;
+ * cost = -mean_b(logsumexp_i log_w - log IW).  One block per individual.  Outputs: cost[1] (zeroed by the call),
+ * log_w[N], normalized importance weights w[N] (vihds/training.py:152-153).  b_total: denominator of the mean
+ * (= B on one GPU; the global batch when individuals are sharded across ranks). */
+int vh_iwae_fwd(int dtype, int B, int IW, int b_total, const void* logp_by_species, const void* logp_theta,
+                const void* logq_theta, void* cost, void* log_w, void* w, void* stream);
+/* gradient of cost*g w.r.t. the three term arrays: d/dlog_w = -w/b_total * g[0]; g is a device scalar (or NULL = 1) */
+int vh_iwae_bwd(int dtype, int B, int IW, int b_total, const void* w, const void* g, void* g_logp_by_species,
+                void* g_logp_theta, void* g_logq_theta, void* stream);
+
+/* Evaluation path (vihds/utils.py:79-99, Results.init): importance-weighted moments of the traces, reduced over IW
+ * on the device so the [B,IW,.,T] traces never leave HBM.
+ *   iw_predict_mu [B][4][T], iw_predict_std [B][4][T], iw_states [B][S][T], iw_variance [B][4][T]
+ * prec_const: [4][N] planes of theta for constant-precision models, NULL for dynamic-precision models. */
+int vh_iw_moments(const vh_problem* p, const void* w, const void* x_states, const void* x_predict,
+                  const void* prec_const, void* iw_predict_mu, void* iw_predict_std, void* iw_states,
+                  void* iw_variance, void* stream);
+
+/* Fused Adam over a flat parameter vector (torch.optim.Adam defaults; vihds/training.py:82, :336). step is 1-based. */
+int vh_adam_step(int dtype, size_t n, void* param, const void* grad, void* exp_avg, void* exp_avg_sq, double lr,
+                 double beta1, double beta2, double eps, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIHDS_B200_H */

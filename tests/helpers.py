@@ -1,0 +1,94 @@
+"""Shared test helpers: golden case -> kernel-layout arrays, slot maps, IWAE upstream gradients (numpy)."""
+import ctypes as C
+import math
+import os
+import subprocess
+
+import numpy as np
+
+from vihds_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+MODEL_IDS = {"dr_constant": 0, "dr_constant_v2": 1, "dr_constant_precisions": 2, "dr_constant_precisions_v2": 3,
+             "relay_constant": 4, "relay_constant_precisions": 5, "dr_blackbox": 6}
+SOLVER_IDS = {"euler": 0, "midpoint": 1, "rk4": 2, "modeuler": 3, "modeulerwhile": 4}
+
+
+def clip_bounds(case, stddevs=4.0):
+    """Prior mu +- 4 sigma (exp'd for LogNormal), computed in the case dtype like the reference does."""
+    dt = case["p_mu"].dtype
+    lo = (case["p_mu"] - dt.type(stddevs) * case["p_sigma"]).astype(dt)
+    hi = (case["p_mu"] + dt.type(stddevs) * case["p_sigma"]).astype(dt)
+    ln = case["kinds"] == 2
+    lo = np.where(ln, np.exp(lo), lo).astype(dt)
+    hi = np.where(ln, np.exp(hi), hi).astype(dt)
+    const = case["kinds"] == 0
+    lo[const], hi[const] = -np.inf, np.inf
+    return lo, hi
+
+
+def slot_map(case, slot_names):
+    """slot_src for a golden case: theta column if the name is sampled, else an extra row (conditioned aR/aS)."""
+    names = [str(n) for n in case["names"]]
+    src = [L.VH_SLOT_UNUSED] * L.VH_MAX_SLOTS
+    extras = []
+    for s, name in enumerate(slot_names):
+        if name in names:
+            src[s] = names.index(name)
+        elif ("cond_" + name) in case:
+            src[s] = -1 - len(extras)
+            extras.append(case["cond_" + name].reshape(-1))
+    extra = np.stack(extras).astype(case["u"].dtype) if extras else None
+    return src, extra
+
+
+def flat_weights(case):
+    """Flat decoder weight vector in the library layout (LinPrecNet: Wp, bp, Wd, bd)."""
+    pre = "w:ode_model.precisions."
+    if (pre + "prec_production.weight") not in case or (pre + "prec_hidden.weight") in case:
+        return None, None
+    order = ["prec_production.weight", "prec_production.bias", "prec_degradation.weight", "prec_degradation.bias"]
+    w = np.concatenate([case[pre + k].reshape(-1) for k in order])
+    gw = np.concatenate([case["gw:ode_model.precisions." + k].reshape(-1) for k in order])
+    return w, gw
+
+
+def iwae_upstream(lpx, lp, lq, B, IW):
+    """Gradients of the IWAE cost (vihds/training.py:134-148) w.r.t. the three per-sample term arrays."""
+    lw = lpx.reshape(B, IW, 4).astype(np.float64).sum(2) + lp.reshape(B, IW) - lq.reshape(B, IW)
+    m = lw.max(1, keepdims=True)
+    e = np.exp(lw - m)
+    w = e / e.sum(1, keepdims=True)
+    lse = m[:, 0] + np.log(e.sum(1))
+    cost = -(lse - math.log(IW)).mean()
+    g = (-w / B).reshape(-1)
+    return cost, g
+
+
+def build_hostcheck():
+    so = os.path.join(ROOT, "tests", "hostcheck", "_hostcheck.so")
+    src = os.path.join(ROOT, "tests", "hostcheck", "vh_hostcheck.cpp")
+    deps = [src] + [os.path.join(ROOT, "vihds_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "vihds_b200", "csrc"))
+                    if f.endswith(".cuh")] + [os.path.join(ROOT, "include", "vihds_b200.h")]
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so, src])
+    lib = C.CDLL(so)
+    lib.hc_fwd.argtypes = [C.POINTER(L.vh_problem), C.POINTER(L.vh_fwd_io)]
+    lib.hc_bwd.argtypes = [C.POINTER(L.vh_problem), C.POINTER(L.vh_bwd_io)]
+    lib.hc_slot_name.argtypes = [C.c_int, C.c_int]
+    lib.hc_slot_name.restype = C.c_char_p
+    return lib
+
+
+def make_problem(case, src, E, n_weights_hidden=0):
+    p = L.vh_problem()
+    p.model = MODEL_IDS[str(case["model"])]
+    p.solver = SOLVER_IDS[str(case["solver"])]
+    p.dtype = L.VH_F64 if str(case["dtype"]) == "float64" else L.VH_F32
+    B, IW, P = case["u"].shape
+    p.B, p.IW, p.T, p.P = B, IW, len(case["times"]), P
+    p.C, p.D, p.E = case["inputs"].shape[1], case["dev_1hot"].shape[1], E
+    for s in range(L.VH_MAX_SLOTS):
+        p.slot_src[s] = src[s]
+    return p

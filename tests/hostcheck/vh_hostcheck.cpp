@@ -1,0 +1,79 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into libvihds_b200.so and never used by the product path.
+// Compiles the VH_HD trajectory maths of vihds_b200/csrc (the very same headers the CUDA kernels instantiate) for the
+// host, so that the hand-written RHS / stepper / adjoint code can be checked against the CPU oracle in the build
+// container, which has no GPU.  Pointers in the io structs are HOST pointers here.
+#include <vector>
+
+#include "../../vihds_b200/csrc/vh_dispatch.cuh"
+
+namespace {
+using namespace vh;
+
+template <typename R>
+struct HostRed {
+  const Call<R>* a;
+  void operator()(int b, int k, R dmu, R dprec, bool active) const {
+    if (!active) return;
+    a->d_q_mu[b * a->P + k] += dmu;
+    a->d_q_prec[b * a->P + k] += dprec;
+  }
+};
+
+template <typename R>
+struct FwdRunner {
+  const Call<R>* a;
+  template <class M, class TB>
+  int run() {
+    for (int n = 0; n < a->N; ++n) traj_forward<M, TB>(*a, n, a->weights);
+    return 0;
+  }
+};
+
+template <typename R>
+struct BwdRunner {
+  const Call<R>* a;
+  size_t nw;
+  template <class M, class TB>
+  int run() {
+    std::vector<R> gw(nw ? nw : 1);
+    for (size_t i = 0; i < (size_t)a->B * a->P; ++i) a->d_q_mu[i] = a->d_q_prec[i] = R(0);
+    for (size_t i = 0; i < nw; ++i) a->d_weights[i] = R(0);
+    HostRed<R> red{a};
+    for (int n = 0; n < a->N; ++n) {
+      for (size_t i = 0; i < nw; ++i) gw[i] = R(0);
+      StridedGW<R> h{gw.data(), 1};
+      traj_backward<M, TB>(*a, n, true, a->weights, h, red);
+      for (size_t i = 0; i < nw; ++i) a->d_weights[i] += gw[i];
+    }
+    return 0;
+  }
+};
+
+template <typename R>
+int fwd_t(const vh_problem* p, const vh_fwd_io* io) {
+  Call<R> a;
+  if (build_call<R>(p, io, nullptr, a)) return VH_ERR_INVALID;
+  FwdRunner<R> f{&a};
+  return dispatch_dr<R>(p->model, p->solver, f);
+}
+template <typename R>
+int bwd_t(const vh_problem* p, const vh_bwd_io* io) {
+  Call<R> a;
+  if (build_call<R>(p, &io->fwd, io, a)) return VH_ERR_INVALID;
+  size_t nw = model_is_dyn(p->model) ? (size_t)2 * (4 * (model_species(p->model) + 1) + 4) : 0;
+  BwdRunner<R> f{&a, nw};
+  return dispatch_dr<R>(p->model, p->solver, f);
+}
+}  // namespace
+
+extern "C" int hc_fwd(const vh_problem* p, const vh_fwd_io* io) {
+  return p->dtype == VH_F64 ? fwd_t<double>(p, io) : fwd_t<float>(p, io);
+}
+extern "C" int hc_bwd(const vh_problem* p, const vh_bwd_io* io) {
+  return p->dtype == VH_F64 ? bwd_t<double>(p, io) : bwd_t<float>(p, io);
+}
+extern "C" int hc_num_slots() { return vh::DR_NSLOT; }
+extern "C" const char* hc_slot_name(int model, int s) {
+  if (vh::model_is_dyn(model) && s >= vh::S_prec_x && s <= vh::S_prec_cfp) return vh::kDrDynPrecNames[s - vh::S_prec_x];
+  return vh::kDrSlotNames[s];
+}

@@ -1,0 +1,52 @@
+// Scalar helpers shared by device kernels and the host-side math check (tests/hostcheck).
+// IEEE-accurate expf/logf/powf/division only: the parity target (<= 1e-4 relative on states and the ELBO against the
+// reference's fp32 CPU path) is met in fp32 if and only if no fast-math approximations are used.
+#pragma once
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define VH_HD __host__ __device__ __forceinline__
+#else
+#define VH_HD inline
+#endif
+
+namespace vh {
+
+VH_HD float vexp(float x) { return expf(x); }
+VH_HD double vexp(double x) { return exp(x); }
+VH_HD float vlog(float x) { return logf(x); }
+VH_HD double vlog(double x) { return log(x); }
+VH_HD float vpow(float x, float y) { return powf(x, y); }
+VH_HD double vpow(double x, double y) { return pow(x, y); }
+VH_HD float vsqrt(float x) { return sqrtf(x); }
+VH_HD double vsqrt(double x) { return sqrt(x); }
+VH_HD float vtanh(float x) { return tanhf(x); }
+VH_HD double vtanh(double x) { return tanh(x); }
+
+template <typename R>
+VH_HD R sigmoid(R z) {
+  return R(1) / (R(1) + vexp(-z));
+}
+
+// torch.clamp semantics: NaN propagates (both comparisons false); gradient passes on the CLOSED interval.
+template <typename R>
+VH_HD R clampv(R x, R lo, R hi) {
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+template <typename R>
+VH_HD R clampmask(R x, R lo, R hi) {
+  return (x >= lo && x <= hi) ? R(1) : R(0);
+}
+
+template <typename R>
+struct Lim;
+template <>
+struct Lim<float> {
+  static constexpr float log2pi = 1.8378770664093453f;
+};
+template <>
+struct Lim<double> {
+  static constexpr double log2pi = 1.8378770664093453;
+};
+
+}  // namespace vh

@@ -1,0 +1,441 @@
+// Model right-hand sides and their hand-written reverse-mode (VJP) counterparts, one trajectory per call.
+//
+// White-box "double receiver" family (dr_constant v1/v2, relay_constant, +- NeuralPrecisions states):
+//   forward maths   <- models/dr_constant.py:14-112, models/relay_constant.py:13-134 (reference, read-only)
+//   initial state   <- models/dr_constant.py:133-150, :178-199; models/relay_constant.py:150-178, :220-250
+//   observe         <- vihds/ode.py:84-93
+//   NeuralPrecisions<- vihds/precisions.py:44-94
+// Everything is VH_HD so that the identical code is compiled for the device kernels and for the host-side math check
+// (tests/hostcheck), which compares it with the CPU oracle without needing a GPU.
+#pragma once
+#include "vh_math.cuh"
+
+namespace vh {
+
+// ---------------------------------------------------------------------------------------------------------------
+// theta slots of the double-receiver family (names as the RHS reads them off `theta`)
+// ---------------------------------------------------------------------------------------------------------------
+enum DrSlot : int {
+  S_r = 0, S_K, S_tlag, S_rc, S_a530, S_a480, S_drfp, S_dyfp, S_dcfp, S_dR, S_dS,
+  S_e76, S_e81, S_aCFP, S_aYFP, S_KGR_76, S_KGS_76, S_KGR_81, S_KGS_81, S_aR, S_aS, S_nR, S_nS,
+  S_KR6, S_KR12, S_KS6, S_KS12,  // version 1
+  S_eS6, S_eR12,                 // version 2
+  S_init_x, S_init_rfp, S_init_yfp, S_init_cfp, S_init_luxR, S_init_lasR,
+  S_prec_x, S_prec_rfp, S_prec_yfp, S_prec_cfp,  // constant precisions: prec_*; dynamic: init_prec_*
+  S_dlasI, S_dluxI, S_KC6, S_KC12, S_Klux, S_Klas, S_init_luxI, S_init_lasI,  // relay
+  DR_NSLOT
+};
+
+static const char* const kDrSlotNames[DR_NSLOT] = {
+    "r", "K", "tlag", "rc", "a530", "a480", "drfp", "dyfp", "dcfp", "dR", "dS",
+    "e76", "e81", "aCFP", "aYFP", "KGR_76", "KGS_76", "KGR_81", "KGS_81", "aR", "aS", "nR", "nS",
+    "KR6", "KR12", "KS6", "KS12", "eS6", "eR12",
+    "init_x", "init_rfp", "init_yfp", "init_cfp", "init_luxR", "init_lasR",
+    "prec_x", "prec_rfp", "prec_yfp", "prec_cfp",
+    "dlasI", "dluxI", "KC6", "KC12", "Klux", "Klas", "init_luxI", "init_lasI"};
+static const char* const kDrDynPrecNames[4] = {"init_prec_x", "init_prec_rfp", "init_prec_yfp", "init_prec_cfp"};
+
+// per-trajectory constants of the RHS (clamped parameters, Hill fractions, pre-multiplied production rates)
+enum DrConst : int {
+  C_r = 0, C_K, C_tlag, C_rc, C_drfp, C_dyfp, C_dcfp, C_dR, C_dS,
+  C_e76, C_e81, C_KGR76, C_KGS76, C_KGR81, C_KGS81, C_fR, C_fS,
+  C_cY,  // rc * aYFP
+  C_cC,  // rc * aCFP
+  C_p4,  // rc * a530
+  C_p5,  // rc * a480
+  C_p6,  // rc * aR
+  C_p7,  // rc * aS
+  C_dluxI, C_dlasI, C_k6, /* KC6*rc */ C_k12, /* KC12*rc */ C_Klux, C_Klas,
+  DR_NCONST
+};
+
+template <typename R, int VERSION_, bool RELAY_, bool DYN_>
+struct DrModel {
+  typedef R real;
+  static constexpr int VERSION = VERSION_;
+  static constexpr bool RELAY = RELAY_;
+  static constexpr bool DYN = DYN_;
+  static constexpr bool BLACKBOX = false;
+  static constexpr int NSLOT = DR_NSLOT;
+  static constexpr int NS = RELAY ? 12 : 8;      // species (OdeModel.n_species)
+  static constexpr int S = NS + (DYN ? 4 : 0);   // ODE state width
+  static constexpr int NC = RELAY ? DR_NCONST : C_dluxI;
+  static constexpr int NIN = NS + 1;             // NeuralPrecisions inputs: [t, species]
+
+  struct Consts {
+    R v[NC];
+  };
+
+  VH_HD static constexpr bool uses(int s) {
+    return (s <= S_nS) || (VERSION == 1 && s >= S_KR6 && s <= S_KS12) || (VERSION == 2 && (s == S_eS6 || s == S_eR12)) ||
+           (s >= S_init_x && s <= S_prec_cfp) || (RELAY && s >= S_dlasI);
+  }
+
+  // treatments -> inducer concentrations, models/dr_constant.py:26
+  VH_HD static void treatments(const R* tr, R& c6, R& c12) {
+    c6 = clampv(vexp(tr[0]) - R(1), R(1e-12), R(1e6));
+    c12 = clampv(vexp(tr[1]) - R(1), R(1e-12), R(1e6));
+  }
+
+  VH_HD static void hill(R Ka, R Kb, R n, R c6, R c12, R& f) {  // version 1 fraction
+    const R A = Ka * c6, Bq = Kb * c12;
+    const R D = R(1) + A + Bq;
+    f = (vpow(A, n) + vpow(Bq, n)) / vpow(D, n);
+  }
+
+  VH_HD static void setup(const R* th, R c6, R c12, Consts& c) {
+    R* v = c.v;
+    v[C_r] = clampv(th[S_r], R(0), R(4));
+    v[C_K] = clampv(th[S_K], R(0), R(4));
+    v[C_tlag] = th[S_tlag];
+    v[C_rc] = th[S_rc];
+    v[C_drfp] = clampv(th[S_drfp], R(1e-12), R(2));
+    v[C_dyfp] = clampv(th[S_dyfp], R(1e-12), R(2));
+    v[C_dcfp] = clampv(th[S_dcfp], R(1e-12), R(2));
+    v[C_dR] = clampv(th[S_dR], R(1e-12), R(5));
+    v[C_dS] = clampv(th[S_dS], R(1e-12), R(5));
+    v[C_e76] = th[S_e76];
+    v[C_e81] = th[S_e81];
+    v[C_KGR76] = th[S_KGR_76];
+    v[C_KGS76] = th[S_KGS_76];
+    v[C_KGR81] = th[S_KGR_81];
+    v[C_KGS81] = th[S_KGS_81];
+    const R nR = clampv(th[S_nR], R(0.5), R(3)), nS = clampv(th[S_nS], R(0.5), R(3));
+    if (VERSION == 1) {
+      const R lb = R(1e-12), ub = R(1);
+      hill(clampv(th[S_KR6], lb, ub), clampv(th[S_KR12], lb, ub), nR, c6, c12, v[C_fR]);
+      hill(clampv(th[S_KS6], lb, ub), clampv(th[S_KS12], lb, ub), nS, c6, c12, v[C_fS]);
+    } else {
+      const R eS6 = clampv(th[S_eS6], R(1e-12), R(1)), eR12 = clampv(th[S_eR12], R(1e-12), R(1));
+      v[C_fR] = vpow(c6, nR) + vpow(eR12 * c12, nR);
+      v[C_fS] = vpow(eS6 * c6, nS) + vpow(c12, nS);
+    }
+    v[C_cY] = th[S_rc] * th[S_aYFP];
+    v[C_cC] = th[S_rc] * th[S_aCFP];
+    v[C_p4] = th[S_rc] * th[S_a530];
+    v[C_p5] = th[S_rc] * th[S_a480];
+    v[C_p6] = th[S_rc] * th[S_aR];
+    v[C_p7] = th[S_rc] * th[S_aS];
+    if (RELAY) {
+      v[C_dluxI] = clampv(th[S_dluxI], R(1e-12), R(5));
+      v[C_dlasI] = clampv(th[S_dlasI], R(1e-12), R(5));
+      v[C_k6] = th[S_KC6] * th[S_rc];
+      v[C_k12] = th[S_KC12] * th[S_rc];
+      v[C_Klux] = th[S_Klux];
+      v[C_Klas] = th[S_Klas];
+    }
+  }
+
+  // d f / d (Ka, Kb, n) for the version-1 Hill fraction, following torch's pow backward
+  VH_HD static void hill_vjp(R Ka, R Kb, R n, R c6, R c12, R f, R gf, R& gKa, R& gKb, R& gn) {
+    const R A = Ka * c6, Bq = Kb * c12;
+    const R D = R(1) + A + Bq;
+    const R An = vpow(A, n), Bn = vpow(Bq, n), Dn = vpow(D, n);
+    const R gnum = gf / Dn;
+    const R gDn = -gnum * f;
+    const R gD = gDn * n * vpow(D, n - R(1));
+    const R gA = gnum * n * vpow(A, n - R(1)) + gD;
+    const R gB = gnum * n * vpow(Bq, n - R(1)) + gD;
+    gn = gnum * (An * vlog(A) + Bn * vlog(Bq)) + gDn * Dn * vlog(D);
+    gKa = gA * c6;
+    gKb = gB * c12;
+  }
+
+  // gc: cotangent of the constants  ->  gth: cotangent of the theta slots (accumulated)
+  VH_HD static void setup_vjp(const R* th, R c6, R c12, const Consts& c, const Consts& gc, R* gth) {
+    const R* g = gc.v;
+    gth[S_r] += g[C_r] * clampmask(th[S_r], R(0), R(4));
+    gth[S_K] += g[C_K] * clampmask(th[S_K], R(0), R(4));
+    gth[S_tlag] += g[C_tlag];
+    gth[S_drfp] += g[C_drfp] * clampmask(th[S_drfp], R(1e-12), R(2));
+    gth[S_dyfp] += g[C_dyfp] * clampmask(th[S_dyfp], R(1e-12), R(2));
+    gth[S_dcfp] += g[C_dcfp] * clampmask(th[S_dcfp], R(1e-12), R(2));
+    gth[S_dR] += g[C_dR] * clampmask(th[S_dR], R(1e-12), R(5));
+    gth[S_dS] += g[C_dS] * clampmask(th[S_dS], R(1e-12), R(5));
+    gth[S_e76] += g[C_e76];
+    gth[S_e81] += g[C_e81];
+    gth[S_KGR_76] += g[C_KGR76];
+    gth[S_KGS_76] += g[C_KGS76];
+    gth[S_KGR_81] += g[C_KGR81];
+    gth[S_KGS_81] += g[C_KGS81];
+    const R rc = th[S_rc];
+    R grc = g[C_rc] + g[C_cY] * th[S_aYFP] + g[C_cC] * th[S_aCFP] + g[C_p4] * th[S_a530] + g[C_p5] * th[S_a480] +
+            g[C_p6] * th[S_aR] + g[C_p7] * th[S_aS];
+    gth[S_aYFP] += g[C_cY] * rc;
+    gth[S_aCFP] += g[C_cC] * rc;
+    gth[S_a530] += g[C_p4] * rc;
+    gth[S_a480] += g[C_p5] * rc;
+    gth[S_aR] += g[C_p6] * rc;
+    gth[S_aS] += g[C_p7] * rc;
+    const R nR = clampv(th[S_nR], R(0.5), R(3)), nS = clampv(th[S_nS], R(0.5), R(3));
+    R gnR, gnS;
+    if (VERSION == 1) {
+      const R lb = R(1e-12), ub = R(1);
+      R ga, gb;
+      hill_vjp(clampv(th[S_KR6], lb, ub), clampv(th[S_KR12], lb, ub), nR, c6, c12, c.v[C_fR], g[C_fR], ga, gb, gnR);
+      gth[S_KR6] += ga * clampmask(th[S_KR6], lb, ub);
+      gth[S_KR12] += gb * clampmask(th[S_KR12], lb, ub);
+      hill_vjp(clampv(th[S_KS6], lb, ub), clampv(th[S_KS12], lb, ub), nS, c6, c12, c.v[C_fS], g[C_fS], ga, gb, gnS);
+      gth[S_KS6] += ga * clampmask(th[S_KS6], lb, ub);
+      gth[S_KS12] += gb * clampmask(th[S_KS12], lb, ub);
+    } else {
+      const R eS6 = clampv(th[S_eS6], R(1e-12), R(1)), eR12 = clampv(th[S_eR12], R(1e-12), R(1));
+      const R E = eR12 * c12, F = eS6 * c6;
+      gnR = g[C_fR] * (vpow(c6, nR) * vlog(c6) + vpow(E, nR) * vlog(E));
+      gnS = g[C_fS] * (vpow(F, nS) * vlog(F) + vpow(c12, nS) * vlog(c12));
+      gth[S_eR12] += g[C_fR] * nR * vpow(E, nR - R(1)) * c12 * clampmask(th[S_eR12], R(1e-12), R(1));
+      gth[S_eS6] += g[C_fS] * nS * vpow(F, nS - R(1)) * c6 * clampmask(th[S_eS6], R(1e-12), R(1));
+    }
+    gth[S_nR] += gnR * clampmask(th[S_nR], R(0.5), R(3));
+    gth[S_nS] += gnS * clampmask(th[S_nS], R(0.5), R(3));
+    if (RELAY) {
+      gth[S_dluxI] += g[C_dluxI] * clampmask(th[S_dluxI], R(1e-12), R(5));
+      gth[S_dlasI] += g[C_dlasI] * clampmask(th[S_dlasI], R(1e-12), R(5));
+      gth[S_KC6] += g[C_k6] * rc;
+      gth[S_KC12] += g[C_k12] * rc;
+      grc += g[C_k6] * th[S_KC6] + g[C_k12] * th[S_KC12];
+      gth[S_Klux] += g[C_Klux];
+      gth[S_Klas] += g[C_Klas];
+    }
+    gth[S_rc] += grc;
+  }
+
+  VH_HD static void init_state(const R* th, R c6, R c12, R* x) {
+    x[0] = th[S_init_x];
+    x[1] = th[S_init_rfp];
+    x[2] = th[S_init_yfp];
+    x[3] = th[S_init_cfp];
+    x[4] = R(0);
+    x[5] = R(0);
+    x[6] = th[S_init_luxR];
+    x[7] = th[S_init_lasR];
+    if (RELAY) {
+      x[8] = th[S_init_luxI];
+      x[9] = th[S_init_lasI];
+      x[10] = c6;
+      x[11] = c12;
+    }
+    if (DYN) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) x[NS + o] = th[S_prec_x + o];
+    }
+  }
+
+  VH_HD static void init_state_vjp(const R* gx, R* gth) {
+    gth[S_init_x] += gx[0];
+    gth[S_init_rfp] += gx[1];
+    gth[S_init_yfp] += gx[2];
+    gth[S_init_cfp] += gx[3];
+    gth[S_init_luxR] += gx[6];
+    gth[S_init_lasR] += gx[7];
+    if (RELAY) {
+      gth[S_init_luxI] += gx[8];
+      gth[S_init_lasI] += gx[9];
+    }
+    if (DYN) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gx[NS + o];
+    }
+  }
+
+  // intermediates shared by rhs and rhs_vjp
+  struct Mid {
+    R sg, gr, g, gam, bR, bS, d76, d81, P76, P81;
+  };
+
+  VH_HD static void mid(R t, const R* x, const R* v, Mid& m) {
+    m.sg = sigmoid(R(4) * (t - v[C_tlag]));
+    m.gr = v[C_r] * m.sg;
+    m.g = R(1) - x[0] / v[C_K];
+    m.gam = m.gr * m.g;
+    m.bR = x[6] * x[6] * v[C_fR];
+    m.bS = x[7] * x[7] * v[C_fS];
+    const R a76 = v[C_KGR76] * m.bR, b76 = v[C_KGS76] * m.bS;
+    const R a81 = v[C_KGR81] * m.bR, b81 = v[C_KGS81] * m.bS;
+    m.d76 = R(1) + a76 + b76;
+    m.d81 = R(1) + a81 + b81;
+    m.P76 = (v[C_e76] + a76 + b76) / m.d76;
+    m.P81 = (v[C_e81] + a81 + b81) / m.d81;
+  }
+
+  // species part of the right-hand side (dx[0..NS))
+  VH_HD static void rhs(R t, const R* x, const Consts& c, R* dx) {
+    const R* v = c.v;
+    Mid m;
+    mid(t, x, v, m);
+    dx[0] = m.gam * x[0];
+    dx[1] = v[C_rc] - (m.gam + v[C_drfp]) * x[1];
+    dx[2] = v[C_cY] * m.P81 - (m.gam + v[C_dyfp]) * x[2];
+    dx[3] = v[C_cC] * m.P76 - (m.gam + v[C_dcfp]) * x[3];
+    dx[4] = v[C_p4] - m.gam * x[4];
+    dx[5] = v[C_p5] - m.gam * x[5];
+    dx[6] = v[C_p6] - (m.gam + v[C_dR]) * x[6];
+    dx[7] = v[C_p7] - (m.gam + v[C_dS]) * x[7];
+    if (RELAY) {
+      dx[8] = v[C_rc] * m.P81 - (m.gam + v[C_dluxI]) * x[8];
+      dx[9] = v[C_rc] * m.P76 - (m.gam + v[C_dlasI]) * x[9];
+      dx[10] = (v[C_k6] * x[0] * x[8]) / (R(1) + x[8] / v[C_Klux]);
+      dx[11] = (v[C_k12] * x[0] * x[9]) / (R(1) + x[9] / v[C_Klas]);
+    }
+  }
+
+  // g: cotangent of dx[0..NS)  ->  gx (accumulated), gc (accumulated)
+  VH_HD static void rhs_vjp(R t, const R* x, const Consts& c, const R* g, R* gx, Consts& gcs) {
+    const R* v = c.v;
+    R* gc = gcs.v;
+    Mid m;
+    mid(t, x, v, m);
+    R ggam = g[0] * x[0] - g[1] * x[1] - g[2] * x[2] - g[3] * x[3] - g[4] * x[4] - g[5] * x[5] - g[6] * x[6] - g[7] * x[7];
+    gx[0] += g[0] * m.gam;
+    gx[1] -= g[1] * (m.gam + v[C_drfp]);
+    gx[2] -= g[2] * (m.gam + v[C_dyfp]);
+    gx[3] -= g[3] * (m.gam + v[C_dcfp]);
+    gx[4] -= g[4] * m.gam;
+    gx[5] -= g[5] * m.gam;
+    gx[6] -= g[6] * (m.gam + v[C_dR]);
+    gx[7] -= g[7] * (m.gam + v[C_dS]);
+    gc[C_drfp] -= g[1] * x[1];
+    gc[C_dyfp] -= g[2] * x[2];
+    gc[C_dcfp] -= g[3] * x[3];
+    gc[C_dR] -= g[6] * x[6];
+    gc[C_dS] -= g[7] * x[7];
+    gc[C_rc] += g[1];
+    gc[C_cY] += g[2] * m.P81;
+    gc[C_cC] += g[3] * m.P76;
+    gc[C_p4] += g[4];
+    gc[C_p5] += g[5];
+    gc[C_p6] += g[6];
+    gc[C_p7] += g[7];
+    R gP81 = g[2] * v[C_cY];
+    R gP76 = g[3] * v[C_cC];
+    if (RELAY) {
+      ggam -= g[8] * x[8] + g[9] * x[9];
+      gx[8] -= g[8] * (m.gam + v[C_dluxI]);
+      gx[9] -= g[9] * (m.gam + v[C_dlasI]);
+      gc[C_dluxI] -= g[8] * x[8];
+      gc[C_dlasI] -= g[9] * x[9];
+      gc[C_rc] += g[8] * m.P81 + g[9] * m.P76;
+      gP81 += g[8] * v[C_rc];
+      gP76 += g[9] * v[C_rc];
+      {
+        const R den = R(1) + x[8] / v[C_Klux];
+        const R gnum = g[10] / den;
+        const R val = (v[C_k6] * x[0] * x[8]) / den;
+        const R gden = -gnum * val;
+        gc[C_k6] += gnum * x[0] * x[8];
+        gx[0] += gnum * v[C_k6] * x[8];
+        gx[8] += gnum * v[C_k6] * x[0] + gden / v[C_Klux];
+        gc[C_Klux] -= gden * x[8] / (v[C_Klux] * v[C_Klux]);
+      }
+      {
+        const R den = R(1) + x[9] / v[C_Klas];
+        const R gnum = g[11] / den;
+        const R val = (v[C_k12] * x[0] * x[9]) / den;
+        const R gden = -gnum * val;
+        gc[C_k12] += gnum * x[0] * x[9];
+        gx[0] += gnum * v[C_k12] * x[9];
+        gx[9] += gnum * v[C_k12] * x[0] + gden / v[C_Klas];
+        gc[C_Klas] -= gden * x[9] / (v[C_Klas] * v[C_Klas]);
+      }
+    }
+    // gamma = gr * g,  gr = r * sg,  g = 1 - x0 / K
+    const R ggr = ggam * m.g, gg = ggam * m.gr;
+    gc[C_r] += ggr * m.sg;
+    gc[C_tlag] -= R(4) * ggr * v[C_r] * m.sg * (R(1) - m.sg);
+    gx[0] -= gg / v[C_K];
+    gc[C_K] += gg * x[0] / (v[C_K] * v[C_K]);
+    // promoter activities P = (e + a + b) / (1 + a + b)
+    const R gn76 = gP76 / m.d76, gn81 = gP81 / m.d81;
+    gc[C_e76] += gn76;
+    gc[C_e81] += gn81;
+    const R ga76 = gn76 * (R(1) - m.P76), ga81 = gn81 * (R(1) - m.P81);
+    gc[C_KGR76] += ga76 * m.bR;
+    gc[C_KGS76] += ga76 * m.bS;
+    gc[C_KGR81] += ga81 * m.bR;
+    gc[C_KGS81] += ga81 * m.bS;
+    const R gbR = ga76 * v[C_KGR76] + ga81 * v[C_KGR81];
+    const R gbS = ga76 * v[C_KGS76] + ga81 * v[C_KGS81];
+    gx[6] += gbR * R(2) * x[6] * v[C_fR];
+    gx[7] += gbS * R(2) * x[7] * v[C_fS];
+    gc[C_fR] += gbR * x[6] * x[6];
+    gc[C_fS] += gbS * x[7] * x[7];
+  }
+
+  // observe, vihds/ode.py:84-93
+  VH_HD static void observe(const R* x, R* xp) {
+    xp[0] = x[0];
+    xp[1] = x[0] * x[1];
+    xp[2] = x[0] * (x[2] + x[4]);
+    xp[3] = x[0] * (x[3] + x[5]);
+  }
+  VH_HD static void observe_vjp(const R* x, const R* gxp, R* gx) {
+    gx[0] += gxp[0] + gxp[1] * x[1] + gxp[2] * (x[2] + x[4]) + gxp[3] * (x[3] + x[5]);
+    gx[1] += gxp[1] * x[0];
+    gx[2] += gxp[2] * x[0];
+    gx[4] += gxp[2] * x[0];
+    gx[3] += gxp[3] * x[0];
+    gx[5] += gxp[3] * x[0];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// NeuralPrecisions with no hidden layer (n_hidden_decoder_precisions: 0; vihds/precisions.py:55-61, :76-87):
+//   a = tanh([t, species]);  prod = sigmoid(Wp a + bp);  degr = sigmoid(Wd a + bd);  dv = prod - degr * v
+// flat weight layout: Wp[4][NIN], bp[4], Wd[4][NIN], bd[4]
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R, int NIN>
+struct LinPrecNet {
+  static constexpr int NW = 2 * (4 * NIN + 4);
+  // species = xin[1..NIN), v = current precision states
+  VH_HD static void rhs(R t, const R* species, const R* v, const R* w, R* dv) {
+    R a[NIN];
+    a[0] = vtanh(t);
+#pragma unroll
+    for (int j = 1; j < NIN; ++j) a[j] = vtanh(species[j - 1]);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      R zp = w[4 * NIN + o], zd = w[(4 * NIN + 4) + 4 * NIN + o];
+#pragma unroll
+      for (int j = 0; j < NIN; ++j) {
+        zp += w[o * NIN + j] * a[j];
+        zd += w[(4 * NIN + 4) + o * NIN + j] * a[j];
+      }
+      dv[o] = sigmoid(zp) - sigmoid(zd) * v[o];
+    }
+  }
+  // gw: this thread's weight-gradient accumulators, element k at gw[k * gstride]
+  template <typename GW>
+  VH_HD static void rhs_vjp(R t, const R* species, const R* v, const R* w, const R* g, R* gspecies, R* gv, GW gw) {
+    R a[NIN], ga[NIN];
+    a[0] = vtanh(t);
+#pragma unroll
+    for (int j = 1; j < NIN; ++j) a[j] = vtanh(species[j - 1]);
+#pragma unroll
+    for (int j = 0; j < NIN; ++j) ga[j] = R(0);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      R zp = w[4 * NIN + o], zd = w[(4 * NIN + 4) + 4 * NIN + o];
+#pragma unroll
+      for (int j = 0; j < NIN; ++j) {
+        zp += w[o * NIN + j] * a[j];
+        zd += w[(4 * NIN + 4) + o * NIN + j] * a[j];
+      }
+      const R sp = sigmoid(zp), sd = sigmoid(zd);
+      gv[o] -= g[o] * sd;
+      const R gzp = g[o] * sp * (R(1) - sp);
+      const R gzd = -g[o] * v[o] * sd * (R(1) - sd);
+      gw.add(4 * NIN + o, gzp);
+      gw.add((4 * NIN + 4) + 4 * NIN + o, gzd);
+#pragma unroll
+      for (int j = 0; j < NIN; ++j) {
+        gw.add(o * NIN + j, gzp * a[j]);
+        gw.add((4 * NIN + 4) + o * NIN + j, gzd * a[j]);
+        ga[j] += gzp * w[o * NIN + j] + gzd * w[(4 * NIN + 4) + o * NIN + j];
+      }
+    }
+#pragma unroll
+    for (int j = 1; j < NIN; ++j) gspecies[j - 1] += ga[j] * (R(1) - a[j] * a[j]);
+  }
+};
+
+}  // namespace vh

@@ -1,0 +1,446 @@
+// One trajectory (individual b, importance sample i) of the hot path, forward and reverse.
+//
+//   forward : sample+clip theta (vihds/distributions.py:119-142, :76-85), log q / log p (:64-74, :338-345, :373-375),
+//             RHS constants, fixed-step solve (vihds/solvers.py:9-41; torchdiffeq 0.1 fixed-grid schemes called at
+//             vihds/ode.py:80-81), observe (vihds/ode.py:84-93), Gaussian log-likelihood summed over time
+//             (vihds/training.py:24-44).
+//   reverse : discrete adjoint of exactly that computation (what autograd's replay yields, vihds/training.py:334),
+//             re-reading the state trace the forward pass wrote.
+//
+// VH_HD throughout: the device kernels (vh_kernels.cu) call these with n = blockIdx.x*blockDim.x+threadIdx.x; the
+// host-side math check (tests/hostcheck) loops over n on the CPU.
+#pragma once
+#include "../../include/vihds_b200.h"
+#include "vh_math.cuh"
+#include "vh_models.cuh"
+
+namespace vh {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Butcher tableaux of the supported fixed-step schemes
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R>
+struct TabEuler {
+  static constexpr int s = 1;
+  static constexpr bool const_h = false, end_is_t1 = false;
+  VH_HD static constexpr R a(int, int) { return R(0); }
+  VH_HD static constexpr R b(int) { return R(1); }
+  VH_HD static constexpr R c(int) { return R(0); }
+};
+template <typename R>
+struct TabMidpoint {
+  static constexpr int s = 2;
+  static constexpr bool const_h = false, end_is_t1 = false;
+  VH_HD static constexpr R a(int i, int j) { return (i == 1 && j == 0) ? R(0.5) : R(0); }
+  VH_HD static constexpr R b(int i) { return i == 1 ? R(1) : R(0); }
+  VH_HD static constexpr R c(int i) { return i == 1 ? R(0.5) : R(0); }
+};
+template <typename R>
+struct TabRK4_38 {  // torchdiffeq 0.1 "rk4" (rk4_alt_step_func): the 3/8 rule
+  static constexpr int s = 4;
+  static constexpr bool const_h = false, end_is_t1 = false;
+  VH_HD static constexpr R a(int i, int j) {
+    return i == 1 ? (j == 0 ? R(1) / R(3) : R(0))
+                  : i == 2 ? (j == 0 ? R(-1) / R(3) : (j == 1 ? R(1) : R(0)))
+                           : i == 3 ? (j == 0 ? R(1) : (j == 1 ? R(-1) : (j == 2 ? R(1) : R(0)))) : R(0);
+  }
+  VH_HD static constexpr R b(int i) { return (i == 0 || i == 3) ? R(0.125) : R(0.375); }
+  VH_HD static constexpr R c(int i) { return i == 1 ? R(1) / R(3) : (i == 2 ? R(2) / R(3) : (i == 3 ? R(1) : R(0))); }
+};
+template <typename R, bool CONST_H>
+struct TabHeun {  // vihds/solvers.py: modeuler (CONST_H: h = times[1]-times[0] for every step) / modeulerwhile
+  static constexpr int s = 2;
+  static constexpr bool const_h = CONST_H, end_is_t1 = true;
+  VH_HD static constexpr R a(int i, int j) { return (i == 1 && j == 0) ? R(1) : R(0); }
+  VH_HD static constexpr R b(int) { return R(0.5); }
+  VH_HD static constexpr R c(int i) { return i == 1 ? R(1) : R(0); }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// typed view of one call (device pointers; built by the launcher from vh_problem + vh_fwd_io / vh_bwd_io)
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R>
+struct Call {
+  int B, IW, N, T, P, C, D, E;
+  int slot_src[VH_MAX_SLOTS];
+  int n_free;                    // theta columns no model slot reads (they still carry log-prob terms)
+  int free_cols[VH_MAX_SLOTS];
+  const R *times, *u, *q_mu, *q_prec, *p_mu, *p_prec, *clip_lo, *clip_hi, *extra, *treatments, *dev_1hot, *obs, *weights;
+  const int* kind;
+  R *theta, *x_states, *x_predict, *logp_species, *logp_theta, *logq_theta;
+  // reverse only
+  const R *g_logp_species, *g_logp_theta, *g_logq_theta, *g_theta, *g_x_states, *g_x_predict;
+  R *d_q_mu, *d_q_prec, *d_extra, *d_weights;
+};
+
+// weight-gradient accumulator handles -------------------------------------------------------------------------
+template <typename R>
+struct NoGW {
+  VH_HD void add(int, R) const {}
+};
+template <typename R>
+struct StridedGW {  // element k of this thread's accumulators lives at base[k * stride]
+  R* base;
+  int stride;
+  VH_HD void add(int k, R v) const { base[k * stride] += v; }
+};
+
+// full right-hand side over the ODE state (species + dynamic-precision states) ---------------------------------
+template <class M>
+struct Rhs {
+  typedef typename M::real R;
+  typename M::Consts c;
+  const R* w;  // NeuralPrecisions weights (shared memory on the device), unused for constant precisions
+
+  VH_HD void eval(R t, const R* x, R* dx) const {
+    M::rhs(t, x, c, dx);
+    if (M::DYN) LinPrecNet<R, M::NIN>::rhs(t, x, x + M::NS, w, dx + M::NS);
+  }
+  template <typename GW>
+  VH_HD void vjp(R t, const R* x, const R* g, R* gx, typename M::Consts& gc, GW gw) const {
+    M::rhs_vjp(t, x, c, g, gx, gc);
+    if (M::DYN) LinPrecNet<R, M::NIN>::rhs_vjp(t, x, x + M::NS, w, g + M::NS, gx, gx + M::NS, gw);
+  }
+};
+
+template <class TB, typename R>
+VH_HD R stage_time(int i, R t0, R t1) {
+  if (TB::c(i) == R(0)) return t0;
+  if (TB::end_is_t1 && TB::c(i) == R(1)) return t1;
+  return t0 + (t1 - t0) * TB::c(i);
+}
+
+// x <- one step of the scheme from t0 to t1 with step size h
+template <class M, class TB>
+VH_HD void rk_step(const Rhs<M>& f, typename M::real t0, typename M::real t1, typename M::real h, typename M::real* x) {
+  typedef typename M::real R;
+  constexpr int S = M::S;
+  R k[TB::s][S];
+#pragma unroll
+  for (int i = 0; i < TB::s; ++i) {
+    R X[S];
+#pragma unroll
+    for (int q = 0; q < S; ++q) X[q] = x[q];
+#pragma unroll
+    for (int j = 0; j < i; ++j)
+      if (TB::a(i, j) != R(0)) {
+        const R ha = h * TB::a(i, j);
+#pragma unroll
+        for (int q = 0; q < S; ++q) X[q] += ha * k[j][q];
+      }
+    f.eval(stage_time<TB, R>(i, t0, t1), X, k[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < TB::s; ++i)
+    if (TB::b(i) != R(0)) {
+      const R hb = h * TB::b(i);
+#pragma unroll
+      for (int q = 0; q < S; ++q) x[q] += hb * k[i][q];
+    }
+}
+
+// lam: in = dL/dx(t1), out = dL/dx(t0);  x = state at t0;  gc/gw accumulate parameter cotangents
+template <class M, class TB, typename GW>
+VH_HD void rk_step_vjp(const Rhs<M>& f, typename M::real t0, typename M::real t1, typename M::real h,
+                       const typename M::real* x, typename M::real* lam, typename M::Consts& gc, GW gw) {
+  typedef typename M::real R;
+  constexpr int S = M::S;
+  constexpr int s = TB::s;
+  R k[s > 1 ? s - 1 : 1][S];  // the last stage derivative is never needed to rebuild a stage state
+#pragma unroll
+  for (int i = 0; i + 1 < s; ++i) {
+    R X[S];
+#pragma unroll
+    for (int q = 0; q < S; ++q) X[q] = x[q];
+#pragma unroll
+    for (int j = 0; j < i; ++j)
+      if (TB::a(i, j) != R(0)) {
+        const R ha = h * TB::a(i, j);
+#pragma unroll
+        for (int q = 0; q < S; ++q) X[q] += ha * k[j][q];
+      }
+    f.eval(stage_time<TB, R>(i, t0, t1), X, k[i]);
+  }
+  R gk[s][S];
+#pragma unroll
+  for (int i = 0; i < s; ++i)
+#pragma unroll
+    for (int q = 0; q < S; ++q) gk[i][q] = (h * TB::b(i)) * lam[q];
+#pragma unroll
+  for (int i = s - 1; i >= 0; --i) {
+    R X[S], gX[S];
+#pragma unroll
+    for (int q = 0; q < S; ++q) {
+      X[q] = x[q];
+      gX[q] = R(0);
+    }
+#pragma unroll
+    for (int j = 0; j < i; ++j)
+      if (TB::a(i, j) != R(0)) {
+        const R ha = h * TB::a(i, j);
+#pragma unroll
+        for (int q = 0; q < S; ++q) X[q] += ha * k[j][q];
+      }
+    f.vjp(stage_time<TB, R>(i, t0, t1), X, gk[i], gX, gc, gw);
+#pragma unroll
+    for (int q = 0; q < S; ++q) lam[q] += gX[q];
+#pragma unroll
+    for (int j = 0; j < i; ++j)
+      if (TB::a(i, j) != R(0)) {
+        const R ha = h * TB::a(i, j);
+#pragma unroll
+        for (int q = 0; q < S; ++q) gk[j][q] += ha * gX[q];
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// theta: sample, clip, log-probabilities
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R>
+VH_HD R sample_column(const Call<R>& a, int n, int b, int k, R& lq, R& lp) {
+  const int kind = a.kind[k];
+  const R mu = a.q_mu[b * a.P + k];
+  R th;
+  if (kind == VH_KIND_CONSTANT) {
+    th = mu;  // TfConstant.sample: 0*u + value; log_prob 0 (vihds/distributions.py:242-246)
+  } else {
+    const R prec = a.q_prec[b * a.P + k];
+    const R sigma = R(1) / vsqrt(prec);
+    const R sv = mu + sigma * a.u[(size_t)n * a.P + k];
+    const R raw = kind == VH_KIND_LOGNORMAL ? vexp(sv) : sv;
+    th = clampv(raw, a.clip_lo[k], a.clip_hi[k]);
+    const R x = kind == VH_KIND_LOGNORMAL ? vlog(th + R(1e-12)) : th;
+    const R jac = kind == VH_KIND_LOGNORMAL ? x : R(0);
+    const R pm = a.p_mu[k], pp = a.p_prec[k];
+    lq += -Lim<R>::log2pi + R(0.5) * vlog(prec + R(1e-12)) - R(0.5) * prec * (mu - x) * (mu - x) - jac;
+    lp += -Lim<R>::log2pi + R(0.5) * vlog(pp + R(1e-12)) - R(0.5) * pp * (pm - x) * (pm - x) - jac;
+  }
+  if (a.theta) a.theta[(size_t)k * a.N + n] = th;
+  return th;
+}
+
+template <class M>
+VH_HD void load_theta(const Call<typename M::real>& a, int n, int b, typename M::real* th, typename M::real& lq,
+                      typename M::real& lp) {
+  typedef typename M::real R;
+#pragma unroll
+  for (int s = 0; s < M::NSLOT; ++s) {
+    th[s] = R(0);
+    if (!M::uses(s)) continue;
+    const int src = a.slot_src[s];
+    if (src >= 0)
+      th[s] = sample_column(a, n, b, src, lq, lp);
+    else if (src != VH_SLOT_UNUSED)
+      th[s] = a.extra[(size_t)(-1 - src) * a.N + n];
+  }
+  for (int j = 0; j < a.n_free; ++j) sample_column(a, n, b, a.free_cols[j], lq, lp);
+}
+
+// cotangent of one sampled column -> (d mu, d prec) of q for this trajectory
+template <typename R>
+VH_HD void column_vjp(const Call<R>& a, int n, int b, int k, R gth, R glq, R glp, R& dmu, R& dprec) {
+  dmu = R(0);
+  dprec = R(0);
+  const int kind = a.kind[k];
+  if (a.g_theta) gth += a.g_theta[(size_t)k * a.N + n];
+  const R mu = a.q_mu[b * a.P + k];
+  if (kind == VH_KIND_CONSTANT) {
+    dmu = gth;  // value of a constant: no trainable parameter behind it, reported for completeness
+    return;
+  }
+  const R prec = a.q_prec[b * a.P + k];
+  const R sigma = R(1) / vsqrt(prec);
+  const R uu = a.u[(size_t)n * a.P + k];
+  const R sv = mu + sigma * uu;
+  const R raw = kind == VH_KIND_LOGNORMAL ? vexp(sv) : sv;
+  const R lo = a.clip_lo[k], hi = a.clip_hi[k];
+  const R th = clampv(raw, lo, hi);
+  const R pm = a.p_mu[k], pp = a.p_prec[k];
+  R x, gx_to_th;
+  if (kind == VH_KIND_LOGNORMAL) {
+    x = vlog(th + R(1e-12));
+    gx_to_th = R(1) / (th + R(1e-12));
+  } else {
+    x = th;
+    gx_to_th = R(1);
+  }
+  const R jac = kind == VH_KIND_LOGNORMAL ? R(1) : R(0);
+  const R dq = mu - x, dp = pm - x;
+  // d logq / dx and d logp / dx (x = log theta for LogNormal, including the -x Jacobian term)
+  const R gx = glq * (prec * dq - jac) + glp * (pp * dp - jac);
+  const R gtot = gth + gx * gx_to_th;
+  const R graw = gtot * clampmask(raw, lo, hi);
+  const R gs = kind == VH_KIND_LOGNORMAL ? graw * raw : graw;
+  dmu = gs - glq * prec * dq;
+  dprec = -R(0.5) * gs * uu * sigma / prec + glq * (R(0.5) / (prec + R(1e-12)) - R(0.5) * dq * dq);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward trajectory
+// ---------------------------------------------------------------------------------------------------------------
+template <class M, class TB>
+VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M::real* w) {
+  typedef typename M::real R;
+  constexpr int S = M::S, NS = M::NS;
+  const int b = n / a.IW;
+  const size_t N = a.N;
+  R th[M::NSLOT];
+  R lq = R(0), lp = R(0);
+  load_theta<M>(a, n, b, th, lq, lp);
+  R c6, c12;
+  M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
+  Rhs<M> f;
+  f.w = w;
+  M::setup(th, c6, c12, f.c);
+  R x[S];
+  M::init_state(th, c6, c12, x);
+  R prec[4], lprec[4], ll[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    prec[o] = M::DYN ? R(1) : th[S_prec_x + o];
+    lprec[o] = M::DYN ? R(0) : vlog(prec[o]);
+    ll[o] = R(0);
+  }
+  const R h0 = a.times[1] - a.times[0];
+  const R* obs = a.obs ? a.obs + (size_t)b * 4 * a.T : nullptr;
+  for (int k = 0; k < a.T; ++k) {
+    if (a.x_states) {
+#pragma unroll
+      for (int q = 0; q < S; ++q) a.x_states[((size_t)k * S + q) * N + n] = x[q];
+    }
+    R xp[4];
+    M::observe(x, xp);
+    if (a.x_predict) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) a.x_predict[((size_t)k * 4 + o) * N + n] = xp[o];
+    }
+    if (obs) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const R pr = M::DYN ? x[NS + o] : prec[o];
+        const R lpr = M::DYN ? vlog(pr) : lprec[o];
+        const R d = xp[o] - obs[o * a.T + k];
+        ll[o] += R(-0.5) * (Lim<R>::log2pi - lpr + pr * d * d);
+      }
+    }
+    if (k + 1 < a.T) {
+      const R t0 = a.times[k], t1 = a.times[k + 1];
+      rk_step<M, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x);
+    }
+  }
+  if (a.logp_species) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) a.logp_species[(size_t)n * 4 + o] = ll[o];
+  }
+  if (a.logp_theta) a.logp_theta[n] = lp;
+  if (a.logq_theta) a.logq_theta[n] = lq;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// reverse trajectory.  RED: functor that folds (d mu, d prec) of column k of individual b into d_q_mu/d_q_prec
+// (warp-aggregated atomics on the device, plain adds on the host).
+// ---------------------------------------------------------------------------------------------------------------
+template <class M, class TB, typename GW, typename RED>
+VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, const typename M::real* w, GW gw, RED red) {
+  typedef typename M::real R;
+  constexpr int S = M::S, NS = M::NS;
+  const int b = n / a.IW;
+  const size_t N = a.N;
+  R gth[M::NSLOT];
+#pragma unroll
+  for (int s = 0; s < M::NSLOT; ++s) gth[s] = R(0);
+  R glq = R(0), glp = R(0);
+  R c6 = R(0), c12 = R(0);
+  if (active) {
+    R th[M::NSLOT];
+    R lq = R(0), lp = R(0);
+    Call<R> a2 = a;
+    a2.theta = nullptr;  // do not rewrite theta in the reverse pass
+    load_theta<M>(a2, n, b, th, lq, lp);
+    M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
+    Rhs<M> f;
+    f.w = w;
+    M::setup(th, c6, c12, f.c);
+    typename M::Consts gc;
+#pragma unroll
+    for (int i = 0; i < M::NC; ++i) gc.v[i] = R(0);
+    R prec[4], gprec[4], gl[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      prec[o] = M::DYN ? R(1) : th[S_prec_x + o];
+      gprec[o] = R(0);
+      gl[o] = a.g_logp_species ? a.g_logp_species[(size_t)n * 4 + o] : R(0);
+    }
+    glq = a.g_logq_theta ? a.g_logq_theta[n] : R(0);
+    glp = a.g_logp_theta ? a.g_logp_theta[n] : R(0);
+    const R h0 = a.times[1] - a.times[0];
+    const R* obs = a.obs ? a.obs + (size_t)b * 4 * a.T : nullptr;
+    R lam[S], x[S], xprev[S];
+#pragma unroll
+    for (int q = 0; q < S; ++q) {
+      lam[q] = R(0);
+      x[q] = a.x_states[((size_t)(a.T - 1) * S + q) * N + n];
+    }
+    for (int k = a.T - 1; k >= 0; --k) {
+      if (k > 0) {  // prefetch the previous checkpoint while this step's adjoint is computed
+#pragma unroll
+        for (int q = 0; q < S; ++q) xprev[q] = a.x_states[((size_t)(k - 1) * S + q) * N + n];
+      }
+      if (k + 1 < a.T) {
+        const R t0 = a.times[k], t1 = a.times[k + 1];
+        rk_step_vjp<M, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, lam, gc, gw);
+      }
+      // emission at time k
+      R xp[4], gxp[4];
+      M::observe(x, xp);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        gxp[o] = a.g_x_predict ? a.g_x_predict[((size_t)k * 4 + o) * N + n] : R(0);
+        if (obs) {
+          const R pr = M::DYN ? x[NS + o] : prec[o];
+          const R d = xp[o] - obs[o * a.T + k];
+          gxp[o] -= gl[o] * pr * d;
+          const R gp = gl[o] * R(0.5) * (R(1) / pr - d * d);
+          if (M::DYN)
+            lam[NS + o] += gp;
+          else
+            gprec[o] += gp;
+        }
+      }
+      M::observe_vjp(x, gxp, lam);
+      if (a.g_x_states) {
+#pragma unroll
+        for (int q = 0; q < S; ++q) lam[q] += a.g_x_states[((size_t)k * S + q) * N + n];
+      }
+#pragma unroll
+      for (int q = 0; q < S; ++q) x[q] = xprev[q];
+    }
+    M::init_state_vjp(lam, gth);
+    M::setup_vjp(th, c6, c12, f.c, gc, gth);
+    if (!M::DYN) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gprec[o];
+    }
+  }
+  // scatter slot cotangents: sampled columns -> (d q_mu, d q_prec); extras -> d_extra
+#pragma unroll
+  for (int s = 0; s < M::NSLOT; ++s) {
+    if (!M::uses(s)) continue;
+    const int src = a.slot_src[s];
+    if (src >= 0) {
+      R dmu = R(0), dprec = R(0);
+      if (active) column_vjp(a, n, b, src, gth[s], glq, glp, dmu, dprec);
+      red(b, src, dmu, dprec, active);
+    } else if (src != VH_SLOT_UNUSED && a.d_extra && active) {
+      a.d_extra[(size_t)(-1 - src) * N + n] = gth[s];
+    }
+  }
+  for (int j = 0; j < a.n_free; ++j) {
+    R dmu = R(0), dprec = R(0);
+    if (active) column_vjp(a, n, b, a.free_cols[j], R(0), glq, glp, dmu, dprec);
+    red(b, a.free_cols[j], dmu, dprec, active);
+  }
+}
+
+}  // namespace vh
