@@ -1,0 +1,6 @@
+// Instantiates the bwd kernels of the double-receiver family for float (one translation unit per dtype x direction so
+// the 30 (model x solver) instantiations of each compile in parallel).
+#include "vh_launch.cuh"
+namespace vh {
+int launch_bwd_f32(const vh_problem* p, const vh_bwd_io* io, cudaStream_t stream) { return launch_bwd<float>(p, io, stream); }
+}  // namespace vh
