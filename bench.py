@@ -1,0 +1,447 @@
+#!/usr/bin/env python
+"""ELBO-gradient step benchmark (BASELINE.json metric: trajectories/s and steps/s of the ELBO-grad step).
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference algorithm's CPU path (oracle port)
+
+One *step* = the body of the reference's ``Training._run_batch`` (vihds/training.py:329-337): encoder forward, theta
+sampling/clipping, fixed-step ODE solve, observation log-likelihood, log p / log q, IWAE cost, backward to every
+trainable parameter, gradient all-reduce (N > 1), Adam.  Workload at N = 1 (default): ``specs/dr_constant_icml.yaml``,
+batch = 36 individuals x IW = 200 samples = 7,200 trajectories, T = 86, midpoint solver, fp32 (BASELINE.json
+configs[1]); real pre-processed plate data (tests/golden/dataset_dr_icml.npz), random-init weights at seed 0.  For
+N > 1 every rank takes its own 36 individuals (weak scaling; the only exchange is the gradient all-reduce).
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract: ``roofline`` (reverse-sweep kernel, the dominant
+launch), ``cpu_baseline`` (oracle port on the host cores), ``e2e`` (same step fed from pinned HOST buffers through
+the public API, H2D + D2H inside the timed region), ``kernels`` (per-launch device times of the four hot launches).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+WORKLOADS = {
+    # name: (spec, dataset fixture, B per GPU, IW, T or None (= dataset grid))
+    "dr_constant_icml": ("dr_constant_icml", "dataset_dr_icml", 36, 200, None),
+    "relay_constant_precisions": ("relay_constant_precisions", "dataset_relay", 36, 200, None),
+    "synthetic_dr_constant": ("dr_constant_icml", "dataset_dr_icml", 1024, 128, 500),
+}
+
+
+class Args(object):
+    """Stand-in for the reference's argparse namespace (run_xval.py:17-57)."""
+
+    def __init__(self, **kw):
+        self.seed, self.gpu, self.precision_hidden_layers, self.yaml = 0, None, None, None
+        self.folds, self.split, self.heldout, self.verbose = 4, 1, None, False
+        self.train_samples, self.test_samples, self.epochs, self.test_epoch = 200, 1000, 1, 0
+        self.__dict__.update(kw)
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(B, IW, T, S, P, E, elem=4):
+    """SURVEY.md section 8d, for the launches as the training step issues them (no x_predict trace):
+    forward  reads u [N,P], obs [B,4,T], extras [E,N], q tables; writes theta [P,N], x_states [T,S,N], 6 terms per n;
+    reverse  reads x_states, u, obs, extras, 6 upstream grads per n; writes d_q [B,P] x 2."""
+    N = B * IW
+    fwd = elem * (N * P + B * 4 * T + E * N + 2 * B * P + N * P + N * T * S + 6 * N)
+    bwd = elem * (N * T * S + N * P + B * 4 * T + E * N + 2 * B * P + 6 * N + 2 * B * P)
+    return fwd, bwd
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0]))
+                mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# workload construction
+# ---------------------------------------------------------------------------------------------------------------
+def load_spec(name):
+    with open(os.path.join(GOLDEN, "specs", name + ".json")) as f:
+        return json.load(f)
+
+
+def synthetic_individuals(ds, B, T, rng):
+    """B synthetic individuals on a uniform T-point grid over [0, 16.5] h.  Treatments:
+    exactly one non-zero inducer per individual, concentration in {25000/3^k} or 0, log1p-transformed; devices
+    uniform over the icml devices; observations: real curves of the same device resampled onto the grid (values in
+    [0, 1] after the reference's scaling) plus N(0, 0.01^2) noise."""
+    import torch
+
+    times = np.linspace(0.0, 16.5, T).astype(np.float32)
+    idx = rng.randint(0, len(ds), size=B)
+    conc = np.concatenate([[0.0], 25000.0 / 3.0 ** np.arange(11)])
+    inputs = np.zeros((B, 2), np.float32)
+    inputs[np.arange(B), rng.randint(0, 2, size=B)] = np.log1p(conc[rng.randint(0, len(conc), size=B)]).astype(np.float32)
+    t0 = ds.times.numpy()
+    obs0 = ds.observations.numpy()[idx]
+    obs = np.empty((B, 4, T), np.float32)
+    for o in range(4):
+        for b in range(B):
+            obs[b, o] = np.interp(times, t0, obs0[b, o])
+    obs = np.clip(obs + rng.randn(B, 4, T).astype(np.float32) * 0.01, 0.0, None)
+    return {"times": torch.as_tensor(times), "inputs": torch.as_tensor(inputs), "dev_1hot": ds.dev_1hot[idx].clone(),
+            "observations": torch.as_tensor(obs), "devices": torch.as_tensor(ds.devices[idx])}
+
+
+def build_workload(name, rank, world, device, B_override=None, IW_override=None, with_training=True):
+    import torch
+
+    from vihds_b200.config import Config
+    from vihds_b200.datasets import TimeSeriesDataset, build_datasets
+    from vihds_b200.parameters import Parameters
+    from vihds_b200.training import Training
+    from vihds_b200.vae import build_model
+
+    spec_name, fixture, B, IW, T = WORKLOADS[name]
+    B, IW = B_override or B, IW_override or IW
+    args = Args(train_samples=IW)
+    settings = Config(args, spec=load_spec(spec_name), device=device)
+    ds = TimeSeriesDataset.from_npz(os.path.join(GOLDEN, fixture + ".npz"), settings.data)
+    pair = build_datasets(args, settings, dataset=ds)
+    parameters = Parameters(settings.params)
+    torch.manual_seed(0)
+    model = build_model(args, settings, pair, parameters)
+    training = Training(args, settings, pair, parameters, model) if with_training else None
+    rng = np.random.RandomState(1234 + rank)
+    if T is None:
+        ids = np.asarray(pair.train.indices)
+        order = np.random.RandomState(0).permutation(len(ids))
+        take = ids[np.take(order, np.arange(rank * B, (rank + 1) * B), mode="wrap")]
+        item = ds[take]
+        host = {"times": ds.times, "inputs": item["inputs"], "dev_1hot": item["dev_1hot"], "observations": item["observations"]}
+    else:
+        host = synthetic_individuals(ds, B, T, rng)
+        if ds.n_times != T:  # the encoder's hidden layer is sized by T: rebuild it for the synthetic grid
+            from vihds_b200.encoders import Encoder
+
+            torch.manual_seed(0)
+            model.encoder = Encoder(parameters, (4, T, pair.n_conditions, pair.depth)).to(device=device, dtype=settings.dtype)
+            training = Training(args, settings, pair, parameters, model) if with_training else None
+    host = {k: v.to(settings.dtype).contiguous() for k, v in host.items() if k != "devices"}
+    return settings, parameters, model, training, host, B, IW, int(host["times"].numel()), rng
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port (plain PyTorch CPU restatement of the reference algorithm at its own granularity)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_case(parameters, model, host, B, IW, rng, solver):
+    """Golden-style case dict for oracle/vihds_oracle.py from the bench workload (q from the freshly initialised
+    encoder, evaluated on the CPU copy of the batch)."""
+    import torch
+
+    from vihds_b200.config import Settings
+
+    enc = model.encoder
+    dev = enc.global_free.device  # (Encoder.parameters is the spec table, as in the reference, not nn.Module.parameters)
+    with torch.no_grad():
+        mu, prec = enc.q_table(Settings(observations=host["observations"].to(dev), inputs=host["inputs"].to(dev),
+                                        dev_1hot=host["dev_1hot"].to(dev)))
+    p_mu, p_prec, _, _ = parameters.prior_arrays(np.float32)
+    ode = model.decoder.ode_model
+    case = {
+        "dtype": "float32", "model": ode.kernel_model, "solver": solver, "names": np.array(parameters.names),
+        "kinds": parameters.kinds(), "u": rng.randn(B, IW, parameters.n_theta).astype(np.float32),
+        "times": host["times"].numpy(), "inputs": host["inputs"].numpy(), "dev_1hot": host["dev_1hot"].numpy(),
+        "observations": host["observations"].numpy(), "q_mu": mu.float().cpu().numpy(), "q_prec": prec.float().cpu().numpy(),
+        "p_mu": p_mu, "p_prec": p_prec, "p_sigma": (1.0 / np.sqrt(p_prec)).astype(np.float32),
+    }
+    if model.decoder.condition_on_device:
+        for nm in ode.conditioned:
+            case["cond_" + nm] = (1.0 + np.abs(rng.randn(B, IW))).astype(np.float32)
+    w = ode.flat_weights()
+    if w is not None:
+        for lname, lin in zip(("prec_production", "prec_degradation"), ode.precisions.layers()):
+            case["w:ode_model.precisions.%s.weight" % lname] = lin.weight.detach().float().cpu().numpy()
+            case["w:ode_model.precisions.%s.bias" % lname] = lin.bias.detach().float().cpu().numpy()
+    return case
+
+
+def time_oracle(case, steps, warmup):
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import vihds_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        out = O.elbo_step(case, requires_grad=True)
+        t1 = time.perf_counter()
+        if i >= warmup:
+            ts.append(t1 - t0)
+    return float(np.mean(ts)), cores, float(out["loss"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dr_constant_icml", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="individuals per GPU (default: the workload's)")
+    ap.add_argument("--iw", type=int, default=None)
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=8)
+    a = ap.parse_args()
+
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    spec_name, _, B0, IW0, T0 = WORKLOADS[a.workload]
+
+    # ---------------- reference arm: the reference algorithm's CPU path on the host cores (rank 0 only) ----------
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        settings, parameters, model, training, host, B, IW, T, rng = build_workload(a.workload, 0, 1, "cpu", a.batch, a.iw, with_training=False)
+        Bc = min(B, 64)  # bounded sample: the autograd graph of the full synthetic slab does not fit in host memory
+        host_c = {k: (v[:Bc] if k != "times" else v) for k, v in host.items()}
+        case = cpu_case(parameters, model, host_c, Bc, IW, rng, settings.params.solver)
+        sec, cores, loss = time_oracle(case, a.steps, a.warmup)
+        tps = Bc * IW / sec
+        line = {
+            "impl": "reference", "metric": "elbo_grad_trajectories_per_sec", "value": tps, "unit": "traj/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "steps_per_sec": 1.0 / sec, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "real plate data (pre-processed fixture), random-init weights",
+            "config": {"workload": a.workload, "spec": spec_name, "batch": Bc, "iw": IW, "T": T, "solver": settings.params.solver},
+            "cpu_baseline": {"value": tps, "unit": "traj/s", "cores": cores, "kind": "port",
+                             "sample": "%d steps of B=%d x IW=%d, T=%d: sample/clip/solve/log-lik/log p,q/IWAE + backward to q "
+                                       "(oracle/vihds_oracle.py, torch CPU, %d threads)" % (a.steps, Bc, IW, T, cores)},
+            "e2e": {"value": tps, "unit": "traj/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "loss": loss,
+        }
+        print(json.dumps(line))
+        return
+
+    # ---------------- this repo's arm ---------------------------------------------------------------------------
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the engine has no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=device)
+        pg = dist.group.WORLD
+    from vihds_b200.training import GraphedStep
+
+    settings, parameters, model, training, host, B, IW, T, rng = build_workload(a.workload, rank, world, device, a.batch, a.iw)
+    P, N = parameters.n_theta, B * IW
+    model.want_predict = False
+    gs = GraphedStep(training, B, IW, T, b_total=B * world, process_group=pg, use_graphs=not a.no_graphs)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    gs.load_batch(pinned)
+    n_pool = 4
+    u_host = [torch.from_numpy(rng.randn(B, IW, P).astype(np.float32)).to(settings.dtype).pin_memory() for _ in range(n_pool)]
+    u_dev = [u.to(device) for u in u_host]
+    gs.load_u(u_dev[0])
+    gs.draw_conditioner()
+    gs.prepare()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)  # > 126 MB L2
+    cost_host = torch.zeros(1, dtype=settings.dtype).pin_memory()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # device-resident pass: inputs already in HBM, CUDA-event timing, L2 flushed between steps
+    for i in range(a.warmup):
+        gs.load_u(u_dev[i % n_pool])
+        gs.draw_conditioner()
+        gs.step()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    wall0 = time.perf_counter()
+    for i in range(a.steps):
+        flush.zero_()
+        ev[i][0].record()
+        gs.load_u(u_dev[i % n_pool])
+        gs.draw_conditioner()
+        gs.ev_hot = kev[i]
+        gs.step()
+        ev[i][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler is not None else None
+    gs.ev_hot = None
+    step_ms = np.array([s.elapsed_time(e) for s, e in ev])
+    bwd_ms = np.array([s.elapsed_time(e) for s, e in kev])
+    total_ms = float(step_ms.sum())
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / a.steps
+    value = N * world / (ms_per_step * 1e-3)
+    final_cost = float(gs.buf.cost.item())
+
+    # end-to-end pass: the public step fed from pinned HOST buffers; H2D of the batch + u, D2H of the cost, host sync
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values()) + u_host[0].numel() * u_host[0].element_size()
+    h2d += gs.cond_w.numel() * gs.cond_w.element_size() if gs.extras else 0
+    e2e_s = []
+    for i in range(a.warmup + a.steps):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        gs.load_batch(pinned)
+        gs.load_u(u_host[i % n_pool])
+        gs.draw_conditioner()
+        cost = gs.step()
+        cost_host.copy_(cost, non_blocking=True)
+        torch.cuda.synchronize()
+        if torch.isnan(cost_host).any():
+            raise RuntimeError("ELBO is NaN")
+        t1 = time.perf_counter()
+        if i >= a.warmup:
+            e2e_s.append(t1 - t0)
+    e2e_step = float(np.sum(e2e_s)) / a.steps
+    if world > 1:
+        t = torch.tensor([e2e_step], dtype=torch.float64, device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        e2e_step = float(t.item())
+
+    # per-launch device times of the hot launches (eager, L2 flushed), for the "kernels" breakdown
+    kern = {}
+    if rank == 0:
+        lib, b = gs.prob.lib, gs.buf
+        import ctypes as C
+
+        from vihds_b200 import _lib as L
+        from vihds_b200.engine import _ptr, _stream
+
+        def t_launch(fn, reps=10):
+            ts = []
+            for _ in range(reps):
+                flush.zero_()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                fn()
+                e.record()
+                torch.cuda.synchronize()
+                ts.append(s.elapsed_time(e))
+            return float(np.median(ts)) * 1e3
+
+        kern["elbo_fwd_us"] = t_launch(lambda: L.check(lib.vh_elbo_terms_fwd(C.byref(gs._p), C.byref(gs._fio), _stream())))
+        kern["elbo_bwd_us"] = t_launch(lambda: L.check(lib.vh_elbo_terms_bwd(C.byref(gs._p), C.byref(gs._bio), _stream())))
+        kern["elbo_bwd_in_step_us"] = float(bwd_ms.mean()) * 1e3
+
+    if rank != 0:
+        if world > 1:
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+        return
+
+    S, E = gs.prob.S, len(gs.extras)
+    bytes_fwd, bytes_bwd = algorithmic_bytes(B, IW, T, S, P, E, 8 if settings.dtype == torch.float64 else 4)
+    peak, peak_src = measured_peak_gbs()
+    bwd_s = float(bwd_ms.mean()) * 1e-3
+    achieved = bytes_bwd / bwd_s / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "traffic_%s.json" % a.workload)
+    if os.path.exists(prof):
+        with open(prof) as f:
+            traffic = json.load(f).get("elbo_bwd_dram_bytes")
+    line = {
+        "metric": "elbo_grad_trajectories_per_sec", "value": value, "unit": "traj/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms_per_step, "steps_per_sec": 1e3 / ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32" if settings.dtype == torch.float32 else "f64",
+        "data": "real plate data (pre-processed fixture tests/golden/%s.npz)%s, random-init weights (seed 0), u ~ N(0,1)" % (
+            WORKLOADS[a.workload][1], "" if T0 is None else " resampled to a synthetic T=%d grid" % T),
+        "config": {"workload": a.workload, "spec": spec_name, "batch_per_gpu": B, "global_batch": B * world, "iw": IW,
+                   "trajectories_per_step": N * world, "T": T, "state_width": S, "n_theta": P, "solver": settings.params.solver,
+                   "parallelism": "dp%d (individuals sharded, one gradient all-reduce)" % world,
+                   "cuda_graphs": not a.no_graphs, "l2": "flushed between timed steps (256 MiB memset)"},
+        "roofline": {"kernel": "elbo_bwd_kernel (discrete-adjoint reverse sweep)", "bound": "hbm", "achieved": achieved,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes": bytes_bwd, "launch_us": bwd_s * 1e6,
+                     "note": "latency/issue-bound at this size: 7,200 trajectories = 225 warps on 148 SMs (see DESIGN.md)"},
+        "kernels": kern,
+        "e2e": {"value": N * world / e2e_step, "unit": "traj/s", "ms_per_step": e2e_step * 1e3, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(cost_host.numel() * cost_host.element_size())},
+        "gpu_launches": int(6 * a.steps),
+        "clocks": clocks, "cost_after_last_step": final_cost, "wall_s_timed_region": wall,
+    }
+    if not a.no_cpu_baseline and world == 1:
+        Bc = min(B, 64)
+        host_c = {k: (v[:Bc] if k != "times" else v) for k, v in host.items()}
+        case = cpu_case(parameters, model, host_c, Bc, IW, np.random.RandomState(7), settings.params.solver)
+        sec, cores, _ = time_oracle(case, a.cpu_steps, 2)
+        line["cpu_baseline"] = {
+            "value": Bc * IW / sec, "unit": "traj/s", "cores": cores, "kind": "port", "ms_per_step": sec * 1e3,
+            "sample": "%d steps of B=%d x IW=%d, T=%d (forward + backward to q; oracle/vihds_oracle.py, torch CPU, %d threads)" % (
+                a.cpu_steps, Bc, IW, T, cores)}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -174,6 +174,11 @@ int vh_iw_moments(const vh_problem* p, const void* w, const void* x_states, cons
 /* Fused Adam over a flat parameter vector (torch.optim.Adam defaults; vihds/training.py:82, :336). step is 1-based. */
 int vh_adam_step(int dtype, size_t n, void* param, const void* grad, void* exp_avg, void* exp_avg_sq, double lr,
                  double beta1, double beta2, double eps, int step, void* stream);
+/* Same update with the hyper-parameters and the step counter ON THE DEVICE, so that the launch can be captured in a
+ * CUDA graph and replayed: hyper = double[4] {lr, beta1, beta2, eps}; step = int64[1], the number of updates done so
+ * far (the call uses step+1 for the bias correction and then increments it). */
+int vh_adam_step_dev(int dtype, size_t n, void* param, const void* grad, void* exp_avg, void* exp_avg_sq,
+                     const void* hyper, void* step, void* stream);
 
 #ifdef __cplusplus
 }

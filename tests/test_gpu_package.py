@@ -1,0 +1,195 @@
+"""-m gpu: the host package (BaseVAE.forward -> Training.cost -> backward; OdeModel.simulate; GraphedStep) driving
+the CUDA library, against the golden vectors minted from the reference.  Tolerances as in test_gpu_parity.py."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_case
+from vihds_b200.config import Config, Settings
+from vihds_b200.datasets import TimeSeriesDataset, build_datasets
+from vihds_b200.parameters import Parameters
+from vihds_b200.training import GraphedStep, Training
+from vihds_b200.vae import build_model
+
+pytestmark = pytest.mark.gpu
+
+
+class Args:
+    seed, gpu, precision_hidden_layers, yaml, verbose = 0, None, None, None, False
+    folds, split, heldout, train_samples, test_samples = 4, 1, None, 8, 8
+
+
+FIXTURE = {"dr_constant_icml": "dataset_dr_icml", "relay_constant_precisions": "dataset_relay"}
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300))
+
+
+def build(spec, dims=None, iw=8):
+    with open(os.path.join(GOLDEN, "specs", spec + ".json")) as f:
+        settings = Config(Args(), spec=json.load(f), device="cuda")
+    par = Parameters(settings.params)
+    pair = None
+    if spec in FIXTURE:
+        ds = TimeSeriesDataset.from_npz(os.path.join(GOLDEN, FIXTURE[spec] + ".npz"), settings.data)
+        pair = build_datasets(Args(), settings, dataset=ds)
+    torch.manual_seed(0)
+    model = build_model(Args(), settings, pair if pair is not None else dims, par)
+    a = Args()
+    a.train_samples = iw
+    return settings, par, model, Training(a, settings, pair, par, model)
+
+
+def batch_from_case(case, dtype=torch.float32):
+    d = lambda k: torch.as_tensor(case[k]).to("cuda", dtype)  # noqa: E731
+    return Settings(times=d("times"), inputs=d("inputs"), dev_1hot=d("dev_1hot"), observations=d("observations"))
+
+
+def pin_conditioner(model, case):
+    """The reference draws fresh random conditioner weights per call; the golden case recorded the result."""
+    ode = model.decoder.ode_model
+    if "cond_aR" in case:
+        planes = torch.stack([torch.as_tensor(case["cond_" + n]).reshape(-1) for n in ode.conditioned]).cuda()
+        ode.conditioned_extras = lambda B, IW, dev_1hot: planes
+
+
+@pytest.mark.parametrize("case_name,spec,dims", [
+    ("dr_constant_icml_midpoint_f32_iw8", "dr_constant_icml", None),
+    ("dr_constant_one_midpoint_f32_iw5", "dr_constant_one", (4, 100, 2, 1)),
+    ("relay_constant_precisions_midpoint_f32_iw8", "relay_constant_precisions", None),
+])
+def test_model_forward_cost_backward_match_reference(case_name, spec, dims):
+    case = load_case(case_name)
+    settings, par, model, training = build(spec, dims)
+    if "w:ode_model.precisions.prec_production.weight" in case:  # decoder weights are drawn after the data split in the reference
+        sd = {k[2:]: torch.as_tensor(case[k]).cuda() for k in case if k.startswith("w:")}
+        model.decoder.load_state_dict(sd)
+    pin_conditioner(model, case)
+    batch = batch_from_case(case)
+    u = torch.as_tensor(case["u"]).cuda()
+    result, theta, q, p = model(batch, u.shape[1], u=u)
+    x_states, x_predict, precisions = result
+    q.mu.retain_grad()
+    q.prec.retain_grad()
+    cost = training.cost(batch, result, theta, q, p).elbo
+    cost.backward()
+    tol = 1e-4
+    assert abs(float(cost) - float(case["loss"])) <= tol * abs(float(case["loss"]))
+    for s in range(case["x_states"].shape[2]):
+        assert _rel(x_states[:, :, s].detach().cpu().numpy(), case["x_states"][:, :, s]) < tol
+    assert _rel(x_predict.detach().cpu().numpy(), case["x_predict"]) < tol
+    assert _rel(precisions.detach().cpu().numpy(), case["precisions"]) < tol
+    assert x_states.shape == case["x_states"].shape and precisions.shape == case["precisions"].shape
+    assert _rel(theta.terms["log_p_by_species"].detach().cpu().numpy(), case["log_p_by_species"]) < tol
+    assert _rel(q.log_prob(theta).detach().cpu().numpy(), case["log_q_theta"]) < tol
+    assert _rel(p.log_prob(theta).detach().cpu().numpy(), case["log_p_theta"]) < tol
+    per_ind = case["per_individual"].astype(bool)
+    sel = case["kinds"] != 0
+    for got, ref in ((q.mu.grad.cpu().numpy(), case["grad_q_mu"]), (q.prec.grad.cpu().numpy(), case["grad_q_prec"])):
+        ref_tot = np.where(per_ind, ref.sum(0), ref[0])
+        assert _rel(got.sum(0)[sel], ref_tot[sel]) < 3e-3
+    for k in case:
+        if k.startswith("gw:"):
+            g = dict(model.decoder.named_parameters())[k[3:]].grad
+            assert _rel(g.cpu().numpy(), case[k]) < 3e-3, k
+    # no NaN gradients on any trainable tensor (tests/test_grad_dr.py of the reference)
+    assert all(torch.isfinite(p_.grad).all() for p_ in model.parameters() if p_.grad is not None)
+
+
+def test_simulate_seam_matches_reference_and_differentiates():
+    """OdeModel.simulate (tests/test_ode_solvers.py of the reference calls it directly)."""
+    case = load_case("dr_constant_one_midpoint_f32_iw5")
+    settings, par, model, training = build("dr_constant_one", (4, 100, 2, 1), iw=5)
+    from vihds_b200.distributions import DotOperatorSamples
+
+    theta = DotOperatorSamples()
+    for k, nm in enumerate(case["names"]):
+        theta.add(str(nm), torch.as_tensor(case["theta"][k]).cuda().requires_grad_(True))
+    batch = batch_from_case(case)
+    ode = model.decoder.ode_model
+    sol = ode.simulate(settings, batch.times, theta, batch.inputs, batch.dev_1hot, condition_on_device=False)
+    assert sol.shape == case["x_states"].shape
+    for s in range(8):
+        assert _rel(sol[:, :, s].detach().cpu().numpy(), case["x_states"][:, :, s]) < 1e-4
+    sol[:, :, 1, -1].sum().backward()
+    assert torch.isfinite(theta.r.grad).all() and float(theta.r.grad.abs().sum()) > 0
+    (x_states, x_predict, precisions), _ = model.decoder(theta, batch)
+    assert _rel(x_predict.detach().cpu().numpy(), case["x_predict"]) < 1e-4
+    assert _rel(precisions.detach().cpu().numpy(), case["precisions"]) < 1e-4
+
+
+@pytest.mark.parametrize("solver", ["modeuler", "rk4", "euler", "modeulerwhile"])
+def test_solver_switch_via_config(solver):
+    case = load_case("dr_constant_one_%s_f32_iw5" % solver)
+    settings, par, model, training = build("dr_constant_one", (4, 100, 2, 1), iw=5)
+    settings.params.solver = solver
+    batch = batch_from_case(case)
+    u = torch.as_tensor(case["u"]).cuda()
+    result, theta, q, p = model(batch, 5, u=u)
+    cost = training.cost(batch, result, theta, q, p).elbo
+    assert abs(float(cost) - float(case["loss"])) <= 1e-4 * abs(float(case["loss"]))
+
+
+def test_adaptive_solver_raises():
+    settings, par, model, training = build("dr_constant_one", (4, 100, 2, 1), iw=5)
+    settings.params.solver = "dopri5"
+    case = load_case("dr_constant_one_midpoint_f32_iw5")
+    with pytest.raises(NotImplementedError):
+        model(batch_from_case(case), 5, u=torch.as_tensor(case["u"]).cuda())
+
+
+@pytest.mark.parametrize("use_graphs", [False, True])
+def test_graphed_step_equals_eager_steps(use_graphs):
+    """Three Adam steps through GraphedStep (static buffers, captured encoder fwd/bwd + fused Adam) land on the same
+    parameters as three reference-shaped eager steps (model -> cost -> backward -> Adam)."""
+    case = load_case("dr_constant_icml_midpoint_f32_iw8")
+    batch = batch_from_case(case)
+    B, IW, P = case["u"].shape
+    us = [torch.randn(B, IW, P, generator=torch.Generator().manual_seed(i)).cuda() for i in range(3)]
+    planes = torch.stack([torch.as_tensor(case["cond_" + n]).reshape(-1) for n in ("aR", "aS")]).cuda()
+
+    _, _, model_a, tr_a = build("dr_constant_icml")
+    model_a.decoder.ode_model.conditioned_extras = lambda B_, IW_, d: planes
+    model_a.want_predict = False
+    costs_a = []
+    for u in us:
+        assert tr_a._run_batch(batch, u=u)
+        costs_a.append(float(tr_a.last_cost))
+
+    _, _, model_b, tr_b = build("dr_constant_icml")
+    gs = GraphedStep(tr_b, B, IW, batch.times.numel(), use_graphs=use_graphs)
+    gs.extras_override = planes
+    gs.load_batch(batch)
+    costs_b = []
+    for u in us:
+        gs.load_u(u)
+        costs_b.append(float(gs.step().item()))
+    assert np.allclose(costs_a, costs_b, rtol=1e-5), (costs_a, costs_b)
+    assert _rel(tr_b.optimizer.flat.cpu().numpy(), tr_a.optimizer.flat.cpu().numpy()) < 1e-4
+    assert int(tr_b.optimizer.step_dev.item()) == 3
+
+
+def test_evaluation_moments_match_numpy_reduction():
+    """Results.init (vihds/utils.py:79-99): device-side IW moments equal the reference's numpy formulas."""
+    case = load_case("dr_constant_icml_midpoint_f32_iw8")
+    settings, par, model, training = build("dr_constant_icml")
+    pin_conditioner(model, case)
+    batch = batch_from_case(case)
+    u = torch.as_tensor(case["u"]).cuda()
+    with torch.no_grad():
+        result, theta, q, p = model(batch, u.shape[1], u=u)
+        out = training.cost(batch, result, theta, q, p, full_output=True)
+    x_states, x_predict, precisions = (t.cpu().numpy().astype(np.float64) for t in result)
+    lw = out.log_unnormalized_iws.cpu().numpy().astype(np.float64)
+    w = np.exp(lw - lw.max(1, keepdims=True))
+    w = (w / w.sum(1, keepdims=True))[:, :, None, None]
+    mu = (w * x_predict).sum(1)
+    sd = np.sqrt((w * (x_predict ** 2 + 1.0 / precisions)).sum(1) - mu ** 2)
+    assert _rel(out.iw_predict_mu, mu) < 1e-4 and _rel(out.iw_predict_std, sd) < 1e-3
+    assert _rel(out.iw_states, (w * x_states).sum(1)) < 1e-4 and _rel(out.iw_variance, (w / precisions).sum(1)) < 1e-4
+    assert abs(float(out.elbo) + float(case["loss"])) <= 1e-4 * abs(float(case["loss"]))

@@ -74,6 +74,7 @@ def load():
     lib.vh_iw_moments.argtypes = [C.POINTER(vh_problem)] + [C.c_void_p] * 9
     lib.vh_adam_step.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                  C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
+    lib.vh_adam_step_dev.argtypes = [C.c_int, C.c_size_t] + [C.c_void_p] * 7
     if lib.vh_abi_version() != 1:
         raise RuntimeError("vihds_b200: ABI version mismatch")
     _lib = lib

@@ -172,6 +172,27 @@ __global__ void adam_kernel(size_t n, R* __restrict__ p, const R* __restrict__ g
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
+// graph-capturable variant: hyper-parameters and step counter are read from device memory
+template <typename R>
+__global__ void adam_dev_kernel(size_t n, R* __restrict__ p, const R* __restrict__ g, R* __restrict__ m, R* __restrict__ v,
+                                const double* __restrict__ hyper, const long long* __restrict__ step) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double t = (double)(step[0] + 1);
+  const double lr = hyper[0], b1d = hyper[1], b2d = hyper[2];
+  const R b1 = (R)b1d, b2 = (R)b2d, eps = (R)hyper[3];
+  const R bc1 = (R)(1.0 - pow(b1d, t));
+  const R bc2_sqrt = (R)sqrt(1.0 - pow(b2d, t));
+  const R gi = g[i];
+  const R mi = m[i] + (gi - m[i]) * (R(1) - b1);
+  const R vi = b2 * v[i] + (R(1) - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  const R denom = vsqrt(vi) / bc2_sqrt + eps;
+  p[i] -= ((R)lr / bc1) * (mi / denom);
+}
+__global__ void step_inc_kernel(long long* step) { step[0] += 1; }
+
 static int dr_num_weights(const vh_problem* p) {
   if (!model_is_dyn(p->model) || p->model == VH_MODEL_DR_BLACKBOX) return 0;
   const int nin = model_species(p->model) + 1;
@@ -400,6 +421,31 @@ int vh_adam_step(int dtype, size_t n, void* param, const void* grad, void* exp_a
     return VH_ERR_INVALID;
   }
   return check_launch("adam_kernel");
+}
+
+int vh_adam_step_dev(int dtype, size_t n, void* param, const void* grad, void* exp_avg, void* exp_avg_sq, const void* hyper,
+                     void* step, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper || !step) {
+    set_error("vh_adam_step_dev: bad arguments");
+    return VH_ERR_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (n > 0) {
+    const int block = 256;
+    const unsigned grid = (unsigned)((n + block - 1) / block);
+    if (dtype == VH_F32)
+      adam_dev_kernel<float><<<grid, block, 0, s>>>(n, (float*)param, (const float*)grad, (float*)exp_avg, (float*)exp_avg_sq,
+                                                     (const double*)hyper, (const long long*)step);
+    else if (dtype == VH_F64)
+      adam_dev_kernel<double><<<grid, block, 0, s>>>(n, (double*)param, (const double*)grad, (double*)exp_avg,
+                                                      (double*)exp_avg_sq, (const double*)hyper, (const long long*)step);
+    else {
+      set_error("unknown dtype %d", dtype);
+      return VH_ERR_INVALID;
+    }
+  }
+  step_inc_kernel<<<1, 1, 0, s>>>((long long*)step);
+  return check_launch("adam_dev_kernel");
 }
 
 }  // extern "C"

@@ -1,0 +1,282 @@
+"""ODE model plugins: ``LOOKUP[name] -> OdeModel subclass`` (reference: models/__init__.py:19-35, vihds/ode.py:28-96).
+
+In the reference a plugin carries the right-hand side as PyTorch code (models/dr_constant.py:14-112, ...).  Here a
+plugin is a DESCRIPTOR: it names the CUDA kernel family that inlines its right-hand side (``kernel_model``), lists the
+species, owns the decoder's trainable weights (NeuralPrecisions / black-box MLPs, packed into the flat layout the
+kernel reads) and does the host-side conditioning of theta.  ``simulate`` / ``observe`` / ``initialize_state`` keep
+the reference's signatures; all arithmetic happens in libvihds_b200.so.
+"""
+import torch
+from torch import nn
+
+from . import _lib as L
+from .engine import ElboProblem, SimulateTrace
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# precisions (vihds/precisions.py)
+# ---------------------------------------------------------------------------------------------------------------
+class ConstantPrecisions(nn.Module):
+    """precisions.py:18-38: the four observation precisions are sampled global parameters, constant in time."""
+
+    dynamic = False
+
+    def __init__(self, precision_vars):
+        super().__init__()
+        self.precision_vars = list(precision_vars)
+
+    def expand(self, theta, n_times, x_states):
+        planes = torch.stack([getattr(theta, v) for v in self.precision_vars], dim=2)  # [B, IW, 4]
+        return x_states, planes.unsqueeze(3).expand(-1, -1, -1, n_times)
+
+    def flat_weights(self):
+        return None
+
+    def summaries(self, _writer, _epoch):
+        pass
+
+
+class NeuralPrecisions(nn.Module):
+    """precisions.py:41-103: four extra ODE states driven by a small net on [t, species(, constants)].  The layers
+    keep the reference's names (state_dict compatible) and initialisation order; ``flat_weights`` packs them in the
+    kernel's layout: [hidden W, b,] production W, b, degradation W, b."""
+
+    dynamic = True
+
+    def __init__(self, n_inputs, n_hidden_precisions, n_outputs=4, inverse=False):
+        super().__init__()
+        if inverse:
+            raise NotImplementedError("inverse NeuralPrecisions has no kernel (unused by every spec of the reference)")
+        self.n_inputs, self.n_outputs, self.n_hidden = n_inputs, n_outputs, int(n_hidden_precisions)
+        n_in = n_inputs + 1
+        if self.n_hidden < 1:
+            self.prec_production = nn.Linear(n_in, n_outputs)
+            nn.init.xavier_uniform_(self.prec_production.weight)
+            self.prec_degradation = nn.Linear(n_in, n_outputs)
+            nn.init.xavier_uniform_(self.prec_degradation.weight)
+        else:
+            self.prec_hidden = nn.Linear(n_in, self.n_hidden)
+            nn.init.xavier_uniform_(self.prec_hidden.weight)
+            self.prec_production = nn.Linear(self.n_hidden, n_outputs)
+            nn.init.xavier_uniform_(self.prec_production.weight, gain=0.5)
+            self.prec_degradation = nn.Linear(self.n_hidden, n_outputs)
+            nn.init.xavier_uniform_(self.prec_degradation.weight, gain=1)
+
+    def layers(self):
+        names = (["prec_hidden"] if self.n_hidden >= 1 else []) + ["prec_production", "prec_degradation"]
+        return [getattr(self, n) for n in names]
+
+    def flat_weights(self):
+        return torch.cat([t.reshape(-1) for lin in self.layers() for t in (lin.weight, lin.bias)])
+
+    def expand(self, theta, _n_times, x_states):
+        return x_states[:, :, :-self.n_outputs, :], x_states[:, :, -self.n_outputs:, :]
+
+    def summaries(self, writer, epoch):
+        pass
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# plugin base
+# ---------------------------------------------------------------------------------------------------------------
+def _draw_conditioner_weight(n_inputs):
+    """The reference builds a FRESH ``DeviceConditioner`` on every call (vihds/ode.py:48, :99-116): a bias-free
+    Linear(n_inputs, 1) whose weight ends up N(2, 1.5), after the default and the xavier initialisers have consumed
+    their share of the torch CPU RNG stream.  Reproduced draw for draw so that a seeded run matches."""
+    lin = nn.Linear(n_inputs, 1, False)
+    nn.init.xavier_uniform_(lin.weight)
+    nn.init.normal_(lin.weight, mean=2.0, std=1.5)
+    return lin.weight.detach()
+
+
+class OdeModel(nn.Module):
+    """vihds/ode.py:28-96.  Subclasses set ``kernel_model`` (a models.LOOKUP key with a kernel), ``species``,
+    ``n_species``, ``precisions`` and ``conditioned`` (names handed to the kernel as per-trajectory extras)."""
+
+    kernel_model = None
+    conditioned = ()
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.device_depth = config.data.device_depth
+        self.n_treatments = len(config.data.conditions)
+        self.use_laplace = bool(config.params.get("use_laplace", False))
+        if self.use_laplace:
+            raise NotImplementedError("use_laplace: log_prob_laplace raises in the reference (training.py:36-38)")
+        self.relevance = config.data.relevance_vectors
+        self.default_devices = config.data.default_devices
+        self.precisions = None
+        self.species = None
+        self.n_species = None
+        self._problems = {}
+
+    # -- engine plumbing ----------------------------------------------------------------------------------------
+    def net_dims(self):
+        return dict(n_hidden=getattr(self.precisions, "n_hidden", 0) if self.precisions is not None else 0)
+
+    def problem(self, names, kinds, priors, extras, device, dtype):
+        """ElboProblem for this model under the current solver / dtype (cached per signature)."""
+        key = (tuple(names), tuple(extras), self.config.params.solver, str(device), dtype)
+        if key not in self._problems:
+            p_mu, p_prec, lo, hi = priors
+            self._problems[key] = ElboProblem(
+                self.kernel_model, self.config.params.solver, dtype, names, kinds, p_mu, p_prec, lo, hi, extras=extras,
+                device=device, C_treat=self.n_treatments, D_dev=self.device_depth, **self.net_dims())
+        return self._problems[key]
+
+    def flat_weights(self):
+        return self.precisions.flat_weights() if self.precisions is not None else None
+
+    # -- reference surface --------------------------------------------------------------------------------------
+    def device_conditioner(self, param, param_name, dev_1hot, use_bias=False, activation="relu"):
+        """vihds/ode.py:43-58 including its quirks: random weights per call and the ``repeat([n_iwae, 1])`` +
+        reshape that assigns row (b*IW + i) % B of the conditioner output to sample (b, i)."""
+        n_batch, n_iwae = param.shape
+        w = _draw_conditioner_weight(dev_1hot.shape[1]).to(dev_1hot)
+        rel = torch.as_tensor(self.relevance[param_name]).to(dev_1hot)
+        cond = torch.relu((dev_1hot * rel) @ w.t())
+        cond = cond.repeat([n_iwae, 1])
+        flat = param.reshape(n_iwae * n_batch, 1)
+        out = flat * (1.0 + cond) if param_name in self.default_devices else flat * cond
+        return out.reshape(n_batch, n_iwae)
+
+    def condition_theta(self, theta, dev_1hot, writer, epoch):
+        raise NotImplementedError("TODO: write your condition_theta")
+
+    def conditioned_extras(self, B, IW, dev_1hot):
+        """[E, N] planes of the conditioned values, in ``self.conditioned`` order (None when E == 0)."""
+        return None
+
+    def initialize_state(self, theta, treatments):
+        raise NotImplementedError("TODO: write your initialize_state")
+
+    def simulate(self, config, times, theta, conditions, dev_1hot, condition_on_device=True):
+        """vihds/ode.py:66-82: theta (DotOperatorSamples of [B, IW] tensors, already clipped / conditioned) ->
+        [B, IW, S, T], S = species + dynamic-precision states; a strided view of the kernel's [T][S][N] trace."""
+        names = [k for k in theta.keys]
+        for extra in self.conditioned:
+            if hasattr(theta, extra) and extra not in names:
+                names.append(extra)
+        first = theta.values[0]
+        B, IW = first.shape
+        dtype = first.dtype
+        prob = self.problem((), (), (None, None, None, None), (), first.device, dtype)
+        src = prob.simulate_variant(names)
+        planes = torch.stack([getattr(theta, n).reshape(B * IW) for n in names])
+        xs = SimulateTrace.apply(prob, src, planes, self.flat_weights(), times, conditions, dev_1hot, B, IW)
+        return xs.view(times.numel(), prob.S, B, IW).permute(2, 3, 1, 0)
+
+    @classmethod
+    def observe(cls, x_sample, _theta):
+        """vihds/ode.py:84-93 -- provided for callers that hold a trace; the fused path takes x_predict from the
+        kernel instead."""
+        od = x_sample[:, :, 0, :]
+        return torch.stack([od, od * x_sample[:, :, 1, :], od * (x_sample[:, :, 2, :] + x_sample[:, :, 4, :]),
+                            od * (x_sample[:, :, 3, :] + x_sample[:, :, 5, :])], dim=2)
+
+    def expand_precisions(self, theta, times, x_states):
+        return self.precisions.expand(theta, len(times), x_states)
+
+    def summaries(self, writer, epoch):
+        pass
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# double-receiver family (models/dr_constant.py:114-215)
+# ---------------------------------------------------------------------------------------------------------------
+class DR_Constant(OdeModel):
+    kernel_model = "dr_constant"
+    conditioned = ("aR", "aS")
+    version = 1
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.precisions = ConstantPrecisions(["prec_x", "prec_rfp", "prec_yfp", "prec_cfp"])
+        self.species = ["OD", "RFP", "YFP", "CFP", "F530", "F480", "LuxR", "LasR"]
+        self.n_species = 8
+        self.device = config.device
+
+    def condition_theta(self, theta, dev_1hot, writer, epoch):
+        """models/dr_constant.py:124-131: aR, aS = conditioner(ones) -- plain attributes, not sampled entries."""
+        B, IW = theta.get_n_batch(), theta.get_n_samples()
+        ones = torch.ones(B, IW, dtype=dev_1hot.dtype, device=dev_1hot.device)
+        theta.aR = self.device_conditioner(ones, "aR", dev_1hot)
+        theta.aS = self.device_conditioner(ones, "aS", dev_1hot)
+        return theta
+
+    def conditioned_extras(self, B, IW, dev_1hot):
+        ones = torch.ones(B, IW, dtype=dev_1hot.dtype, device=dev_1hot.device)
+        aR = self.device_conditioner(ones, "aR", dev_1hot)
+        aS = self.device_conditioner(ones, "aS", dev_1hot)
+        return torch.stack([aR.reshape(-1), aS.reshape(-1)])
+
+    def initialize_state(self, theta, _treatments):
+        zero = torch.zeros_like(theta.init_x)
+        rows = [theta.init_x, theta.init_rfp, theta.init_yfp, theta.init_cfp, zero, zero, theta.init_luxR, theta.init_lasR]
+        if self.precisions.dynamic:
+            rows += [theta.init_prec_x, theta.init_prec_rfp, theta.init_prec_yfp, theta.init_prec_cfp]
+        return torch.stack(rows, dim=2)
+
+
+class DR_Constant_V2(DR_Constant):
+    kernel_model = "dr_constant_v2"
+    version = 2
+
+
+class DR_Constant_Precisions(DR_Constant):
+    kernel_model = "dr_constant_precisions"
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.precisions = NeuralPrecisions(self.n_species, config.params.n_hidden_decoder_precisions, 4)
+
+
+class DR_Constant_Precisions_V2(DR_Constant_Precisions):
+    kernel_model = "dr_constant_precisions_v2"
+    version = 2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# relay (models/relay_constant.py:137-263; the reference classes are broken as shipped -- SURVEY.md section 8c --
+# the behaviour reproduced is that of the two-line monkeypatch recorded in tests/golden/_ref_harness.py)
+# ---------------------------------------------------------------------------------------------------------------
+class Relay_Constant(DR_Constant):
+    kernel_model = "relay_constant"
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.species = ["OD", "RFP", "YFP", "CFP", "F530", "F480", "LuxR", "LasR", "LuxI", "LasI", "C6", "C12"]
+        self.n_species = 12
+
+    def initialize_state(self, theta, treatments):
+        zero = torch.zeros_like(theta.init_x)
+        c = torch.clamp(torch.exp(treatments) - 1.0, 1e-12, 1e6)
+        c6, c12 = c[:, 0:1].expand_as(zero), c[:, 1:2].expand_as(zero)
+        rows = [theta.init_x, theta.init_rfp, theta.init_yfp, theta.init_cfp, zero, zero, theta.init_luxR, theta.init_lasR,
+                theta.init_luxI, theta.init_lasI, c6, c12]
+        if self.precisions.dynamic:
+            rows += [theta.init_prec_x, theta.init_prec_rfp, theta.init_prec_yfp, theta.init_prec_cfp]
+        return torch.stack(rows, dim=2)
+
+
+class Relay_Constant_Precisions(Relay_Constant):
+    kernel_model = "relay_constant_precisions"
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.precisions = NeuralPrecisions(self.n_species, config.params.n_hidden_decoder_precisions, 4)
+
+
+LOOKUP = {
+    "dr_constant": DR_Constant,
+    "dr_constant_v2": DR_Constant_V2,
+    "dr_constant_precisions": DR_Constant_Precisions,
+    "dr_constant_precisions_v2": DR_Constant_Precisions_V2,
+    "relay_constant": Relay_Constant,
+    "relay_constant_precisions": Relay_Constant_Precisions,
+}
+
+
+def kernel_available(name):
+    return name in LOOKUP and L.load().vh_model_id(LOOKUP[name].kernel_model.encode()) >= 0

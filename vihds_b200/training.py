@@ -1,0 +1,295 @@
+"""Training: IWAE cost, the ELBO-gradient step and its CUDA-graph form.
+
+Takes over the hot part of vihds/training.py (reference): ``Training.cost`` (:127-174), ``Training._run_batch``
+(:324-340) and the Adam / MultiStepLR set-up (:82-86).  Orchestration that has no performance content (TensorBoard,
+plotting, cross-validation merge) is out of scope.
+
+Two equivalent ways to take a step:
+
+* ``Training._run_batch(batch)``   eager, reference-shaped: ``model(batch, IW)`` -> ``cost`` -> ``backward`` -> Adam.
+  Every arithmetic op of the hot path is a launch of libvihds_b200.so through engine.* autograd Functions.
+* ``GraphedStep``                  the production form: static device buffers, the encoder forward and the encoder
+  backward + gradient all-reduce + Adam captured as two CUDA graphs, with the four hot-path launches (fused forward,
+  IWAE forward / backward, fused reverse sweep) issued between them through pre-built C-ABI descriptors on the same
+  stream -- no allocation, no Python tensor work and ~4 ctypes calls per step.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .config import Settings
+from .datasets import batch_of
+from .engine import FlatAdam, IwaeCost, _ptr, _stream, iw_moments
+
+
+class Results(object):
+    """Evaluation output (vihds/utils.py:65-99): importance-weighted trace moments, reduced on the device by
+    vh_iw_moments so that the [B, IW, ., T] traces never travel to the host."""
+
+    def __init__(self):
+        self.species_names = self.q_names = self.q_values = self.theta = self.elbo = None
+        self.iw_predict_mu = self.iw_predict_std = self.iw_states = self.iw_variance = None
+
+    def init(self, species_names, q, theta, elbo, normalized_iws, x_predict, x_states, precisions):
+        terms = theta.terms
+        prob = terms["problem"]
+        B, IW = normalized_iws.shape
+        prec_planes = None
+        if not prob.dynamic_precisions:
+            names = ["prec_x", "prec_rfp", "prec_yfp", "prec_cfp"]
+            prec_planes = torch.stack([theta.samples[n].reshape(-1) for n in names]).contiguous()
+        mu, sd, st, var = iw_moments(prob, normalized_iws.reshape(-1), terms["trace"], terms["predict"], prec_planes, B, IW)
+        self.species_names = species_names
+        self.q_names = q.get_tensor_names()
+        self.q_values = np.array([x.detach().cpu().numpy() for x in q.get_tensors()], dtype=object)
+        self.theta = np.array([x.detach().cpu().numpy() for x in theta.get_tensors()])
+        self.elbo = elbo.detach().cpu().numpy()
+        self.iw_predict_mu, self.iw_predict_std = mu.cpu().numpy(), sd.cpu().numpy()
+        self.iw_states, self.iw_variance = st.cpu().numpy(), var.cpu().numpy()
+
+
+def multistep_lr(base_lr, boundaries, gamma, epoch):
+    """torch.optim.lr_scheduler.MultiStepLR (training.py:84-86) as a pure function of the epoch."""
+    return base_lr * gamma ** sum(1 for b in boundaries if epoch >= b)
+
+
+class Training(object):
+    def __init__(self, args, settings, data, parameters, model):
+        self.args, self.settings, self.dataset_pair, self.model = args, settings, data, model
+        self.parameters = parameters
+        self.optimizer = FlatAdam(model.parameters(recurse=True), lr=settings.params.learning_rate)
+        self.model.n_theta = parameters.n_theta
+        self.n_batch = min(settings.params.n_batch, data.n_train) if data is not None else settings.params.n_batch
+        self.epoch = 0
+        if data is not None:
+            dev, dt = settings.device, settings.dtype
+            self.train_data = batch_of(data.train.dataset, data.train.indices, dev, dt)
+            self.valid_data = batch_of(data.test.dataset, data.test.indices, dev, dt)
+
+    # -- cost (training.py:127-174) -----------------------------------------------------------------------------
+    def cost(self, batch_data, batch_results, theta, q, p, full_output=False, writer=None, epoch=None, b_total=None):
+        """IWAE cost from the per-sample terms the fused kernel attached to ``theta``; ``.elbo`` is the NEGATIVE
+        bound, as in the reference (:174)."""
+        x_states, x_predict, precisions = batch_results
+        terms = getattr(theta, "terms", None)
+        if terms is None:
+            raise RuntimeError("cost() needs the theta returned by BaseVAE.forward / Decoder.fused (it carries the "
+                               "per-sample ELBO terms computed by the CUDA kernel); there is no PyTorch fallback")
+        lpx = terms["log_p_by_species"]
+        B, IW = lpx.shape[0], lpx.shape[1]
+        cost, log_w, w = IwaeCost.apply(lpx.reshape(B * IW, 4), p.log_prob(theta).reshape(-1), q.log_prob(theta).reshape(-1),
+                                        B, IW, b_total or B)
+        if not full_output:
+            return Settings(elbo=cost[0])
+        out = Results()
+        out.init(self.model.decoder.state_names, q, theta, -cost[0], w.view(B, IW), x_predict, x_states, precisions)
+        out.log_unnormalized_iws = log_w.view(B, IW)
+        return out
+
+    # -- eager step (training.py:324-340) -----------------------------------------------------------------------
+    def _run_batch(self, batch, u=None):
+        result, theta, q, p = self.model(batch, self.args.train_samples, u=u)
+        elbo = self.cost(batch, result, theta, q, p).elbo
+        if torch.isnan(elbo):
+            print("\nELBO is NaN. Stopping training.")
+            return False
+        self.optimizer.zero_grad()
+        elbo.backward()
+        self.optimizer.step()
+        self.last_cost = elbo.detach()
+        return True
+
+    def set_epoch(self, epoch):
+        self.epoch = epoch
+        p = self.settings.params
+        self.optimizer.set_lr(multistep_lr(p.learning_rate, p.learning_boundaries, p.learning_gamma, epoch))
+
+    def evaluate(self, data, samples):
+        """training.py:267-300 without plotting: full-output cost on a whole data set."""
+        with torch.no_grad():
+            result, theta, q, p = self.model(data, samples)
+            return self.cost(data, result, theta, q, p, full_output=True)
+
+    def run(self, epochs=None, loader=None, verbose=True):
+        """Epoch loop (training.py:342-383) over shuffled mini-batches drawn with numpy's global RNG."""
+        epochs = epochs or self.args.epochs
+        ds, ids = self.dataset_pair.train.dataset, np.asarray(self.dataset_pair.train.indices)
+        for epoch in range(1, epochs + 1):
+            self.set_epoch(epoch - 1)
+            order = torch.randperm(len(ids)).numpy()
+            for s in range(0, len(ids), self.n_batch):
+                batch = batch_of(ds, ids[order[s:s + self.n_batch]], self.settings.device, self.settings.dtype)
+                if not self._run_batch(batch):
+                    return False
+            test_epoch = getattr(self.args, "test_epoch", 0)
+            if test_epoch and epoch % test_epoch == 0:
+                out = self.evaluate(self.valid_data, self.args.test_samples)
+                if verbose:
+                    print("epoch %4d | valid iwae-elbo = %0.4f" % (epoch, float(out.elbo)))
+        return True
+
+
+class GraphedStep(object):
+    """One ELBO-gradient step over static buffers (see module docstring).
+
+    b_total       denominator of the batch mean (global batch when individuals are sharded over ranks)
+    process_group torch.distributed group for the single gradient all-reduce (None: one GPU)
+    """
+
+    def __init__(self, training, B, IW, T, b_total=None, process_group=None, use_graphs=True):
+        self.tr, self.model = training, training.model
+        m = self.model
+        dev, dt = training.settings.device, training.settings.dtype
+        self.B, self.IW, self.T, self.N = B, IW, T, B * IW
+        self.b_total = b_total or B
+        self.pg = process_group
+        self.use_graphs = use_graphs
+        enc, ode = m.encoder, m.decoder.ode_model
+        P = enc.parameters.n_theta
+        self.P = P
+        z = lambda *s: torch.zeros(*s, dtype=dt, device=dev)  # noqa: E731
+        Cn, Dn = ode.n_treatments, ode.device_depth
+        self.batch = Settings(times=z(T), inputs=z(B, Cn), dev_1hot=z(B, Dn), observations=z(B, 4, T))
+        self.u = z(self.N, P)
+        self.extras = list(ode.conditioned) if m.decoder.condition_on_device else []
+        self.cond_w = z(max(1, len(self.extras)), Dn)
+        self.rel = [torch.as_tensor(np.asarray(ode.relevance[n])).to(device=dev, dtype=dt) for n in self.extras]
+        prior = m.prior_tables(dt)
+        self.prob = ode.problem(enc.names, enc.kinds, prior, self.extras, dev, dt)
+        S = self.prob.S
+        N = self.N
+        self.buf = Settings(theta=z(P, N), x_states=z(T, S, N), lpx=z(N, 4), lp=z(N), lq=z(N), cost=z(1), log_w=z(N), w=z(N),
+                            g_lpx=z(N, 4), g_lp=z(N), g_lq=z(N), d_q_mu=z(B, P), d_q_prec=z(B, P))
+        self.d_weights = z(self.prob.n_weights) if self.prob.n_weights else None
+        self.ready = False
+        self.steps_done = 0
+        self.ev_hot = None  # optional (start, end) CUDA events around the reverse-sweep kernel
+
+    # -- the three segments -------------------------------------------------------------------------------------
+    def _pre(self):
+        """encoder forward + device conditioning (stock PyTorch; captured)."""
+        enc, ode = self.model.encoder, self.model.decoder.ode_model
+        self.q_mu, self.q_prec = enc.q_table(self.batch)
+        self.q_mu, self.q_prec = self.q_mu.contiguous(), self.q_prec.contiguous()
+        if self.extras and getattr(self, "extras_override", None) is not None:
+            self.extra = self.extras_override  # tests: pin the (random, per-call) conditioner to recorded values
+        elif self.extras:
+            rows = []
+            for k, name in enumerate(self.extras):
+                cond = torch.relu((self.batch.dev_1hot * self.rel[k]) @ self.cond_w[k:k + 1].t())
+                cond = cond.repeat([self.IW, 1]).reshape(self.N)
+                rows.append(1.0 + cond if name in ode.default_devices else cond)
+            self.extra = torch.stack(rows).contiguous()
+        else:
+            self.extra = None
+        w = ode.flat_weights()
+        self.weights = w.contiguous() if w is not None else None
+
+    def _build_descriptors(self):
+        pr, b, bt = self.prob, self.buf, self.batch
+        self._p = pr.problem(self.B, self.IW, self.T)
+        self._fio = L.vh_fwd_io(
+            times=_ptr(bt.times), u=_ptr(self.u), q_mu=_ptr(self.q_mu), q_prec=_ptr(self.q_prec), p_mu=_ptr(pr.p_mu),
+            p_prec=_ptr(pr.p_prec), clip_lo=_ptr(pr.clip_lo), clip_hi=_ptr(pr.clip_hi), kind=_ptr(pr.kind),
+            extra=_ptr(self.extra), treatments=_ptr(bt.inputs), dev_1hot=_ptr(bt.dev_1hot),
+            observations=_ptr(bt.observations), weights=_ptr(self.weights), theta=_ptr(b.theta),
+            x_states=_ptr(b.x_states), x_predict=None, logp_by_species=_ptr(b.lpx), logp_theta=_ptr(b.lp),
+            logq_theta=_ptr(b.lq))
+        self._bio = L.vh_bwd_io(fwd=self._fio, g_logp_by_species=_ptr(b.g_lpx), g_logp_theta=_ptr(b.g_lp),
+                                g_logq_theta=_ptr(b.g_lq), d_q_mu=_ptr(b.d_q_mu), d_q_prec=_ptr(b.d_q_prec),
+                                d_weights=_ptr(self.d_weights))
+        self._bio.fwd.theta = None
+
+    def _hot(self):
+        """The hot path: four launches of libvihds_b200.so on the current stream."""
+        lib, b, s = self.prob.lib, self.buf, _stream()
+        vdt = self.prob.vh_dtype
+        L.check(lib.vh_elbo_terms_fwd(C.byref(self._p), C.byref(self._fio), s))
+        L.check(lib.vh_iwae_fwd(vdt, self.B, self.IW, self.b_total, _ptr(b.lpx), _ptr(b.lp), _ptr(b.lq), _ptr(b.cost),
+                                _ptr(b.log_w), _ptr(b.w), s))
+        L.check(lib.vh_iwae_bwd(vdt, self.B, self.IW, self.b_total, _ptr(b.w), None, _ptr(b.g_lpx), _ptr(b.g_lp),
+                                _ptr(b.g_lq), s))
+        if self.ev_hot is not None:
+            self.ev_hot[0].record()
+        L.check(lib.vh_elbo_terms_bwd(C.byref(self._p), C.byref(self._bio), s))
+        if self.ev_hot is not None:
+            self.ev_hot[1].record()
+
+    def _post(self):
+        """encoder backward, ONE gradient all-reduce, fused Adam (captured)."""
+        opt = self.tr.optimizer
+        opt.zero_grad()
+        outs, grads = [self.q_mu, self.q_prec], [self.buf.d_q_mu, self.buf.d_q_prec]
+        if self.weights is not None and self.weights.requires_grad:
+            outs.append(self.weights)
+            grads.append(self.d_weights)
+        torch.autograd.backward(outs, grads)
+        if self.pg is not None:
+            torch.distributed.all_reduce(opt.grad, group=self.pg)
+        opt.step()
+
+    # -- capture / replay ---------------------------------------------------------------------------------------
+    def prepare(self):
+        """Warm up eagerly on a side stream, then capture the pre and post segments."""
+        if self.ready:
+            return
+        if not self.use_graphs:
+            self.ready = True
+            return
+        opt = self.tr.optimizer
+        snap = [t.clone() for t in (opt.flat, opt.exp_avg, opt.exp_avg_sq, opt.step_dev)]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._pre()
+                self._build_descriptors()
+                self._hot()
+                self._post()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.g_pre, self.g_post = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_pre):
+            self._pre()
+        self._build_descriptors()
+        self.g_pre.replay()
+        self._hot()
+        with torch.cuda.graph(self.g_post, pool=self.g_pre.pool()):
+            self._post()
+        torch.cuda.synchronize()
+        for t, s in zip((opt.flat, opt.exp_avg, opt.exp_avg_sq, opt.step_dev), snap):
+            t.copy_(s)  # warm-up and capture passes must not count as training steps
+        self.ready = True
+
+    def load_batch(self, batch, non_blocking=True):
+        for k in ("times", "inputs", "dev_1hot", "observations"):
+            self.batch[k].copy_(batch[k], non_blocking=non_blocking)
+
+    def load_u(self, u, non_blocking=True):
+        self.u.copy_(u.reshape(self.N, self.P), non_blocking=non_blocking)
+
+    def draw_conditioner(self):
+        """Fresh conditioner weights per step from the torch CPU RNG (reference quirk, vihds/ode.py:48)."""
+        from .models import _draw_conditioner_weight
+
+        if self.extras:
+            w = torch.cat([_draw_conditioner_weight(self.cond_w.shape[1]) for _ in self.extras], 0)
+            self.cond_w.copy_(w.to(self.cond_w.dtype), non_blocking=True)
+
+    def step(self):
+        """One step on whatever the static buffers hold.  Returns the cost (device tensor, no sync)."""
+        self.prepare()
+        if self.use_graphs:
+            self.g_pre.replay()
+            self._hot()
+            self.g_post.replay()
+        else:
+            self._pre()
+            self._build_descriptors()
+            self._hot()
+            self._post()
+        self.steps_done += 1
+        return self.buf.cost
