@@ -235,8 +235,8 @@ def time_oracle(case, steps, warmup):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dr_constant_icml", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=None, help="individuals per GPU (default: the workload's)")
@@ -244,6 +244,7 @@ def main():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=8)
+    ap.add_argument("--spin", type=float, default=1.5, help="seconds of untimed steps before the warm-up (clock ramp)")
     a = ap.parse_args()
 
     import torch
@@ -309,6 +310,17 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
+    # clock ramp: an idle B200 sits at ~120 MHz SM clock and needs a few hundred ms of load to reach its boost
+    # clocks; spin untimed steps for ~a.spin seconds first (on top of the W warm-up steps), sampling clocks from here on
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_spin = time.perf_counter()
+    n_spin = 0
+    while time.perf_counter() - t_spin < a.spin:
+        for _ in range(20):
+            gs.load_u(u_dev[n_spin % n_pool])
+            gs.step()
+            n_spin += 1
+        torch.cuda.synchronize()
     # device-resident pass: inputs already in HBM, CUDA-event timing, L2 flushed between steps
     for i in range(a.warmup):
         gs.load_u(u_dev[i % n_pool])
@@ -317,7 +329,6 @@ def main():
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     wall0 = time.perf_counter()
     for i in range(a.steps):
         flush.zero_()
@@ -329,7 +340,6 @@ def main():
         ev[i][1].record()
     barrier()
     wall = time.perf_counter() - wall0
-    clocks = sampler.stop() if sampler is not None else None
     gs.ev_hot = None
     step_ms = np.array([s.elapsed_time(e) for s, e in ev])
     bwd_ms = np.array([s.elapsed_time(e) for s, e in kev])
@@ -367,6 +377,7 @@ def main():
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e_step = float(t.item())
 
+    clocks = sampler.stop() if sampler is not None else None
     # per-launch device times of the hot launches (eager, L2 flushed), for the "kernels" breakdown
     kern = {}
     if rank == 0:

@@ -12,7 +12,7 @@ VH_F32, VH_F64 = 0, 1
 KIND_CONSTANT, KIND_NORMAL, KIND_LOGNORMAL = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libvihds_b200.so")
+LIB_PATH = os.environ.get("VIHDS_B200_LIB") or os.path.join(_HERE, "csrc", "libvihds_b200.so")  # env: kernel experiments
 
 
 class vh_problem(C.Structure):

@@ -17,10 +17,20 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-int launch_fwd_f32(const vh_problem*, const vh_fwd_io*, cudaStream_t);
-int launch_fwd_f64(const vh_problem*, const vh_fwd_io*, cudaStream_t);
-int launch_bwd_f32(const vh_problem*, const vh_bwd_io*, cudaStream_t);
-int launch_bwd_f64(const vh_problem*, const vh_bwd_io*, cudaStream_t);
+// white-box instantiations, one translation unit each (vh_inst.cu): inst_<dir>_<dtype>_m<vh_model>
+#define VH_DECL_MODEL(m)                                                      \
+  int inst_fwd_f32_m##m(const vh_problem*, const vh_fwd_io*, cudaStream_t); \
+  int inst_fwd_f64_m##m(const vh_problem*, const vh_fwd_io*, cudaStream_t); \
+  int inst_bwd_f32_m##m(const vh_problem*, const vh_bwd_io*, cudaStream_t); \
+  int inst_bwd_f64_m##m(const vh_problem*, const vh_bwd_io*, cudaStream_t);
+VH_DECL_MODEL(0) VH_DECL_MODEL(1) VH_DECL_MODEL(2) VH_DECL_MODEL(3) VH_DECL_MODEL(4) VH_DECL_MODEL(5)
+#undef VH_DECL_MODEL
+typedef int (*fwd_fn)(const vh_problem*, const vh_fwd_io*, cudaStream_t);
+typedef int (*bwd_fn)(const vh_problem*, const vh_bwd_io*, cudaStream_t);
+static const fwd_fn kFwd[2][6] = {{inst_fwd_f32_m0, inst_fwd_f32_m1, inst_fwd_f32_m2, inst_fwd_f32_m3, inst_fwd_f32_m4, inst_fwd_f32_m5},
+                                  {inst_fwd_f64_m0, inst_fwd_f64_m1, inst_fwd_f64_m2, inst_fwd_f64_m3, inst_fwd_f64_m4, inst_fwd_f64_m5}};
+static const bwd_fn kBwd[2][6] = {{inst_bwd_f32_m0, inst_bwd_f32_m1, inst_bwd_f32_m2, inst_bwd_f32_m3, inst_bwd_f32_m4, inst_bwd_f32_m5},
+                                  {inst_bwd_f64_m0, inst_bwd_f64_m1, inst_bwd_f64_m2, inst_bwd_f64_m3, inst_bwd_f64_m4, inst_bwd_f64_m5}};
 int launch_bb_fwd(const vh_problem*, const vh_fwd_io*, cudaStream_t);
 int launch_bb_bwd(const vh_problem*, const vh_bwd_io*, cudaStream_t);
 
@@ -283,10 +293,15 @@ static int run_fwd(const vh_problem* p, const vh_fwd_io* io, void* stream) {
   }
   cudaStream_t s = (cudaStream_t)stream;
   if (p->model == VH_MODEL_DR_BLACKBOX) return launch_bb_fwd(p, io, s);
-  if (p->dtype == VH_F32) return launch_fwd_f32(p, io, s);
-  if (p->dtype == VH_F64) return launch_fwd_f64(p, io, s);
-  set_error("unknown dtype %d", p->dtype);
-  return VH_ERR_INVALID;
+  if (p->dtype != VH_F32 && p->dtype != VH_F64) {
+    set_error("unknown dtype %d", p->dtype);
+    return VH_ERR_INVALID;
+  }
+  if (!model_is_dr_family(p->model)) {
+    set_error("model %d has no kernel", p->model);
+    return VH_ERR_UNSUPPORTED;
+  }
+  return kFwd[p->dtype][p->model](p, io, s);
 }
 
 static int run_bwd(const vh_problem* p, const vh_bwd_io* io, void* stream) {
@@ -300,10 +315,15 @@ static int run_bwd(const vh_problem* p, const vh_bwd_io* io, void* stream) {
   }
   cudaStream_t s = (cudaStream_t)stream;
   if (p->model == VH_MODEL_DR_BLACKBOX) return launch_bb_bwd(p, io, s);
-  if (p->dtype == VH_F32) return launch_bwd_f32(p, io, s);
-  if (p->dtype == VH_F64) return launch_bwd_f64(p, io, s);
-  set_error("unknown dtype %d", p->dtype);
-  return VH_ERR_INVALID;
+  if (p->dtype != VH_F32 && p->dtype != VH_F64) {
+    set_error("unknown dtype %d", p->dtype);
+    return VH_ERR_INVALID;
+  }
+  if (!model_is_dr_family(p->model)) {
+    set_error("model %d has no kernel", p->model);
+    return VH_ERR_UNSUPPORTED;
+  }
+  return kBwd[p->dtype][p->model](p, io, s);
 }
 
 int vh_elbo_terms_fwd(const vh_problem* p, const vh_fwd_io* io, void* stream) { return run_fwd(p, io, stream); }

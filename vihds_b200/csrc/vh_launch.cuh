@@ -70,8 +70,11 @@ __global__ void __launch_bounds__(128) elbo_fwd_kernel(const Call<typename M::re
   if (n < a.N) traj_forward<M, TB>(a, n, w);
 }
 
+#ifndef VH_BWD_MINB
+#define VH_BWD_MINB 1
+#endif
 template <class M, class TB>
-__global__ void __launch_bounds__(128) elbo_bwd_kernel(const Call<typename M::real> a) {
+__global__ void __launch_bounds__(128, VH_BWD_MINB) elbo_bwd_kernel(const Call<typename M::real> a) {
   typedef typename M::real R;
   constexpr int NW = NetInfo<M>::NW;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -160,42 +163,36 @@ struct BwdLauncher {
   }
 };
 
-template <typename R>
-int launch_fwd(const vh_problem* p, const vh_fwd_io* io, cudaStream_t stream) {
+template <class M>
+int launch_fwd_model(const vh_problem* p, const vh_fwd_io* io, cudaStream_t stream) {
+  typedef typename M::real R;
   FwdLauncher<R> f;
   if (const char* err = build_call<R>(p, io, nullptr, f.a)) {
     set_error("vh_elbo_terms_fwd: %s", err);
     return VH_ERR_INVALID;
   }
   f.stream = stream;
-  if (!model_is_dr_family(p->model)) {
-    set_error("model %d has no kernel in this translation unit", p->model);
-    return VH_ERR_UNSUPPORTED;
-  }
-  if (model_is_dyn(p->model) && p->n_hidden != 0) {
+  if (M::DYN && p->n_hidden != 0) {
     set_error("NeuralPrecisions with a hidden layer (n_hidden=%d) is not implemented for the white-box models yet", p->n_hidden);
     return VH_ERR_UNSUPPORTED;
   }
-  return dispatch_dr<R>(p->model, p->solver, f);
+  return dispatch_solver<M>(p->solver, f);
 }
 
-template <typename R>
-int launch_bwd(const vh_problem* p, const vh_bwd_io* io, cudaStream_t stream) {
+template <class M>
+int launch_bwd_model(const vh_problem* p, const vh_bwd_io* io, cudaStream_t stream) {
+  typedef typename M::real R;
   BwdLauncher<R> f;
   if (const char* err = build_call<R>(p, &io->fwd, io, f.a)) {
     set_error("vh_elbo_terms_bwd: %s", err);
     return VH_ERR_INVALID;
   }
   f.stream = stream;
-  if (!model_is_dr_family(p->model)) {
-    set_error("model %d has no kernel in this translation unit", p->model);
-    return VH_ERR_UNSUPPORTED;
-  }
-  if (model_is_dyn(p->model) && p->n_hidden != 0) {
+  if (M::DYN && p->n_hidden != 0) {
     set_error("NeuralPrecisions with a hidden layer (n_hidden=%d) is not implemented for the white-box models yet", p->n_hidden);
     return VH_ERR_UNSUPPORTED;
   }
-  return dispatch_dr<R>(p->model, p->solver, f);
+  return dispatch_solver<M>(p->solver, f);
 }
 
 }  // namespace vh

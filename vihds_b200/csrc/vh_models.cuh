@@ -64,6 +64,7 @@ struct DrModel {
 
   struct Consts {
     R v[NC];
+    R iK, iKlux, iKlas;  // reciprocals of K, Klux, Klas: not differentiated themselves (their cotangent goes to v[C_K]...)
   };
 
   VH_HD static constexpr bool uses(int s) {
@@ -123,7 +124,12 @@ struct DrModel {
       v[C_k12] = th[S_KC12] * th[S_rc];
       v[C_Klux] = th[S_Klux];
       v[C_Klas] = th[S_Klas];
+      c.iKlux = R(1) / v[C_Klux];
+      c.iKlas = R(1) / v[C_Klas];
+    } else {
+      c.iKlux = c.iKlas = R(0);
     }
+    c.iK = R(1) / v[C_K];
   }
 
   // d f / d (Ka, Kb, n) for the version-1 Hill fraction, following torch's pow backward
@@ -238,31 +244,30 @@ struct DrModel {
     }
   }
 
-  // intermediates shared by rhs and rhs_vjp
+  // intermediates shared by rhs and rhs_vjp (the reverse sweep keeps them between the stage evaluation and its vjp)
   struct Mid {
-    R sg, gr, g, gam, bR, bS, d76, d81, P76, P81;
+    R sg, gr, g, gam, bR, bS, i76, i81, P76, P81;
   };
 
-  VH_HD static void mid(R t, const R* x, const R* v, Mid& m) {
+  VH_HD static void mid(R t, const R* x, const Consts& c, Mid& m) {
+    const R* v = c.v;
     m.sg = sigmoid(R(4) * (t - v[C_tlag]));
     m.gr = v[C_r] * m.sg;
-    m.g = R(1) - x[0] / v[C_K];
+    m.g = R(1) - x[0] * c.iK;
     m.gam = m.gr * m.g;
     m.bR = x[6] * x[6] * v[C_fR];
     m.bS = x[7] * x[7] * v[C_fS];
     const R a76 = v[C_KGR76] * m.bR, b76 = v[C_KGS76] * m.bS;
     const R a81 = v[C_KGR81] * m.bR, b81 = v[C_KGS81] * m.bS;
-    m.d76 = R(1) + a76 + b76;
-    m.d81 = R(1) + a81 + b81;
-    m.P76 = (v[C_e76] + a76 + b76) / m.d76;
-    m.P81 = (v[C_e81] + a81 + b81) / m.d81;
+    m.i76 = vdiv(R(1), R(1) + a76 + b76);
+    m.i81 = vdiv(R(1), R(1) + a81 + b81);
+    m.P76 = (v[C_e76] + a76 + b76) * m.i76;
+    m.P81 = (v[C_e81] + a81 + b81) * m.i81;
   }
 
-  // species part of the right-hand side (dx[0..NS))
-  VH_HD static void rhs(R t, const R* x, const Consts& c, R* dx) {
+  // species part of the right-hand side (dx[0..NS)) from precomputed intermediates
+  VH_HD static void rhs_from(const R* x, const Consts& c, const Mid& m, R* dx) {
     const R* v = c.v;
-    Mid m;
-    mid(t, x, v, m);
     dx[0] = m.gam * x[0];
     dx[1] = v[C_rc] - (m.gam + v[C_drfp]) * x[1];
     dx[2] = v[C_cY] * m.P81 - (m.gam + v[C_dyfp]) * x[2];
@@ -274,17 +279,21 @@ struct DrModel {
     if (RELAY) {
       dx[8] = v[C_rc] * m.P81 - (m.gam + v[C_dluxI]) * x[8];
       dx[9] = v[C_rc] * m.P76 - (m.gam + v[C_dlasI]) * x[9];
-      dx[10] = (v[C_k6] * x[0] * x[8]) / (R(1) + x[8] / v[C_Klux]);
-      dx[11] = (v[C_k12] * x[0] * x[9]) / (R(1) + x[9] / v[C_Klas]);
+      dx[10] = vdiv(v[C_k6] * x[0] * x[8], R(1) + x[8] * c.iKlux);
+      dx[11] = vdiv(v[C_k12] * x[0] * x[9], R(1) + x[9] * c.iKlas);
     }
   }
 
-  // g: cotangent of dx[0..NS)  ->  gx (accumulated), gc (accumulated)
-  VH_HD static void rhs_vjp(R t, const R* x, const Consts& c, const R* g, R* gx, Consts& gcs) {
+  VH_HD static void rhs(R t, const R* x, const Consts& c, R* dx) {
+    Mid m;
+    mid(t, x, c, m);
+    rhs_from(x, c, m, dx);
+  }
+
+  // g: cotangent of dx[0..NS)  ->  gx (accumulated), gc (accumulated); m = mid(t, x, c)
+  VH_HD static void rhs_vjp_from(const R* x, const Consts& c, const Mid& m, const R* g, R* gx, Consts& gcs) {
     const R* v = c.v;
     R* gc = gcs.v;
-    Mid m;
-    mid(t, x, v, m);
     R ggam = g[0] * x[0] - g[1] * x[1] - g[2] * x[2] - g[3] * x[3] - g[4] * x[4] - g[5] * x[5] - g[6] * x[6] - g[7] * x[7];
     gx[0] += g[0] * m.gam;
     gx[1] -= g[1] * (m.gam + v[C_drfp]);
@@ -318,34 +327,34 @@ struct DrModel {
       gP81 += g[8] * v[C_rc];
       gP76 += g[9] * v[C_rc];
       {
-        const R den = R(1) + x[8] / v[C_Klux];
-        const R gnum = g[10] / den;
-        const R val = (v[C_k6] * x[0] * x[8]) / den;
+        const R iden = vdiv(R(1), R(1) + x[8] * c.iKlux);
+        const R gnum = g[10] * iden;
+        const R val = (v[C_k6] * x[0] * x[8]) * iden;
         const R gden = -gnum * val;
         gc[C_k6] += gnum * x[0] * x[8];
         gx[0] += gnum * v[C_k6] * x[8];
-        gx[8] += gnum * v[C_k6] * x[0] + gden / v[C_Klux];
-        gc[C_Klux] -= gden * x[8] / (v[C_Klux] * v[C_Klux]);
+        gx[8] += gnum * v[C_k6] * x[0] + gden * c.iKlux;
+        gc[C_Klux] -= gden * x[8] * (c.iKlux * c.iKlux);
       }
       {
-        const R den = R(1) + x[9] / v[C_Klas];
-        const R gnum = g[11] / den;
-        const R val = (v[C_k12] * x[0] * x[9]) / den;
+        const R iden = vdiv(R(1), R(1) + x[9] * c.iKlas);
+        const R gnum = g[11] * iden;
+        const R val = (v[C_k12] * x[0] * x[9]) * iden;
         const R gden = -gnum * val;
         gc[C_k12] += gnum * x[0] * x[9];
         gx[0] += gnum * v[C_k12] * x[9];
-        gx[9] += gnum * v[C_k12] * x[0] + gden / v[C_Klas];
-        gc[C_Klas] -= gden * x[9] / (v[C_Klas] * v[C_Klas]);
+        gx[9] += gnum * v[C_k12] * x[0] + gden * c.iKlas;
+        gc[C_Klas] -= gden * x[9] * (c.iKlas * c.iKlas);
       }
     }
     // gamma = gr * g,  gr = r * sg,  g = 1 - x0 / K
     const R ggr = ggam * m.g, gg = ggam * m.gr;
     gc[C_r] += ggr * m.sg;
     gc[C_tlag] -= R(4) * ggr * v[C_r] * m.sg * (R(1) - m.sg);
-    gx[0] -= gg / v[C_K];
-    gc[C_K] += gg * x[0] / (v[C_K] * v[C_K]);
+    gx[0] -= gg * c.iK;
+    gc[C_K] += gg * x[0] * (c.iK * c.iK);
     // promoter activities P = (e + a + b) / (1 + a + b)
-    const R gn76 = gP76 / m.d76, gn81 = gP81 / m.d81;
+    const R gn76 = gP76 * m.i76, gn81 = gP81 * m.i81;
     gc[C_e76] += gn76;
     gc[C_e81] += gn81;
     const R ga76 = gn76 * (R(1) - m.P76), ga81 = gn81 * (R(1) - m.P81);
@@ -359,6 +368,12 @@ struct DrModel {
     gx[7] += gbS * R(2) * x[7] * v[C_fS];
     gc[C_fR] += gbR * x[6] * x[6];
     gc[C_fS] += gbS * x[7] * x[7];
+  }
+
+  VH_HD static void rhs_vjp(R t, const R* x, const Consts& c, const R* g, R* gx, Consts& gcs) {
+    Mid m;
+    mid(t, x, c, m);
+    rhs_vjp_from(x, c, m, g, gx, gcs);
   }
 
   // observe, vihds/ode.py:84-93

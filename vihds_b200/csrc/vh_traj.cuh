@@ -89,17 +89,30 @@ struct StridedGW {  // element k of this thread's accumulators lives at base[k *
 template <class M>
 struct Rhs {
   typedef typename M::real R;
+  typedef typename M::Mid Mid;
   typename M::Consts c;
   const R* w;  // NeuralPrecisions weights (shared memory on the device), unused for constant precisions
 
   VH_HD void eval(R t, const R* x, R* dx) const {
-    M::rhs(t, x, c, dx);
+    Mid m;
+    eval_keep(t, x, dx, m);
+  }
+  // same, handing back the species intermediates so that the reverse sweep need not recompute them
+  VH_HD void eval_keep(R t, const R* x, R* dx, Mid& m) const {
+    M::mid(t, x, c, m);
+    M::rhs_from(x, c, m, dx);
     if (M::DYN) LinPrecNet<R, M::NIN>::rhs(t, x, x + M::NS, w, dx + M::NS);
   }
   template <typename GW>
-  VH_HD void vjp(R t, const R* x, const R* g, R* gx, typename M::Consts& gc, GW gw) const {
-    M::rhs_vjp(t, x, c, g, gx, gc);
+  VH_HD void vjp_kept(R t, const R* x, const Mid& m, const R* g, R* gx, typename M::Consts& gc, GW gw) const {
+    M::rhs_vjp_from(x, c, m, g, gx, gc);
     if (M::DYN) LinPrecNet<R, M::NIN>::rhs_vjp(t, x, x + M::NS, w, g + M::NS, gx, gx + M::NS, gw);
+  }
+  template <typename GW>
+  VH_HD void vjp(R t, const R* x, const R* g, R* gx, typename M::Consts& gc, GW gw) const {
+    Mid m;
+    M::mid(t, x, c, m);
+    vjp_kept(t, x, m, g, gx, gc, gw);
   }
 };
 
@@ -146,7 +159,9 @@ VH_HD void rk_step_vjp(const Rhs<M>& f, typename M::real t0, typename M::real t1
   typedef typename M::real R;
   constexpr int S = M::S;
   constexpr int s = TB::s;
-  R k[s > 1 ? s - 1 : 1][S];  // the last stage derivative is never needed to rebuild a stage state
+  constexpr int nk = s > 1 ? s - 1 : 1;
+  R k[nk][S];               // the last stage derivative is never needed to rebuild a stage state
+  typename M::Mid kept[nk];  // intermediates of the stages that had to be re-evaluated: reused by their vjp
 #pragma unroll
   for (int i = 0; i + 1 < s; ++i) {
     R X[S];
@@ -159,7 +174,7 @@ VH_HD void rk_step_vjp(const Rhs<M>& f, typename M::real t0, typename M::real t1
 #pragma unroll
         for (int q = 0; q < S; ++q) X[q] += ha * k[j][q];
       }
-    f.eval(stage_time<TB, R>(i, t0, t1), X, k[i]);
+    f.eval_keep(stage_time<TB, R>(i, t0, t1), X, k[i], kept[i]);
   }
   R gk[s][S];
 #pragma unroll
@@ -181,7 +196,10 @@ VH_HD void rk_step_vjp(const Rhs<M>& f, typename M::real t0, typename M::real t1
 #pragma unroll
         for (int q = 0; q < S; ++q) X[q] += ha * k[j][q];
       }
-    f.vjp(stage_time<TB, R>(i, t0, t1), X, gk[i], gX, gc, gw);
+    if (i + 1 < s)
+      f.vjp_kept(stage_time<TB, R>(i, t0, t1), X, kept[i], gk[i], gX, gc, gw);
+    else
+      f.vjp(stage_time<TB, R>(i, t0, t1), X, gk[i], gX, gc, gw);
 #pragma unroll
     for (int q = 0; q < S; ++q) lam[q] += gX[q];
 #pragma unroll
@@ -198,7 +216,7 @@ VH_HD void rk_step_vjp(const Rhs<M>& f, typename M::real t0, typename M::real t1
 // theta: sample, clip, log-probabilities
 // ---------------------------------------------------------------------------------------------------------------
 template <typename R>
-VH_HD R sample_column(const Call<R>& a, int n, int b, int k, R& lq, R& lp) {
+VH_HD R sample_column(const Call<R>& a, int n, int b, int k, R& lq, R& lp, bool store = true) {
   const int kind = a.kind[k];
   const R mu = a.q_mu[b * a.P + k];
   R th;
@@ -216,13 +234,13 @@ VH_HD R sample_column(const Call<R>& a, int n, int b, int k, R& lq, R& lp) {
     lq += -Lim<R>::log2pi + R(0.5) * vlog(prec + R(1e-12)) - R(0.5) * prec * (mu - x) * (mu - x) - jac;
     lp += -Lim<R>::log2pi + R(0.5) * vlog(pp + R(1e-12)) - R(0.5) * pp * (pm - x) * (pm - x) - jac;
   }
-  if (a.theta) a.theta[(size_t)k * a.N + n] = th;
+  if (store && a.theta) a.theta[(size_t)k * a.N + n] = th;
   return th;
 }
 
 template <class M>
 VH_HD void load_theta(const Call<typename M::real>& a, int n, int b, typename M::real* th, typename M::real& lq,
-                      typename M::real& lp) {
+                      typename M::real& lp, bool store = true) {
   typedef typename M::real R;
 #pragma unroll
   for (int s = 0; s < M::NSLOT; ++s) {
@@ -230,11 +248,11 @@ VH_HD void load_theta(const Call<typename M::real>& a, int n, int b, typename M:
     if (!M::uses(s)) continue;
     const int src = a.slot_src[s];
     if (src >= 0)
-      th[s] = sample_column(a, n, b, src, lq, lp);
+      th[s] = sample_column(a, n, b, src, lq, lp, store);
     else if (src != VH_SLOT_UNUSED)
       th[s] = a.extra[(size_t)(-1 - src) * a.N + n];
   }
-  for (int j = 0; j < a.n_free; ++j) sample_column(a, n, b, a.free_cols[j], lq, lp);
+  for (int j = 0; j < a.n_free; ++j) sample_column(a, n, b, a.free_cols[j], lq, lp, store);
 }
 
 // cotangent of one sampled column -> (d mu, d prec) of q for this trajectory
@@ -277,7 +295,9 @@ VH_HD void column_vjp(const Call<R>& a, int n, int b, int k, R gth, R glq, R glp
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// forward trajectory
+// forward trajectory.  Trace pointers are bumped by one time slab (S*N resp. 4*N elements) per step and the next
+// step's observations / grid time are fetched one iteration ahead, so the loop carries no 64-bit index arithmetic
+// and no exposed load latency.
 // ---------------------------------------------------------------------------------------------------------------
 template <class M, class TB>
 VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M::real* w) {
@@ -285,49 +305,71 @@ VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M
   constexpr int S = M::S, NS = M::NS;
   const int b = n / a.IW;
   const size_t N = a.N;
-  R th[M::NSLOT];
-  R lq = R(0), lp = R(0);
-  load_theta<M>(a, n, b, th, lq, lp);
-  R c6, c12;
-  M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
+  const int T = a.T;
   Rhs<M> f;
   f.w = w;
-  M::setup(th, c6, c12, f.c);
   R x[S];
-  M::init_state(th, c6, c12, x);
   R prec[4], lprec[4], ll[4];
+  R lq = R(0), lp = R(0);
+  {
+    R th[M::NSLOT];
+    load_theta<M>(a, n, b, th, lq, lp);
+    R c6, c12;
+    M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
+    M::setup(th, c6, c12, f.c);
+    M::init_state(th, c6, c12, x);
 #pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    prec[o] = M::DYN ? R(1) : th[S_prec_x + o];
-    lprec[o] = M::DYN ? R(0) : vlog(prec[o]);
-    ll[o] = R(0);
+    for (int o = 0; o < 4; ++o) {
+      prec[o] = M::DYN ? R(1) : th[S_prec_x + o];
+      lprec[o] = M::DYN ? R(0) : vlog(prec[o]);
+      ll[o] = R(0);
+    }
   }
   const R h0 = a.times[1] - a.times[0];
-  const R* obs = a.obs ? a.obs + (size_t)b * 4 * a.T : nullptr;
-  for (int k = 0; k < a.T; ++k) {
-    if (a.x_states) {
+  const R* obs = a.obs ? a.obs + (size_t)b * 4 * T : nullptr;
+  R* xs = a.x_states ? a.x_states + n : nullptr;
+  R* xpr = a.x_predict ? a.x_predict + n : nullptr;
+  R ob[4] = {R(0), R(0), R(0), R(0)};
+  if (obs) {
 #pragma unroll
-      for (int q = 0; q < S; ++q) a.x_states[((size_t)k * S + q) * N + n] = x[q];
+    for (int o = 0; o < 4; ++o) ob[o] = obs[o * T];
+  }
+  R t0 = a.times[0], t1 = a.times[1];
+  for (int k = 0; k < T; ++k) {
+    // fetch what the NEXT iteration consumes
+    R obn[4] = {R(0), R(0), R(0), R(0)};
+    const int kn = k + 1 < T ? k + 1 : k;
+    if (obs) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) obn[o] = obs[o * T + kn];
+    }
+    const R t2 = a.times[k + 2 < T ? k + 2 : T - 1];
+    if (xs) {
+#pragma unroll
+      for (int q = 0; q < S; ++q) xs[(size_t)q * N] = x[q];
+      xs += (size_t)S * N;
     }
     R xp[4];
     M::observe(x, xp);
-    if (a.x_predict) {
+    if (xpr) {
 #pragma unroll
-      for (int o = 0; o < 4; ++o) a.x_predict[((size_t)k * 4 + o) * N + n] = xp[o];
+      for (int o = 0; o < 4; ++o) xpr[(size_t)o * N] = xp[o];
+      xpr += (size_t)4 * N;
     }
     if (obs) {
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
         const R pr = M::DYN ? x[NS + o] : prec[o];
         const R lpr = M::DYN ? vlog(pr) : lprec[o];
-        const R d = xp[o] - obs[o * a.T + k];
+        const R d = xp[o] - ob[o];
         ll[o] += R(-0.5) * (Lim<R>::log2pi - lpr + pr * d * d);
       }
     }
-    if (k + 1 < a.T) {
-      const R t0 = a.times[k], t1 = a.times[k + 1];
-      rk_step<M, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x);
-    }
+    if (k + 1 < T) rk_step<M, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x);
+    t0 = t1;
+    t1 = t2;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) ob[o] = obn[o];
   }
   if (a.logp_species) {
 #pragma unroll
@@ -340,6 +382,10 @@ VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M
 // ---------------------------------------------------------------------------------------------------------------
 // reverse trajectory.  RED: functor that folds (d mu, d prec) of column k of individual b into d_q_mu/d_q_prec
 // (warp-aggregated atomics on the device, plain adds on the host).
+// Register budget: theta (up to NSLOT values) is only needed before the time loop (RHS constants) and after it
+// (chain rule through setup / clip / sample), so it is re-derived from u after the loop instead of being kept
+// alive across it; the loop itself carries x, the prefetched previous checkpoint, lambda, the constants and their
+// cotangents.
 // ---------------------------------------------------------------------------------------------------------------
 template <class M, class TB, typename GW, typename RED>
 VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, const typename M::real* w, GW gw, RED red) {
@@ -347,61 +393,83 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
   constexpr int S = M::S, NS = M::NS;
   const int b = n / a.IW;
   const size_t N = a.N;
+  const int T = a.T;
   R gth[M::NSLOT];
 #pragma unroll
   for (int s = 0; s < M::NSLOT; ++s) gth[s] = R(0);
   R glq = R(0), glp = R(0);
-  R c6 = R(0), c12 = R(0);
   if (active) {
-    R th[M::NSLOT];
-    R lq = R(0), lp = R(0);
-    Call<R> a2 = a;
-    a2.theta = nullptr;  // do not rewrite theta in the reverse pass
-    load_theta<M>(a2, n, b, th, lq, lp);
-    M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
     Rhs<M> f;
     f.w = w;
-    M::setup(th, c6, c12, f.c);
+    R prec[4], iprec[4];
+    {
+      R th[M::NSLOT];
+      R lq = R(0), lp = R(0), c6, c12;
+      load_theta<M>(a, n, b, th, lq, lp, false);  // never rewrite theta in the reverse pass
+      M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
+      M::setup(th, c6, c12, f.c);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        prec[o] = M::DYN ? R(1) : th[S_prec_x + o];
+        iprec[o] = R(1) / prec[o];
+      }
+    }
     typename M::Consts gc;
 #pragma unroll
     for (int i = 0; i < M::NC; ++i) gc.v[i] = R(0);
-    R prec[4], gprec[4], gl[4];
+    R gprec[4], gl[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
-      prec[o] = M::DYN ? R(1) : th[S_prec_x + o];
       gprec[o] = R(0);
       gl[o] = a.g_logp_species ? a.g_logp_species[(size_t)n * 4 + o] : R(0);
     }
     glq = a.g_logq_theta ? a.g_logq_theta[n] : R(0);
     glp = a.g_logp_theta ? a.g_logp_theta[n] : R(0);
     const R h0 = a.times[1] - a.times[0];
-    const R* obs = a.obs ? a.obs + (size_t)b * 4 * a.T : nullptr;
+    const R* obs = a.obs ? a.obs + (size_t)b * 4 * T : nullptr;
+    const size_t slab = (size_t)S * N;
+    const R* xs = a.x_states + (size_t)(T - 1) * slab + n;             // checkpoint at time k
+    const R* gxs = a.g_x_states ? a.g_x_states + (size_t)(T - 1) * slab + n : nullptr;
+    const R* gxpr = a.g_x_predict ? a.g_x_predict + (size_t)(T - 1) * 4 * N + n : nullptr;
     R lam[S], x[S], xprev[S];
+    R ob[4] = {R(0), R(0), R(0), R(0)}, obp[4] = {R(0), R(0), R(0), R(0)};
 #pragma unroll
     for (int q = 0; q < S; ++q) {
       lam[q] = R(0);
-      x[q] = a.x_states[((size_t)(a.T - 1) * S + q) * N + n];
+      x[q] = xs[(size_t)q * N];
+      xprev[q] = x[q];
     }
-    for (int k = a.T - 1; k >= 0; --k) {
-      if (k > 0) {  // prefetch the previous checkpoint while this step's adjoint is computed
+    if (obs) {
 #pragma unroll
-        for (int q = 0; q < S; ++q) xprev[q] = a.x_states[((size_t)(k - 1) * S + q) * N + n];
+      for (int o = 0; o < 4; ++o) ob[o] = obs[o * T + T - 1];
+    }
+    R t0 = a.times[T - 1], t1 = t0;  // interval [t0, t1] = [times[k], times[k+1]]; unused at k = T-1
+    for (int k = T - 1; k >= 0; --k) {
+      // prefetch what iteration k-1 consumes while this step's adjoint is computed
+      const int kp = k > 0 ? k - 1 : 0;
+      if (k > 0) {
+        xs -= slab;
+#pragma unroll
+        for (int q = 0; q < S; ++q) xprev[q] = xs[(size_t)q * N];
       }
-      if (k + 1 < a.T) {
-        const R t0 = a.times[k], t1 = a.times[k + 1];
-        rk_step_vjp<M, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, lam, gc, gw);
+      if (obs) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) obp[o] = obs[o * T + kp];
       }
+      const R tp = a.times[kp];
+      if (k + 1 < T) rk_step_vjp<M, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, lam, gc, gw);
       // emission at time k
       R xp[4], gxp[4];
       M::observe(x, xp);
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
-        gxp[o] = a.g_x_predict ? a.g_x_predict[((size_t)k * 4 + o) * N + n] : R(0);
+        gxp[o] = gxpr ? gxpr[(size_t)o * N] : R(0);
         if (obs) {
           const R pr = M::DYN ? x[NS + o] : prec[o];
-          const R d = xp[o] - obs[o * a.T + k];
+          const R ipr = M::DYN ? vdiv(R(1), pr) : iprec[o];
+          const R d = xp[o] - ob[o];
           gxp[o] -= gl[o] * pr * d;
-          const R gp = gl[o] * R(0.5) * (R(1) / pr - d * d);
+          const R gp = gl[o] * R(0.5) * (ipr - d * d);
           if (M::DYN)
             lam[NS + o] += gp;
           else
@@ -409,13 +477,24 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
         }
       }
       M::observe_vjp(x, gxp, lam);
-      if (a.g_x_states) {
+      if (gxs) {
 #pragma unroll
-        for (int q = 0; q < S; ++q) lam[q] += a.g_x_states[((size_t)k * S + q) * N + n];
+        for (int q = 0; q < S; ++q) lam[q] += gxs[(size_t)q * N];
+        gxs -= slab;
       }
+      if (gxpr) gxpr -= (size_t)4 * N;
 #pragma unroll
       for (int q = 0; q < S; ++q) x[q] = xprev[q];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) ob[o] = obp[o];
+      t1 = t0;
+      t0 = tp;
     }
+    // chain rule back to theta: re-derive theta (cheap) rather than keep it live across the loop
+    R th[M::NSLOT];
+    R lq = R(0), lp = R(0), c6, c12;
+    load_theta<M>(a, n, b, th, lq, lp, false);
+    M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
     M::init_state_vjp(lam, gth);
     M::setup_vjp(th, c6, c12, f.c, gc, gth);
     if (!M::DYN) {
