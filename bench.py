@@ -282,13 +282,10 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the engine has no CPU fallback)"
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    pg = None
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=device)
-        pg = dist.group.WORLD
+    from vihds_b200.distributed import init_from_env
     from vihds_b200.training import GraphedStep
+
+    _, _, pg = init_from_env("nccl", device)
 
     settings, parameters, model, training, host, B, IW, T, rng = build_workload(a.workload, rank, world, device, a.batch, a.iw)
     P, N = parameters.n_theta, B * IW
@@ -313,14 +310,22 @@ def main():
     # clock ramp: an idle B200 sits at ~120 MHz SM clock and needs a few hundred ms of load to reach its boost
     # clocks; spin untimed steps for ~a.spin seconds first (on top of the W warm-up steps), sampling clocks from here on
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    t_spin = time.perf_counter()
-    n_spin = 0
-    while time.perf_counter() - t_spin < a.spin:
-        for _ in range(20):
-            gs.load_u(u_dev[n_spin % n_pool])
+    def run_untimed(k):
+        for j in range(k):
+            gs.load_u(u_dev[j % n_pool])
             gs.step()
-            n_spin += 1
         torch.cuda.synchronize()
+
+    run_untimed(3)
+    t_spin = time.perf_counter()
+    run_untimed(5)
+    per_step = (time.perf_counter() - t_spin) / 5
+    n_spin = int(min(5000, max(0, a.spin / max(per_step, 1e-6))))
+    if world > 1:  # every rank must issue the SAME number of steps (each one contains an all-reduce)
+        t = torch.tensor([n_spin], dtype=torch.int64, device=device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        n_spin = int(t.item())
+    run_untimed(n_spin)
     # device-resident pass: inputs already in HBM, CUDA-event timing, L2 flushed between steps
     for i in range(a.warmup):
         gs.load_u(u_dev[i % n_pool])
@@ -404,9 +409,7 @@ def main():
         kern["elbo_bwd_in_step_us"] = float(bwd_ms.mean()) * 1e3
 
     if rank != 0:
-        if world > 1:
-            torch.distributed.barrier()
-            torch.distributed.destroy_process_group()
+        finish(world)
         return
 
     S, E = gs.prob.S, len(gs.extras)
@@ -448,10 +451,21 @@ def main():
             "value": Bc * IW / sec, "unit": "traj/s", "cores": cores, "kind": "port", "ms_per_step": sec * 1e3,
             "sample": "%d steps of B=%d x IW=%d, T=%d (forward + backward to q; oracle/vihds_oracle.py, torch CPU, %d threads)" % (
                 a.cpu_steps, Bc, IW, T, cores)}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    finish(world)
+
+
+def finish(world):
+    """Leave without tearing the NCCL communicator down: destroy_process_group() blocks while captured CUDA graphs that
+    contain NCCL kernels are still alive (observed on torch 2.11 / NCCL 2.28), and there is nothing left to clean up."""
     if world > 1:
+        import torch
+
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
