@@ -33,6 +33,7 @@ WORKLOADS = {
     # name: (spec, dataset fixture, B per GPU, IW, T or None (= dataset grid))
     "dr_constant_icml": ("dr_constant_icml", "dataset_dr_icml", 36, 200, None),
     "relay_constant_precisions": ("relay_constant_precisions", "dataset_relay", 36, 200, None),
+    "dr_blackbox_icml": ("dr_blackbox_icml", "dataset_dr_icml", 36, 200, None),
     "synthetic_dr_constant": ("dr_constant_icml", "dataset_dr_icml", 1024, 128, 500),
 }
 
@@ -202,14 +203,12 @@ def cpu_case(parameters, model, host, B, IW, rng, solver):
         "observations": host["observations"].numpy(), "q_mu": mu.float().cpu().numpy(), "q_prec": prec.float().cpu().numpy(),
         "p_mu": p_mu, "p_prec": p_prec, "p_sigma": (1.0 / np.sqrt(p_prec)).astype(np.float32),
     }
-    if model.decoder.condition_on_device:
+    if model.decoder.condition_on_device and ode.kernel_model != "dr_blackbox":
         for nm in ode.conditioned:
             case["cond_" + nm] = (1.0 + np.abs(rng.randn(B, IW))).astype(np.float32)
-    w = ode.flat_weights()
-    if w is not None:
-        for lname, lin in zip(("prec_production", "prec_degradation"), ode.precisions.layers()):
-            case["w:ode_model.precisions.%s.weight" % lname] = lin.weight.detach().float().cpu().numpy()
-            case["w:ode_model.precisions.%s.bias" % lname] = lin.bias.detach().float().cpu().numpy()
+    for name, w in model.decoder.named_parameters():
+        case["w:" + name] = w.detach().float().cpu().numpy()
+    case["params"] = dict(model.decoder.config.params)
     return case
 
 

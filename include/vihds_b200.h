@@ -81,7 +81,7 @@ typedef struct vh_problem {
   int P; /* sampled parameters = columns of u (0 in vh_simulate) */
   int C; /* treatments per individual (2: C6, C12) */
   int D; /* device one-hot width (used by the black-box model only) */
-  int E; /* rows of `extra` */
+  int E; /* rows of `extra` (black-box: E == n_y device offsets ADDED to the sampled y_k, see vh_bb.cuh) */
   int n_hidden; /* NeuralPrecisions hidden width (0 = single linear layer), black-box: precision-net hidden width */
   int n_hidden_states; /* black-box NeuralStates hidden width */
   int n_latent; /* black-box latent species */
@@ -89,6 +89,9 @@ typedef struct vh_problem {
   /* slot_src[s]: where model slot s (see vh_slot_name) takes its value from:
    *   >= 0  column of u / theta;   -1-e  row e of `extra`;   VH_SLOT_UNUSED  not provided (value 0). */
   int slot_src[VH_MAX_SLOTS];
+  /* black-box only: initial value of the latent species and of the precision states (params.init_latent_species,
+   * params.init_prec; vihds/config.py:74-75, models/dr_blackbox.py:101-104) */
+  double init_latent_species, init_prec;
 } vh_problem;
 
 /* Forward: replaces, in ONE launch, q.sample + p.clip (vihds/distributions.py:119-142, :76-85), Decoder.forward

@@ -28,9 +28,25 @@ def clip_bounds(case, stddevs=4.0):
     return lo, hi
 
 
+def bb_latent_names(params):
+    return (["z%d" % (i + 1) for i in range(params["n_z"])] + ["x%d" % (i + 1) for i in range(params["n_x"])] +
+            ["y%d" % (i + 1) for i in range(params["n_y"])])
+
+
 def slot_map(case, slot_names):
-    """slot_src for a golden case: theta column if the name is sampled, else an extra row (conditioned aR/aS)."""
+    """slot_src for a golden case: theta column if the name is sampled, else an extra row (conditioned aR/aS).
+    dr_blackbox: slots 4.. are the latent parameters z, x, y; the extra rows are the device offsets added to y."""
     names = [str(n) for n in case["names"]]
+    if str(case["model"]) == "dr_blackbox":
+        par = case["params"]
+        src = [L.VH_SLOT_UNUSED] * L.VH_MAX_SLOTS
+        for s, nm in enumerate(["init_x", "init_rfp", "init_yfp", "init_cfp"] + bb_latent_names(par)):
+            src[s] = names.index(nm)
+        W, b = case["w:ode_model.offset_layer.weight"], case["w:ode_model.offset_layer.bias"]
+        off = case["dev_1hot"].astype(np.float64) @ W.astype(np.float64).T + b  # [B, n_y]
+        IW = case["u"].shape[1]
+        extra = np.stack([np.repeat(off[:, k], IW) for k in range(par["n_y"])]).astype(case["u"].dtype)
+        return src, extra
     src = [L.VH_SLOT_UNUSED] * L.VH_MAX_SLOTS
     extras = []
     for s, name in enumerate(slot_names):
@@ -43,8 +59,17 @@ def slot_map(case, slot_names):
     return src, extra
 
 
+BB_LAYERS = ["neural_states.states_hidden", "neural_states.states_production", "neural_states.states_degradation",
+             "precisions.prec_hidden", "precisions.prec_production", "precisions.prec_degradation"]
+
+
 def flat_weights(case):
-    """Flat decoder weight vector in the library layout (LinPrecNet: Wp, bp, Wd, bd)."""
+    """Flat decoder weight vector in the library layout (LinPrecNet: Wp, bp, Wd, bd; dr_blackbox: vh_bb.cuh)."""
+    if str(case["model"]) == "dr_blackbox":
+        keys = ["%s.%s" % (l, t) for l in BB_LAYERS for t in ("weight", "bias")]
+        w = np.concatenate([case["w:ode_model." + k].reshape(-1) for k in keys])
+        gw = np.concatenate([case["gw:ode_model." + k].reshape(-1) for k in keys])
+        return w, gw
     pre = "w:ode_model.precisions."
     if (pre + "prec_production.weight") not in case or (pre + "prec_hidden.weight") in case:
         return None, None
@@ -91,4 +116,16 @@ def make_problem(case, src, E, n_weights_hidden=0):
     p.C, p.D, p.E = case["inputs"].shape[1], case["dev_1hot"].shape[1], E
     for s in range(L.VH_MAX_SLOTS):
         p.slot_src[s] = src[s]
+    if str(case["model"]) == "dr_blackbox":
+        par = case["params"]
+        p.n_hidden, p.n_hidden_states, p.n_latent = par["n_hidden_decoder_precisions"], par["n_hidden_decoder"], par["n_latent_species"]
+        p.n_z, p.n_x, p.n_y = par["n_z"], par["n_x"], par["n_y"]
+        p.init_latent_species, p.init_prec = par.get("init_latent_species", 0.001), par.get("init_prec", 0.00001)
     return p
+
+
+def offset_layer_grads(case, d_extra):
+    """Gradient of the black-box offset layer from the kernel's d_extra [n_y][N] (chain rule done by torch in the product)."""
+    B, IW, _ = case["u"].shape
+    d_off = d_extra.reshape(d_extra.shape[0], B, IW).sum(2).T.astype(np.float64)  # [B, n_y]
+    return d_off.T @ case["dev_1hot"].astype(np.float64), d_off.sum(0)

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "../../vihds_b200/csrc/vh_dispatch.cuh"
+#include "../../vihds_b200/csrc/vh_bb.cuh"
 
 namespace {
 using namespace vh;
@@ -49,10 +50,53 @@ struct BwdRunner {
   }
 };
 
+// dr_blackbox on the host: same BbRhs / bb_traj_* code, weight gradients accumulated directly
+template <typename R>
+struct BbFwdRunner {
+  const Call<R>* a;
+  template <class F, class TB>
+  int run() {
+    std::vector<R> row(F::ROWL::ROW);
+    for (int n = 0; n < a->N; ++n) bb_traj_forward<F, TB>(*a, n, a->weights, row.data());
+    return 0;
+  }
+};
+template <typename R>
+struct BbBwdRunner {
+  const Call<R>* a;
+  template <class F, class TB>
+  int run() {
+    if (a->bb_nlat + a->C + a->D != F::NC) return VH_ERR_UNSUPPORTED;
+    for (size_t i = 0; i < (size_t)a->B * a->P; ++i) a->d_q_mu[i] = a->d_q_prec[i] = R(0);
+    for (int i = 0; i < F::L::total; ++i) a->d_weights[i] = R(0);
+    HostRed<R> red{a};
+    BbDirectWgrad<F> sink{a->d_weights};
+    std::vector<R> row(F::ROWL::ROW);
+    for (int n = 0; n < a->N; ++n) bb_traj_backward<F, TB>(*a, n, true, a->weights, row.data(), sink, red);
+    return 0;
+  }
+};
+template <class F, class L>
+int bb_solver(int solver, L& f) {
+  typedef typename F::real R;
+  switch (solver) {
+    case VH_SOLVER_EULER: return f.template run<F, TabEuler<R> >();
+    case VH_SOLVER_MIDPOINT: return f.template run<F, TabMidpoint<R> >();
+    case VH_SOLVER_RK4: return f.template run<F, TabRK4_38<R> >();
+    case VH_SOLVER_MODEULER: return f.template run<F, TabHeun<R, true> >();
+    case VH_SOLVER_MODEULERWHILE: return f.template run<F, TabHeun<R, false> >();
+    default: return VH_ERR_UNSUPPORTED;
+  }
+}
+
 template <typename R>
 int fwd_t(const vh_problem* p, const vh_fwd_io* io) {
   Call<R> a;
   if (build_call<R>(p, io, nullptr, a)) return VH_ERR_INVALID;
+  if (p->model == VH_MODEL_DR_BLACKBOX) {
+    BbFwdRunner<R> f{&a};
+    return bb_solver<BbRhs<R, 2, 25, 20, 21> >(p->solver, f);
+  }
   FwdRunner<R> f{&a};
   return dispatch_dr<R>(p->model, p->solver, f);
 }
@@ -60,6 +104,10 @@ template <typename R>
 int bwd_t(const vh_problem* p, const vh_bwd_io* io) {
   Call<R> a;
   if (build_call<R>(p, &io->fwd, io, a)) return VH_ERR_INVALID;
+  if (p->model == VH_MODEL_DR_BLACKBOX) {
+    BbBwdRunner<R> f{&a};
+    return bb_solver<BbRhs<R, 2, 25, 20, 21> >(p->solver, f);
+  }
   size_t nw = model_is_dyn(p->model) ? (size_t)2 * (4 * (model_species(p->model) + 1) + 4) : 0;
   BwdRunner<R> f{&a, nw};
   return dispatch_dr<R>(p->model, p->solver, f);
@@ -73,6 +121,11 @@ extern "C" int hc_bwd(const vh_problem* p, const vh_bwd_io* io) {
   return p->dtype == VH_F64 ? bwd_t<double>(p, io) : bwd_t<float>(p, io);
 }
 extern "C" int hc_num_slots() { return vh::DR_NSLOT; }
+extern "C" const char* hc_build_error(const vh_problem* p, const vh_fwd_io* io) {
+  Call<float> a;
+  const char* e = build_call<float>(p, io, nullptr, a);
+  return e ? e : "";
+}
 extern "C" const char* hc_slot_name(int model, int s) {
   if (vh::model_is_dyn(model) && s >= vh::S_prec_x && s <= vh::S_prec_cfp) return vh::kDrDynPrecNames[s - vh::S_prec_x];
   return vh::kDrSlotNames[s];

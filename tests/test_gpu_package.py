@@ -22,7 +22,8 @@ class Args:
     folds, split, heldout, train_samples, test_samples = 4, 1, None, 8, 8
 
 
-FIXTURE = {"dr_constant_icml": "dataset_dr_icml", "relay_constant_precisions": "dataset_relay"}
+FIXTURE = {"dr_constant_icml": "dataset_dr_icml", "relay_constant_precisions": "dataset_relay",
+           "dr_blackbox_icml": "dataset_dr_icml"}
 
 
 def _rel(a, b):
@@ -62,11 +63,12 @@ def pin_conditioner(model, case):
     ("dr_constant_icml_midpoint_f32_iw8", "dr_constant_icml", None),
     ("dr_constant_one_midpoint_f32_iw5", "dr_constant_one", (4, 100, 2, 1)),
     ("relay_constant_precisions_midpoint_f32_iw8", "relay_constant_precisions", None),
+    ("dr_blackbox_icml_midpoint_f32_iw8", "dr_blackbox_icml", None),
 ])
 def test_model_forward_cost_backward_match_reference(case_name, spec, dims):
     case = load_case(case_name)
     settings, par, model, training = build(spec, dims)
-    if "w:ode_model.precisions.prec_production.weight" in case:  # decoder weights are drawn after the data split in the reference
+    if any(k.startswith("w:") for k in case):  # decoder weights: recorded from the reference run
         sd = {k[2:]: torch.as_tensor(case[k]).cuda() for k in case if k.startswith("w:")}
         model.decoder.load_state_dict(sd)
     pin_conditioner(model, case)

@@ -14,7 +14,7 @@ from vihds_b200 import _lib as L
 
 pytestmark = pytest.mark.gpu
 
-DR_CASES = [c for c in golden_cases() if "blackbox" not in c]
+DR_CASES = golden_cases()
 
 
 def _rel(a, b):
@@ -68,7 +68,8 @@ def run_case_on_gpu(case):
     L.check(lib.vh_iwae_bwd(p.dtype, B, IW, B, _p(wts), None, _p(g["g_logp_by_species"]), _p(g["g_logp_theta"]),
                             _p(g["g_logq_theta"]), None))
     out = dict(d_q_mu=torch.full((B, P), 7.0, dtype=dt, device="cuda"), d_q_prec=torch.full((B, P), 7.0, dtype=dt, device="cuda"),
-               d_weights=None if w is None else torch.full((len(w),), 7.0, dtype=dt, device="cuda"))
+               d_weights=None if w is None else torch.full((len(w),), 7.0, dtype=dt, device="cuda"),
+               d_extra=None if extra is None else torch.zeros(extra.shape, dtype=dt, device="cuda"))
     bio = L.vh_bwd_io(fwd=io, **{k: _p(v) for k, v in {**g, **out}.items()})
     L.check(lib.vh_elbo_terms_bwd(C.byref(p), C.byref(bio), None))
     torch.cuda.synchronize()
@@ -115,6 +116,10 @@ def test_cuda_matches_reference_golden(name):
             assert _rel(got[:, per_ind], ref[:, per_ind]) < gtol
     if r["gw_ref"] is not None:
         assert _rel(r["d_weights"], r["gw_ref"]) < gtol
+    if str(case["model"]) == "dr_blackbox":
+        dW, db = H.offset_layer_grads(case, r["d_extra"])
+        assert _rel(dW, case["gw:ode_model.offset_layer.weight"]) < gtol
+        assert _rel(db, case["gw:ode_model.offset_layer.bias"]) < gtol
 
 
 @pytest.mark.parametrize("name", ["dr_constant_icml_midpoint_f32_iw8", "dr_constant_one_modeuler_f32_iw5"])

@@ -20,7 +20,7 @@ def _rel(a, b):
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-300))
 
 
-DR_CASES = [c for c in golden_cases() if "blackbox" not in c]
+DR_CASES = golden_cases()
 
 
 @pytest.fixture(scope="module")
@@ -40,7 +40,7 @@ def test_host_math_matches_reference(hc, name):
     p = H.make_problem(case, src, 0 if extra is None else extra.shape[0])
     B, IW, P, T = p.B, p.IW, p.P, p.T
     N = B * IW
-    S = {0: 8, 1: 8, 2: 12, 3: 12, 4: 12, 5: 16}[model]
+    S = {0: 8, 1: 8, 2: 12, 3: 12, 4: 12, 5: 16, 6: 10}[model]
     lo, hi = H.clip_bounds(case)
     keep = dict(
         times=case["times"].astype(dt), u=np.ascontiguousarray(case["u"].reshape(N, P)), q_mu=case["q_mu"].astype(dt),
@@ -77,7 +77,8 @@ def test_host_math_matches_reference(hc, name):
     g = g.astype(dt)
     bkeep = dict(g_logp_by_species=np.ascontiguousarray(np.repeat(g[:, None], 4, 1)), g_logp_theta=g, g_logq_theta=(-g).astype(dt),
                  d_q_mu=np.zeros((B, P), dt), d_q_prec=np.zeros((B, P), dt),
-                 d_weights=None if w is None else np.zeros_like(w, dtype=dt))
+                 d_weights=None if w is None else np.zeros_like(w, dtype=dt),
+                 d_extra=None if extra is None else np.zeros_like(extra))
     bio = L.vh_bwd_io(fwd=io, **{k: _ptr(v) for k, v in bkeep.items()})
     assert hc.hc_bwd(C.byref(p), C.byref(bio)) == 0
     gtol = 1e-6 if f64 else 3e-3
@@ -93,3 +94,7 @@ def test_host_math_matches_reference(hc, name):
             assert _rel(got[:, per_ind], ref[:, per_ind]) < gtol
     if w is not None:
         assert _rel(bkeep["d_weights"], gw_ref) < gtol
+    if str(case["model"]) == "dr_blackbox":
+        dW, db = H.offset_layer_grads(case, bkeep["d_extra"])
+        assert _rel(dW, case["gw:ode_model.offset_layer.weight"]) < gtol
+        assert _rel(db, case["gw:ode_model.offset_layer.bias"]) < gtol

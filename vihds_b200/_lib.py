@@ -22,6 +22,7 @@ class vh_problem(C.Structure):
         ("n_hidden", C.c_int), ("n_hidden_states", C.c_int), ("n_latent", C.c_int),
         ("n_z", C.c_int), ("n_x", C.c_int), ("n_y", C.c_int),
         ("slot_src", C.c_int * VH_MAX_SLOTS),
+        ("init_latent_species", C.c_double), ("init_prec", C.c_double),
     ]
 
 

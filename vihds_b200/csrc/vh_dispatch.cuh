@@ -33,6 +33,11 @@ inline const char* build_call(const vh_problem* p, const vh_fwd_io* io, const vh
   if ((long long)p->B * p->IW > 0x7fffffffLL) return "B*IW exceeds int32";
   a.B = p->B; a.IW = p->IW; a.N = p->B * p->IW; a.T = p->T; a.P = p->P; a.C = p->C; a.D = p->D; a.E = p->E;
   if (p->C < 2) return "C (treatments) must be >= 2";
+  a.bb_nlat = p->n_z + p->n_x + p->n_y;
+  a.bb_ny = p->n_y;
+  a.bb_noff = (p->model == VH_MODEL_DR_BLACKBOX && p->P > 0) ? p->E : 0;
+  a.bb_init_latent = (R)p->init_latent_species;
+  a.bb_init_prec = (R)p->init_prec;
   bool used[VH_MAX_SLOTS];
   for (int k = 0; k < VH_MAX_SLOTS; ++k) used[k] = false;
   for (int s = 0; s < VH_MAX_SLOTS; ++s) {
@@ -68,6 +73,12 @@ inline const char* build_call(const vh_problem* p, const vh_fwd_io* io, const vh
     if (!a.x_states) return "backward needs the forward x_states trace";
     if (p->P > 0 && (!a.d_q_mu || !a.d_q_prec)) return "backward with P > 0 needs d_q_mu and d_q_prec";
     if (model_is_dyn(p->model) && !a.d_weights) return "backward of a dynamic-precision model needs d_weights";
+  }
+  if (p->model == VH_MODEL_DR_BLACKBOX) {
+    if (a.bb_nlat + p->C + p->D > 48) return "black-box: n_z + n_x + n_y + C + D exceeds 48";
+    if (4 + a.bb_nlat > VH_MAX_SLOTS) return "black-box: too many latent parameters";
+    if (p->P > 0 && p->E != 0 && p->E != p->n_y) return "black-box: E must be 0 or n_y (device offsets of the y parameters)";
+    if (p->D > 0 && !a.dev_1hot) return "black-box needs dev_1hot";
   }
   return nullptr;
 }

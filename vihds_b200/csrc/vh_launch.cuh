@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(128, VH_BWD_MINB) elbo_bwd_kernel(const Call<t
       atomicAdd(a.d_weights + k, s);
     }
   } else {
-    traj_backward<M, TB>(a, nn, active, w, NoGW<R>(), red);
+    NoGW<R> nogw;
+    traj_backward<M, TB>(a, nn, active, w, nogw, red);
   }
 }
 

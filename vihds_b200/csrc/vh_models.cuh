@@ -420,7 +420,7 @@ struct LinPrecNet {
   }
   // gw: this thread's weight-gradient accumulators, element k at gw[k * gstride]
   template <typename GW>
-  VH_HD static void rhs_vjp(R t, const R* species, const R* v, const R* w, const R* g, R* gspecies, R* gv, GW gw) {
+  VH_HD static void rhs_vjp(R t, const R* species, const R* v, const R* w, const R* g, R* gspecies, R* gv, GW& gw) {
     R a[NIN], ga[NIN];
     a[0] = vtanh(t);
 #pragma unroll

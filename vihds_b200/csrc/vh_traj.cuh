@@ -63,6 +63,8 @@ template <typename R>
 struct Call {
   int B, IW, N, T, P, C, D, E;
   int slot_src[VH_MAX_SLOTS];
+  int bb_nlat, bb_ny, bb_noff;   // dr_blackbox: latent-parameter count (n_z + n_x + n_y), its conditioned tail n_y, offset rows
+  R bb_init_latent, bb_init_prec;
   int n_free;                    // theta columns no model slot reads (they still carry log-prob terms)
   int free_cols[VH_MAX_SLOTS];
   const R *times, *u, *q_mu, *q_prec, *p_mu, *p_prec, *clip_lo, *clip_hi, *extra, *treatments, *dev_1hot, *obs, *weights;
@@ -89,7 +91,11 @@ struct StridedGW {  // element k of this thread's accumulators lives at base[k *
 template <class M>
 struct Rhs {
   typedef typename M::real R;
+  typedef R real;
   typedef typename M::Mid Mid;
+  typedef Mid Kept;                  // what eval_keep hands to vjp_kept
+  typedef typename M::Consts Grad;   // cotangent accumulator of the per-trajectory constants
+  static constexpr int S = M::S;
   typename M::Consts c;
   const R* w;  // NeuralPrecisions weights (shared memory on the device), unused for constant precisions
 
@@ -104,12 +110,12 @@ struct Rhs {
     if (M::DYN) LinPrecNet<R, M::NIN>::rhs(t, x, x + M::NS, w, dx + M::NS);
   }
   template <typename GW>
-  VH_HD void vjp_kept(R t, const R* x, const Mid& m, const R* g, R* gx, typename M::Consts& gc, GW gw) const {
+  VH_HD void vjp_kept(R t, const R* x, const Mid& m, const R* g, R* gx, typename M::Consts& gc, GW& gw) const {
     M::rhs_vjp_from(x, c, m, g, gx, gc);
     if (M::DYN) LinPrecNet<R, M::NIN>::rhs_vjp(t, x, x + M::NS, w, g + M::NS, gx, gx + M::NS, gw);
   }
   template <typename GW>
-  VH_HD void vjp(R t, const R* x, const R* g, R* gx, typename M::Consts& gc, GW gw) const {
+  VH_HD void vjp(R t, const R* x, const R* g, R* gx, typename M::Consts& gc, GW& gw) const {
     Mid m;
     M::mid(t, x, c, m);
     vjp_kept(t, x, m, g, gx, gc, gw);
@@ -124,10 +130,10 @@ VH_HD R stage_time(int i, R t0, R t1) {
 }
 
 // x <- one step of the scheme from t0 to t1 with step size h
-template <class M, class TB>
-VH_HD void rk_step(const Rhs<M>& f, typename M::real t0, typename M::real t1, typename M::real h, typename M::real* x) {
-  typedef typename M::real R;
-  constexpr int S = M::S;
+template <class F, class TB>
+VH_HD void rk_step(const F& f, typename F::real t0, typename F::real t1, typename F::real h, typename F::real* x) {
+  typedef typename F::real R;
+  constexpr int S = F::S;
   R k[TB::s][S];
 #pragma unroll
   for (int i = 0; i < TB::s; ++i) {
@@ -153,15 +159,15 @@ VH_HD void rk_step(const Rhs<M>& f, typename M::real t0, typename M::real t1, ty
 }
 
 // lam: in = dL/dx(t1), out = dL/dx(t0);  x = state at t0;  gc/gw accumulate parameter cotangents
-template <class M, class TB, typename GW>
-VH_HD void rk_step_vjp(const Rhs<M>& f, typename M::real t0, typename M::real t1, typename M::real h,
-                       const typename M::real* x, typename M::real* lam, typename M::Consts& gc, GW gw) {
-  typedef typename M::real R;
-  constexpr int S = M::S;
+template <class F, class TB, typename GW>
+VH_HD void rk_step_vjp(const F& f, typename F::real t0, typename F::real t1, typename F::real h,
+                       const typename F::real* x, typename F::real* lam, typename F::Grad& gc, GW& gw) {
+  typedef typename F::real R;
+  constexpr int S = F::S;
   constexpr int s = TB::s;
   constexpr int nk = s > 1 ? s - 1 : 1;
   R k[nk][S];               // the last stage derivative is never needed to rebuild a stage state
-  typename M::Mid kept[nk];  // intermediates of the stages that had to be re-evaluated: reused by their vjp
+  typename F::Kept kept[nk];  // intermediates of the stages that had to be re-evaluated: reused by their vjp
 #pragma unroll
   for (int i = 0; i + 1 < s; ++i) {
     R X[S];
@@ -365,7 +371,7 @@ VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M
         ll[o] += R(-0.5) * (Lim<R>::log2pi - lpr + pr * d * d);
       }
     }
-    if (k + 1 < T) rk_step<M, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x);
+    if (k + 1 < T) rk_step<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x);
     t0 = t1;
     t1 = t2;
 #pragma unroll
@@ -388,7 +394,7 @@ VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M
 // cotangents.
 // ---------------------------------------------------------------------------------------------------------------
 template <class M, class TB, typename GW, typename RED>
-VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, const typename M::real* w, GW gw, RED red) {
+VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, const typename M::real* w, GW& gw, RED& red) {
   typedef typename M::real R;
   constexpr int S = M::S, NS = M::NS;
   const int b = n / a.IW;
@@ -457,7 +463,7 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
         for (int o = 0; o < 4; ++o) obp[o] = obs[o * T + kp];
       }
       const R tp = a.times[kp];
-      if (k + 1 < T) rk_step_vjp<M, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, lam, gc, gw);
+      if (k + 1 < T) rk_step_vjp<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, lam, gc, gw);
       // emission at time k
       R xp[4], gxp[4];
       M::observe(x, xp);

@@ -50,8 +50,7 @@ class Decoder(nn.Module):
         T = data.times.numel()
         theta = DotOperatorSamples.from_planes(q.names, planes, B, IW)
         if extras:
-            for k, name in enumerate(extras):
-                setattr(theta, name, extra[k].view(B, IW))
+            m.attach_conditioned(theta, extras, extra, B, IW)
         theta.terms = {q: lq.view(B, IW), p: lp.view(B, IW), "log_p_by_species": lpx.view(B, IW, 4), "problem": prob,
                        "trace": xs, "predict": xp if want_predict else None}
         sol = xs.view(T, prob.S, B, IW).permute(2, 3, 1, 0)

@@ -54,7 +54,8 @@ class ElboProblem(object):
     """
 
     def __init__(self, model, solver, dtype, names, kinds, p_mu, p_prec, clip_lo, clip_hi, extras=(), device="cuda",
-                 n_hidden=0, n_hidden_states=0, n_latent=0, n_z=0, n_x=0, n_y=0, C_treat=2, D_dev=1):
+                 n_hidden=0, n_hidden_states=0, n_latent=0, n_z=0, n_x=0, n_y=0, C_treat=2, D_dev=1,
+                 init_latent_species=0.001, init_prec=0.00001, slot_alias=None):
         self.lib = L.load()
         self.model_name, self.solver_name = model, solver
         self.model, self.solver = L.model_id(model), L.solver_id(solver)
@@ -65,9 +66,11 @@ class ElboProblem(object):
         self.P, self.E = len(self.names), len(self.extras)
         self.C, self.D = int(C_treat), int(D_dev)
         self.net = dict(n_hidden=n_hidden, n_hidden_states=n_hidden_states, n_latent=n_latent, n_z=n_z, n_x=n_x, n_y=n_y)
+        self.init_values = (float(init_latent_species), float(init_prec))
+        self.slot_alias = dict(slot_alias or {})  # library slot name -> theta name (dr_blackbox: latent0 -> z1, ...)
         if self.P > L.VH_MAX_SLOTS:
             raise ValueError("more than %d sampled parameters" % L.VH_MAX_SLOTS)
-        self.slot_names = L.slot_names(self.model)
+        self.slot_names = [self.slot_alias.get(nm, nm) for nm in L.slot_names(self.model)]
         self.slot_src = self._slot_map(self.names, self.extras)
         dev = self.device
         td = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(device=dev, dtype=dtype)  # noqa: E731
@@ -76,8 +79,8 @@ class ElboProblem(object):
         self.clip_lo, self.clip_hi = (td(clip_lo), td(clip_hi)) if self.P else (None, None)
         probe = self.problem(1, 1, 2)
         self.S = self.lib.vh_state_width(C.byref(probe))
-        self.n_species = self.S - 4 if self.lib.vh_num_weights(C.byref(probe)) > 0 else self.S
         self.n_weights = int(self.lib.vh_num_weights(C.byref(probe)))
+        self.n_species = self.S - 4 if self.n_weights > 0 else self.S
         self.dynamic_precisions = self.n_weights > 0
 
     def _slot_map(self, names, extras):
@@ -98,6 +101,7 @@ class ElboProblem(object):
         p.C, p.D = self.C, self.D
         for k, v in self.net.items():
             setattr(p, k, int(v))
+        p.init_latent_species, p.init_prec = self.init_values
         src = self.slot_src if slot_src is None else slot_src
         for s in range(L.VH_MAX_SLOTS):
             p.slot_src[s] = src[s]

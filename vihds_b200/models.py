@@ -115,6 +115,11 @@ class OdeModel(nn.Module):
     def net_dims(self):
         return dict(n_hidden=getattr(self.precisions, "n_hidden", 0) if self.precisions is not None else 0)
 
+    def attach_conditioned(self, theta, extras, extra, B, IW):
+        """Expose the conditioned values on theta the way condition_theta does in the reference (plain attributes)."""
+        for k, name in enumerate(extras):
+            setattr(theta, name, extra[k].view(B, IW))
+
     def problem(self, names, kinds, priors, extras, device, dtype):
         """ElboProblem for this model under the current solver / dtype (cached per signature)."""
         key = (tuple(names), tuple(extras), self.config.params.solver, str(device), dtype)
@@ -158,6 +163,7 @@ class OdeModel(nn.Module):
         for extra in self.conditioned:
             if hasattr(theta, extra) and extra not in names:
                 names.append(extra)
+        # conditioned values replace the samples of the same name (condition_theta overwrites the attribute)
         first = theta.values[0]
         B, IW = first.shape
         dtype = first.dtype
@@ -268,7 +274,94 @@ class Relay_Constant_Precisions(Relay_Constant):
         self.precisions = NeuralPrecisions(self.n_species, config.params.n_hidden_decoder_precisions, 4)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# black box (models/dr_blackbox.py:61-125, vihds/ode.py:119-138)
+# ---------------------------------------------------------------------------------------------------------------
+class NeuralStates(nn.Module):
+    """ode.py:119-138: same layer names and initialisation order as the reference (state_dict compatible)."""
+
+    def __init__(self, n_inputs, n_hidden, n_states, n_latents):
+        super().__init__()
+        self.n_latents, self.n_states = n_latents, n_states
+        self.states_hidden = nn.Linear(n_inputs, n_hidden)
+        nn.init.xavier_uniform_(self.states_hidden.weight)
+        self.states_production = nn.Linear(n_hidden, n_states)
+        nn.init.xavier_uniform_(self.states_production.weight)
+        self.states_degradation = nn.Linear(n_hidden, n_states)
+        nn.init.xavier_uniform_(self.states_degradation.weight)
+
+    def layers(self):
+        return [self.states_hidden, self.states_production, self.states_degradation]
+
+
+class DR_Blackbox(OdeModel):
+    """MLP right-hand side over [states, latent parameters, treatments, device one-hot] + a NeuralPrecisions net with
+    a hidden layer; y_k are conditioned on the device through a trainable offset layer (dr_blackbox.py:86-96)."""
+
+    kernel_model = "dr_blackbox"
+
+    def __init__(self, config):
+        super().__init__(config)
+        p = config.params
+        self.n_x, self.n_y, self.n_z = p.n_x, p.n_y, p.n_z
+        n_latents = self.n_x + self.n_y + self.n_z
+        self.n_species = 4
+        self.n_latent_species = p.n_latent_species
+        self.n_hidden_precisions = p.n_hidden_decoder_precisions
+        self.n_states = self.n_species + self.n_latent_species
+        n_inputs = self.n_states + n_latents + self.n_treatments + self.device_depth
+        self.precisions = NeuralPrecisions(n_inputs, self.n_hidden_precisions, 4)
+        self.species = ["OD", "RFP", "YFP", "CFP"]
+        self.n_hidden = p.n_hidden_decoder
+        self.init_latent_species = p.get("init_latent_species", 0.001)
+        self.init_prec = p.get("init_prec", 0.00001)
+        self.offset_layer = nn.Linear(self.device_depth, self.n_y)
+        self.neural_states = NeuralStates(n_inputs, p.n_hidden_decoder, self.n_states, n_latents)
+        self.latent_names = (["z%d" % (i + 1) for i in range(self.n_z)] + ["x%d" % (i + 1) for i in range(self.n_x)] +
+                             ["y%d" % (i + 1) for i in range(self.n_y)])
+        self.conditioned = tuple("offset:y%d" % (i + 1) for i in range(self.n_y))
+
+    def net_dims(self):
+        return dict(n_hidden=self.n_hidden_precisions, n_hidden_states=self.n_hidden, n_latent=self.n_latent_species,
+                    n_z=self.n_z, n_x=self.n_x, n_y=self.n_y, init_latent_species=self.init_latent_species,
+                    init_prec=self.init_prec, slot_alias={"latent%d" % k: nm for k, nm in enumerate(self.latent_names)})
+
+    def flat_weights(self):
+        layers = self.neural_states.layers() + self.precisions.layers()
+        return torch.cat([t.reshape(-1) for lin in layers for t in (lin.weight, lin.bias)])
+
+    def conditioned_extras(self, B, IW, dev_1hot):
+        """[n_y, N] planes of offset_layer(dev_1hot)[:, k]; the kernel adds them to the sampled y_k."""
+        off = self.offset_layer(dev_1hot)
+        return off.t().repeat_interleave(IW, dim=1).contiguous()
+
+    def attach_conditioned(self, theta, extras, extra, B, IW):
+        for k in range(self.n_y):
+            name = "y%d" % (k + 1)
+            setattr(theta, name, theta.samples[name] + extra[k].view(B, IW))
+
+    def condition_theta(self, theta, dev_1hot, writer, epoch):
+        off = self.offset_layer(dev_1hot)
+        for k in range(self.n_y):
+            name = "y%d" % (k + 1)
+            setattr(theta, name, getattr(theta, name) + off[:, k:k + 1])
+        return theta
+
+    def initialize_state(self, theta, _treatments):
+        B, IW = theta.get_n_batch(), theta.get_n_samples()
+        x0 = torch.stack([theta.init_x, theta.init_rfp, theta.init_yfp, theta.init_cfp], dim=2)
+        h0 = torch.full([B, IW, self.n_latent_species], self.init_latent_species, dtype=x0.dtype, device=x0.device)
+        prec0 = torch.full([B, IW, 4], self.init_prec, dtype=x0.dtype, device=x0.device)
+        return torch.cat([x0, h0, prec0], dim=2)
+
+    @classmethod
+    def observe(cls, x_sample, _theta):
+        od = x_sample[:, :, 0, :]
+        return torch.stack([od, od * x_sample[:, :, 1, :], od * x_sample[:, :, 2, :], od * x_sample[:, :, 3, :]], dim=2)
+
+
 LOOKUP = {
+    "dr_blackbox": DR_Blackbox,
     "dr_constant": DR_Constant,
     "dr_constant_v2": DR_Constant_V2,
     "dr_constant_precisions": DR_Constant_Precisions,

@@ -156,7 +156,8 @@ class GraphedStep(object):
         self.u = z(self.N, P)
         self.extras = list(ode.conditioned) if m.decoder.condition_on_device else []
         self.cond_w = z(max(1, len(self.extras)), Dn)
-        self.rel = [torch.as_tensor(np.asarray(ode.relevance[n])).to(device=dev, dtype=dt) for n in self.extras]
+        self.rel = [torch.as_tensor(np.asarray(ode.relevance[n])).to(device=dev, dtype=dt) for n in self.extras
+                    if n in ode.relevance]
         prior = m.prior_tables(dt)
         self.prob = ode.problem(enc.names, enc.kinds, prior, self.extras, dev, dt)
         S = self.prob.S
@@ -164,6 +165,7 @@ class GraphedStep(object):
         self.buf = Settings(theta=z(P, N), x_states=z(T, S, N), lpx=z(N, 4), lp=z(N), lq=z(N), cost=z(1), log_w=z(N), w=z(N),
                             g_lpx=z(N, 4), g_lp=z(N), g_lq=z(N), d_q_mu=z(B, P), d_q_prec=z(B, P))
         self.d_weights = z(self.prob.n_weights) if self.prob.n_weights else None
+        self.d_extra = z(len(self.extras), N) if (self.extras and hasattr(ode, "offset_layer")) else None
         self.ready = False
         self.steps_done = 0
         self.ev_hot = None  # optional (start, end) CUDA events around the reverse-sweep kernel
@@ -174,8 +176,12 @@ class GraphedStep(object):
         enc, ode = self.model.encoder, self.model.decoder.ode_model
         self.q_mu, self.q_prec = enc.q_table(self.batch)
         self.q_mu, self.q_prec = self.q_mu.contiguous(), self.q_prec.contiguous()
+        self.extra_grad = False
         if self.extras and getattr(self, "extras_override", None) is not None:
             self.extra = self.extras_override  # tests: pin the (random, per-call) conditioner to recorded values
+        elif self.extras and hasattr(ode, "offset_layer"):
+            self.extra = ode.conditioned_extras(self.B, self.IW, self.batch.dev_1hot)  # trainable: gradient flows back
+            self.extra_grad = True
         elif self.extras:
             rows = []
             for k, name in enumerate(self.extras):
@@ -200,7 +206,7 @@ class GraphedStep(object):
             logq_theta=_ptr(b.lq))
         self._bio = L.vh_bwd_io(fwd=self._fio, g_logp_by_species=_ptr(b.g_lpx), g_logp_theta=_ptr(b.g_lp),
                                 g_logq_theta=_ptr(b.g_lq), d_q_mu=_ptr(b.d_q_mu), d_q_prec=_ptr(b.d_q_prec),
-                                d_weights=_ptr(self.d_weights))
+                                d_extra=_ptr(self.d_extra), d_weights=_ptr(self.d_weights))
         self._bio.fwd.theta = None
 
     def _hot(self):
@@ -226,6 +232,9 @@ class GraphedStep(object):
         if self.weights is not None and self.weights.requires_grad:
             outs.append(self.weights)
             grads.append(self.d_weights)
+        if self.extra_grad:
+            outs.append(self.extra)
+            grads.append(self.d_extra)
         torch.autograd.backward(outs, grads)
         if self.pg is not None:
             torch.distributed.all_reduce(opt.grad, group=self.pg)
@@ -275,7 +284,7 @@ class GraphedStep(object):
         """Fresh conditioner weights per step from the torch CPU RNG (reference quirk, vihds/ode.py:48)."""
         from .models import _draw_conditioner_weight
 
-        if self.extras:
+        if self.rel:
             w = torch.cat([_draw_conditioner_weight(self.cond_w.shape[1]) for _ in self.extras], 0)
             self.cond_w.copy_(w.to(self.cond_w.dtype), non_blocking=True)
 
