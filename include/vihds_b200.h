@@ -183,6 +183,44 @@ int vh_adam_step(int dtype, size_t n, void* param, const void* grad, void* exp_a
 int vh_adam_step_dev(int dtype, size_t n, void* param, const void* grad, void* exp_avg, void* exp_avg_sq,
                      const void* hyper, void* step, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fused amortised encoder q(theta | x, d) (vihds/encoders.py:16-55 ConditionalEncoder, :126-253 Q_Local / Q_Global_Cond
+ * / Q_Global / Q_Constant, :383-404 evaluate_q): delta-observations -> Conv1d -> AvgPool1d(stride 1) -> Linear -> tanh
+ * -> packed (mu, log_prec) heads -> q_mu / q_prec [B][P] in the column order local, global-conditioned, global, constant.
+ * Weight layouts are PyTorch's: conv_w [F][n_signals][K], lin_w [H][F*NP], local_w [2*n_local][H (+C) (+D)] with rows
+ * (mu, log_prec) interleaved per parameter, gcond_w [2*n_gcond][(C) (+D)] (no bias), global_free [2*n_global].
+ * vh_encoder_bwd ACCUMULATES into the g_* buffers (views of the flat gradient, zeroed by the optimizer). */
+typedef struct vh_encoder_desc {
+  int dtype;
+  int B, T, n_signals, n_filters, filter_size, pool_size, n_hidden, C, D;
+  int n_local, n_gcond, n_global, n_const;
+  int local_cond_treatments, local_cond_devices, gcond_cond_treatments, gcond_cond_devices;
+} vh_encoder_desc;
+
+typedef struct vh_encoder_io {
+  const void *observations /* [B][n_signals][T] */, *inputs /* [B][C] */, *dev_1hot /* [B][D] */;
+  const void *conv_w, *conv_b, *lin_w, *lin_b, *local_w, *local_b, *gcond_w, *global_free, *const_values;
+  void *q_mu, *q_prec; /* out [B][P] */
+  void *pooled;        /* out, saved for the backward: [B][F*NP] */
+  void *enc;           /* out, saved for the backward: [B][H] (tanh features) */
+} vh_encoder_io;
+
+typedef struct vh_encoder_grads {
+  const void *d_q_mu, *d_q_prec; /* [B][P] */
+  void *g_conv_w, *g_conv_b, *g_lin_w, *g_lin_b, *g_local_w, *g_local_b, *g_gcond_w, *g_global_free;
+  void* d_pre; /* workspace [B][H] */
+} vh_encoder_grads;
+
+int vh_encoder_fwd(const vh_encoder_desc* e, const vh_encoder_io* io, void* stream);
+int vh_encoder_bwd(const vh_encoder_desc* e, const vh_encoder_io* io, const vh_encoder_grads* g, void* stream);
+
+/* Device conditioner (vihds/ode.py:43-58 OdeModel.device_conditioner with param = ones, :99-116 DeviceConditioner):
+ * out[k][n] = (plus_one[k] ? 1 : 0) + relu(dot(w[k], dev_1hot[n % B] * rel[k])),  n = b*IW + i.  `n % B` reproduces the
+ * reference's repeat([n_iwae, 1]) + reshape, which hands sample (b, i) the conditioner row (b*IW + i) % B.
+ * rel, w: [n_cond][D];  plus_one[k] = the parameter is listed in data.default_devices. */
+int vh_device_conditioner(int dtype, int B, int IW, int D, int n_cond, const void* dev_1hot, const void* rel, const void* w,
+                          const int* plus_one, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

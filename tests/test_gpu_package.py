@@ -15,6 +15,10 @@ from vihds_b200.training import GraphedStep, Training
 from vihds_b200.vae import build_model
 
 pytestmark = pytest.mark.gpu
+# the stock-PyTorch encoder is the fp32 REFERENCE here: cuDNN would otherwise run its conv weight-gradient in TF32
+# (2.7e-4 relative error on conv.weight.grad, measured), which is the reference's imprecision, not the fused kernel's
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 class Args:
@@ -195,3 +199,78 @@ def test_evaluation_moments_match_numpy_reduction():
     assert _rel(out.iw_predict_mu, mu) < 1e-4 and _rel(out.iw_predict_std, sd) < 1e-3
     assert _rel(out.iw_states, (w * x_states).sum(1)) < 1e-4 and _rel(out.iw_variance, (w / precisions).sum(1)) < 1e-4
     assert abs(float(out.elbo) + float(case["loss"])) <= 1e-4 * abs(float(case["loss"]))
+
+
+@pytest.mark.parametrize("case_name,spec,dims", [
+    ("dr_constant_icml_midpoint_f32_iw8", "dr_constant_icml", None),           # local heads conditioned on devices
+    ("dr_constant_one_midpoint_f32_iw5", "dr_constant_one", (4, 100, 2, 1)),     # + global-conditioned heads
+    ("dr_blackbox_icml_midpoint_f32_iw8", "dr_blackbox_icml", None),
+])
+def test_fused_encoder_matches_pytorch_reference(case_name, spec, dims):
+    """csrc/vh_encoder.cu (one launch forward, two backward) against the same encoder in stock PyTorch ops: q tables
+    and the gradient of a random linear functional of them w.r.t. all eight parameter tensors.  fp32, rtol 2e-5."""
+    case = load_case(case_name)
+    settings, par, model, training = build(spec, dims)
+    enc = model.encoder
+    batch = batch_from_case(case)
+    mu1, pr1 = enc.q_table(batch)
+    mu0, pr0 = enc.q_table_reference(batch)
+    assert torch.allclose(mu1, mu0, rtol=2e-5, atol=1e-6) and torch.allclose(pr1, pr0, rtol=2e-5, atol=1e-6)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    g_mu, g_pr = torch.randn(mu0.shape, device="cuda", generator=g), torch.randn(mu0.shape, device="cuda", generator=g)
+    params = [p for p in enc.fused_parameters() if p.numel()]
+    got = torch.autograd.grad([mu1, pr1], params, [g_mu, g_pr], allow_unused=True)
+    ref = torch.autograd.grad([mu0, pr0], params, [g_mu, g_pr], allow_unused=True)
+    for a, b, p in zip(got, ref, params):
+        assert _rel(a.cpu().numpy(), b.cpu().numpy()) < 2e-5, tuple(p.shape)
+
+
+def test_graphed_step_fused_encoder_equals_pytorch_encoder():
+    """Same three steps with the fused encoder kernels and with the stock-PyTorch encoder inside GraphedStep."""
+    case = load_case("dr_constant_icml_midpoint_f32_iw8")
+    batch = batch_from_case(case)
+    B, IW, P = case["u"].shape
+    us = [torch.randn(B, IW, P, generator=torch.Generator().manual_seed(i)).cuda() for i in range(3)]
+    flats, costs = [], []
+    for fused in (True, False):
+        _, _, model, tr = build("dr_constant_icml")
+        model.encoder.fused = fused
+        gs = GraphedStep(tr, B, IW, batch.times.numel())
+        assert gs.fused_encoder == fused
+        gs.load_batch(batch)
+        gs.cond_w.copy_(torch.tensor([[2.0, 1.0, 3.0, 0.5, 2.5, 1.5, 0.2], [1.0, 2.0, 0.3, 3.0, 0.7, 2.2, 1.1]]).cuda())
+        c = []
+        for u in us:
+            gs.load_u(u)
+            c.append(float(gs.step().item()))
+        costs.append(c)
+        flats.append(tr.optimizer.flat.cpu().numpy())
+    assert np.allclose(costs[0], costs[1], rtol=1e-5)
+    assert _rel(flats[0], flats[1]) < 1e-4
+
+
+def test_device_conditioner_kernel_matches_reference_quirk():
+    """vh_device_conditioner == OdeModel.device_conditioner(ones) including the repeat/reshape row scramble."""
+    import ctypes as C
+
+    from vihds_b200 import _lib as L
+
+    settings, par, model, training = build("dr_constant_icml")
+    ode = model.decoder.ode_model
+    case = load_case("dr_constant_icml_midpoint_f32_iw8")
+    dev_1hot = torch.as_tensor(case["dev_1hot"]).cuda()
+    B, IW, D = dev_1hot.shape[0], 5, dev_1hot.shape[1]
+    torch.manual_seed(3)
+    ones = torch.ones(B, IW, device="cuda")
+    ref = torch.stack([ode.device_conditioner(ones, n, dev_1hot).reshape(-1) for n in ("aR", "aS")])
+    torch.manual_seed(3)
+    from vihds_b200.models import _draw_conditioner_weight
+
+    w = torch.cat([_draw_conditioner_weight(D) for _ in range(2)], 0).cuda()
+    rel = torch.stack([torch.as_tensor(ode.relevance[n]) for n in ("aR", "aS")]).cuda().contiguous()
+    plus = torch.tensor([1, 1], dtype=torch.int32, device="cuda")
+    out = torch.zeros(2, B * IW, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    L.check(L.load().vh_device_conditioner(0, B, IW, D, 2, p(dev_1hot), p(rel), p(w), p(plus), p(out), None))
+    torch.cuda.synchronize()
+    assert torch.allclose(out, ref, rtol=1e-6, atol=1e-6)

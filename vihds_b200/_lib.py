@@ -41,6 +41,24 @@ class vh_bwd_io(C.Structure):
     _fields_ = [("fwd", vh_fwd_io)] + [(n, C.c_void_p) for n in _BWD_FIELDS]
 
 
+class vh_encoder_desc(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "dtype", "B", "T", "n_signals", "n_filters", "filter_size", "pool_size", "n_hidden", "C", "D", "n_local", "n_gcond",
+        "n_global", "n_const", "local_cond_treatments", "local_cond_devices", "gcond_cond_treatments", "gcond_cond_devices")]
+
+
+class vh_encoder_io(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "observations", "inputs", "dev_1hot", "conv_w", "conv_b", "lin_w", "lin_b", "local_w", "local_b", "gcond_w",
+        "global_free", "const_values", "q_mu", "q_prec", "pooled", "enc")]
+
+
+class vh_encoder_grads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "d_q_mu", "d_q_prec", "g_conv_w", "g_conv_b", "g_lin_w", "g_lin_b", "g_local_w", "g_local_b", "g_gcond_w",
+        "g_global_free", "d_pre")]
+
+
 _lib = None
 
 
@@ -76,6 +94,9 @@ def load():
     lib.vh_adam_step.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                  C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
     lib.vh_adam_step_dev.argtypes = [C.c_int, C.c_size_t] + [C.c_void_p] * 7
+    lib.vh_device_conditioner.argtypes = [C.c_int] * 5 + [C.c_void_p] * 6
+    lib.vh_encoder_fwd.argtypes = [C.POINTER(vh_encoder_desc), C.POINTER(vh_encoder_io), C.c_void_p]
+    lib.vh_encoder_bwd.argtypes = [C.POINTER(vh_encoder_desc), C.POINTER(vh_encoder_io), C.POINTER(vh_encoder_grads), C.c_void_p]
     if lib.vh_abi_version() != 1:
         raise RuntimeError("vihds_b200: ABI version mismatch")
     _lib = lib

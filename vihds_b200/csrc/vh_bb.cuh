@@ -163,7 +163,7 @@ struct BbRhs {
       for (int o = 0; o < 4; ++o) dx[NST + o] = sigmoid(zp[o]) - sigmoid(zd[o]) * x[NST + o];
     }
   }
-  VH_HD void eval_keep(R t, const R* x, R* dx, Kept&) const { eval(t, x, dx); }
+  VH_HD void eval_keep(R t, const R* x, R* dx, Kept&) const { eval(t, x, dx); }  // eval() never writes the row
 
   // g: cotangent of dx  ->  gx (accumulated); the staged rows go to the weight-gradient sink gw
   template <typename GW>

@@ -49,7 +49,7 @@ struct BbWarpWgrad {
     const int hl = lane < H ? lane : 0;
     const int ol = lane < NST ? lane : 0;
     const R mh = lane < H ? R(1) : R(0), mo = lane < NST ? R(1) : R(0);
-#pragma unroll 2
+#pragma unroll 4
     for (int t = 0; t < 32; ++t) {
       const R* r = rows + t * ROW;
       const R myhid = r[RW::sHID + hl] * mh, mygp = r[RW::sGPRE + hl] * mh;
@@ -70,7 +70,7 @@ struct BbWarpWgrad {
     const int hl = lane < HP ? lane : 0;
     const int ol = lane < 4 ? lane : 0;
     const R mh = lane < HP ? R(1) : R(0), mo = lane < 4 ? R(1) : R(0);
-#pragma unroll 2
+#pragma unroll 4
     for (int t = 0; t < 32; ++t) {
       const R* r = rows + t * ROW;
       const R myhp = r[RW::pHP + hl] * mh, mygp = r[RW::pGPRE + hl] * mh;

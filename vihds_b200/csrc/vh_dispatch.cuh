@@ -51,8 +51,14 @@ inline const char* build_call(const vh_problem* p, const vh_fwd_io* io, const vh
     }
   }
   a.n_free = 0;
+  for (int k = 0; k < VH_MAX_SLOTS; ++k) a.col_slot[k] = -1;
   for (int k = 0; k < p->P; ++k)
     if (!used[k]) a.free_cols[a.n_free++] = k;
+  for (int s = 0; s < VH_MAX_SLOTS; ++s)
+    if (p->slot_src[s] >= 0) {
+      if (a.col_slot[p->slot_src[s]] >= 0) return "a theta column feeds two model slots";
+      a.col_slot[p->slot_src[s]] = s;
+    }
   a.times = (const R*)io->times; a.u = (const R*)io->u; a.q_mu = (const R*)io->q_mu; a.q_prec = (const R*)io->q_prec;
   a.p_mu = (const R*)io->p_mu; a.p_prec = (const R*)io->p_prec; a.clip_lo = (const R*)io->clip_lo;
   a.clip_hi = (const R*)io->clip_hi; a.kind = io->kind; a.extra = (const R*)io->extra;

@@ -1,0 +1,409 @@
+// Fused amortised encoder q(theta | x, d): forward in ONE launch, backward in two (vihds/encoders.py:16-55, :126-253,
+// :383-404).  The reference runs Conv1d -> AvgPool1d -> Linear -> tanh and then 2 x n_param Linear(., 1) heads one by
+// one; under PyTorch that is ~15 forward and ~35 backward launches of 2-7 us each, which after the ODE kernels were
+// fused had become ~40 % of the ELBO-gradient step at the icml size.  Everything here is per individual and tiny
+// (30 k + 36 k multiply-adds), so one CTA per individual does the whole chain out of shared memory:
+//
+//   enc_fwd_kernel   delta = diff(obs) -> conv (F x 4 x K) -> mean-pool (P) -> [saved] -> Linear + tanh [saved] ->
+//                    packed heads (local: [enc, treatments?, devices?]; global-conditioned: [treatments?, devices?]) ->
+//                    q_mu / q_prec rows (global and constant columns filled in the same pass)
+//   enc_bwd_kernel   per individual: head / hidden-layer / pool / conv backward; small parameter gradients by atomics
+//   enc_lin_wgrad    dW_lin[o][i] = sum_b d_pre[b][o] * pooled[b][i]   (one thread per weight, coalesced over i)
+//
+// Gradients are ACCUMULATED into the caller's buffers (views of the flat gradient vector, zeroed by the optimizer).
+#include <cuda_runtime.h>
+
+#include "../../include/vihds_b200.h"
+#include "vh_math.cuh"
+
+namespace vh {
+void set_error(const char* fmt, ...);
+
+struct EncDims {
+  int B, T, NS, F, K, PL, H, C, D;
+  int nl, ng, nglob, nconst, P;
+  int lt, ld, gt, gd;       // conditioning flags (treatments / devices) of the local and global-conditioned groups
+  int L1, NCV, NP, NLIN;    // T-1, conv outputs per filter, pooled outputs per filter, F*NP
+  int nin_l, nin_g;
+};
+
+template <typename R>
+struct EncPtrs {
+  const R *obs, *inputs, *dev, *conv_w, *conv_b, *lin_w, *lin_b, *local_w, *local_b, *gcond_w, *global_free, *const_values;
+  R *q_mu, *q_prec, *pooled, *enc;
+  const R *d_q_mu, *d_q_prec;
+  R *g_conv_w, *g_conv_b, *g_lin_w, *g_lin_b, *g_local_w, *g_local_b, *g_gcond_w, *g_global_free, *d_pre;
+};
+
+template <typename R>
+__device__ R warp_sum(R v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// shared-memory carve-up (elements): delta [NS][L1] | conv scratch [F][NCV] | pooled [NLIN] | xloc [nin_l] | freev | conv w+b
+// Everything here is latency-bound (36 CTAs for the icml batch), so the loops that read weights from global memory
+// keep several independent loads in flight: the hidden layer accumulates up to ENC_OPW outputs per warp at once, the
+// heads use one warp per row.
+#define ENC_THREADS 512
+#define ENC_OPW 4
+template <typename R>
+__global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, const EncPtrs<R> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  R* delta = reinterpret_cast<R*>(smem_raw);
+  R* conv = delta + d.NS * d.L1;
+  R* pooled = conv + d.F * d.NCV;
+  R* xloc = pooled + d.NLIN;
+  R* freev = xloc + d.nin_l;  // 2*(nl+ng)
+  R* cw = freev + 2 * (d.nl + d.ng);  // conv weights [F][NS][K] + bias [F]
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const R* obs = p.obs + (size_t)b * d.NS * d.T;
+  const int ncw = d.F * d.NS * d.K;
+  for (int i = tid; i < ncw + d.F; i += nt) cw[i] = i < ncw ? p.conv_w[i] : p.conv_b[i - ncw];
+  for (int i = tid; i < d.NS * d.L1; i += nt) {
+    const int c = i / d.L1, j = i % d.L1;
+    delta[i] = obs[c * d.T + j + 1] - obs[c * d.T + j];
+  }
+  for (int i = tid; i < d.nin_l - d.H; i += nt)  // conditioning inputs of the local heads
+    xloc[d.H + i] = (d.lt && i < d.C) ? p.inputs[(size_t)b * d.C + i] : p.dev[(size_t)b * d.D + (i - (d.lt ? d.C : 0))];
+  __syncthreads();
+  for (int i = tid; i < d.F * d.NCV; i += nt) {
+    const int f = i / d.NCV, j = i % d.NCV;
+    R a = cw[ncw + f];
+    for (int c = 0; c < d.NS; ++c) {
+      const R* w = cw + (f * d.NS + c) * d.K;
+      const R* x = delta + c * d.L1 + j;
+      for (int k = 0; k < d.K; ++k) a += w[k] * x[k];
+    }
+    conv[i] = a;
+  }
+  __syncthreads();
+  const R inv_pool = R(1) / R(d.PL);
+  for (int i = tid; i < d.NLIN; i += nt) {
+    const int f = i / d.NP, j = i % d.NP;
+    R a = R(0);
+    for (int k = 0; k < d.PL; ++k) a += conv[f * d.NCV + j + k];
+    a *= inv_pool;
+    pooled[i] = a;
+    p.pooled[(size_t)b * d.NLIN + i] = a;
+  }
+  __syncthreads();
+  // hidden layer: each warp owns outputs o0, o0 + nw, ... and accumulates ENC_OPW of them per pass over the inputs
+  for (int o0 = warp; o0 < d.H; o0 += nw * ENC_OPW) {
+    R acc[ENC_OPW];
+#pragma unroll
+    for (int q = 0; q < ENC_OPW; ++q) acc[q] = R(0);
+#pragma unroll 2
+    for (int i = lane; i < d.NLIN; i += 32) {
+      const R x = pooled[i];
+#pragma unroll
+      for (int q = 0; q < ENC_OPW; ++q) {
+        const int o = o0 + q * nw;
+        if (o < d.H) acc[q] += p.lin_w[(size_t)o * d.NLIN + i] * x;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < ENC_OPW; ++q) {
+      const int o = o0 + q * nw;
+      const R a = warp_sum(acc[q]);
+      if (lane == 0 && o < d.H) {
+        const R e = vtanh(a + p.lin_b[o]);
+        xloc[o] = e;
+        p.enc[(size_t)b * d.H + o] = e;
+      }
+    }
+  }
+  __syncthreads();
+  // packed heads: one warp per row, lanes over the inputs
+  for (int r = warp; r < 2 * (d.nl + d.ng); r += nw) {
+    R a = R(0);
+    if (r < 2 * d.nl) {
+      const R* w = p.local_w + (size_t)r * d.nin_l;
+      for (int i = lane; i < d.nin_l; i += 32) a += w[i] * xloc[i];
+    } else {
+      const R* w = p.gcond_w + (size_t)(r - 2 * d.nl) * d.nin_g;
+      for (int i = lane; i < d.nin_g; i += 32) {
+        const R x = (d.gt && i < d.C) ? p.inputs[(size_t)b * d.C + i] : p.dev[(size_t)b * d.D + (i - (d.gt ? d.C : 0))];
+        a += w[i] * x;
+      }
+    }
+    a = warp_sum(a);
+    if (lane == 0) freev[r] = a + (r < 2 * d.nl ? p.local_b[r] : R(0));
+  }
+  __syncthreads();
+  R* qm = p.q_mu + (size_t)b * d.P;
+  R* qp = p.q_prec + (size_t)b * d.P;
+  for (int k = tid; k < d.P; k += nt) {
+    const int ncond = d.nl + d.ng;
+    if (k < ncond) {
+      qm[k] = freev[2 * k];
+      qp[k] = vexp(freev[2 * k + 1]);
+    } else if (k < ncond + d.nglob) {
+      qm[k] = p.global_free[2 * (k - ncond)];
+      qp[k] = vexp(p.global_free[2 * (k - ncond) + 1]);
+    } else {
+      qm[k] = p.const_values[k - ncond - d.nglob];
+      qp[k] = R(1);
+    }
+  }
+}
+
+// backward, one CTA per individual.  shared: delta | dconv [F][NCV] | dpool [NLIN] | xloc | dfree | dxloc | dpre
+template <typename R>
+__global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, const EncPtrs<R> p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  R* delta = reinterpret_cast<R*>(smem_raw);
+  R* dconv = delta + d.NS * d.L1;
+  R* dpool = dconv + d.F * d.NCV;
+  R* xloc = dpool + d.NLIN;
+  R* dfree = xloc + d.nin_l;
+  R* dpre = dfree + 2 * (d.nl + d.ng + d.nglob);
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const R* obs = p.obs + (size_t)b * d.NS * d.T;
+  for (int i = tid; i < d.NS * d.L1; i += nt) {
+    const int c = i / d.L1, j = i % d.L1;
+    delta[i] = obs[c * d.T + j + 1] - obs[c * d.T + j];
+  }
+  for (int i = tid; i < d.nin_l; i += nt) {
+    R v;
+    if (i < d.H)
+      v = p.enc[(size_t)b * d.H + i];
+    else {
+      const int j = i - d.H;
+      v = (d.lt && j < d.C) ? p.inputs[(size_t)b * d.C + j] : p.dev[(size_t)b * d.D + (j - (d.lt ? d.C : 0))];
+    }
+    xloc[i] = v;
+  }
+  const int ncond = d.nl + d.ng;
+  for (int k = tid; k < ncond + d.nglob; k += nt) {
+    dfree[2 * k] = p.d_q_mu[(size_t)b * d.P + k];
+    dfree[2 * k + 1] = p.d_q_prec[(size_t)b * d.P + k] * p.q_prec[(size_t)b * d.P + k];  // d exp(log_prec)
+  }
+  __syncthreads();
+  // global free parameters
+  for (int j = tid; j < 2 * d.nglob; j += nt) atomicAdd(p.g_global_free + j, dfree[2 * ncond + j]);
+  // packed heads: weight / bias gradients and the cotangent of the hidden features
+  for (int e = tid; e < 2 * d.nl * d.nin_l; e += nt) atomicAdd(p.g_local_w + e, dfree[e / d.nin_l] * xloc[e % d.nin_l]);
+  for (int r = tid; r < 2 * d.nl; r += nt) atomicAdd(p.g_local_b + r, dfree[r]);
+  for (int e = tid; e < 2 * d.ng * d.nin_g; e += nt) {
+    const int r = e / d.nin_g, i = e % d.nin_g;
+    const R x = (d.gt && i < d.C) ? p.inputs[(size_t)b * d.C + i] : p.dev[(size_t)b * d.D + (i - (d.gt ? d.C : 0))];
+    atomicAdd(p.g_gcond_w + e, dfree[2 * d.nl + r] * x);
+  }
+  for (int o = tid; o < d.H; o += nt) {
+    R g = R(0);
+    for (int r = 0; r < 2 * d.nl; ++r) g += p.local_w[(size_t)r * d.nin_l + o] * dfree[r];
+    const R e = xloc[o];
+    const R gp = g * (R(1) - e * e);  // tanh'
+    dpre[o] = gp;
+    p.d_pre[(size_t)b * d.H + o] = gp;
+    atomicAdd(p.g_lin_b + o, gp);
+  }
+  __syncthreads();
+  // cotangent of the pooled features: dpool[i] = sum_o W[o][i] dpre[o]   (coalesced over i)
+  for (int i = tid; i < d.NLIN; i += nt) {
+    R g0 = R(0), g1 = R(0);
+    int o = 0;
+#pragma unroll 5
+    for (; o + 1 < d.H; o += 2) {  // two accumulators, ten weight loads in flight
+      g0 += p.lin_w[(size_t)o * d.NLIN + i] * dpre[o];
+      g1 += p.lin_w[(size_t)(o + 1) * d.NLIN + i] * dpre[o + 1];
+    }
+    if (o < d.H) g0 += p.lin_w[(size_t)o * d.NLIN + i] * dpre[o];
+    dpool[i] = g0 + g1;
+  }
+  __syncthreads();
+  const R inv_pool = R(1) / R(d.PL);
+  for (int i = tid; i < d.F * d.NCV; i += nt) {
+    const int f = i / d.NCV, j = i % d.NCV;
+    R g = R(0);
+    for (int k = 0; k < d.PL; ++k) {
+      const int jp = j - k;
+      if (jp >= 0 && jp < d.NP) g += dpool[f * d.NP + jp];
+    }
+    dconv[i] = g * inv_pool;
+  }
+  __syncthreads();
+  // conv weight / bias gradients: one warp per weight, lanes over the NCV positions
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const int nwc = d.F * d.NS * d.K;
+  for (int e = warp; e < nwc + d.F; e += nw) {
+    R a = R(0);
+    if (e < nwc) {
+      const int f = e / (d.NS * d.K), c = (e / d.K) % d.NS, k = e % d.K;
+      for (int j = lane; j < d.NCV; j += 32) a += dconv[f * d.NCV + j] * delta[c * d.L1 + j + k];
+    } else {
+      const int f = e - nwc;
+      for (int j = lane; j < d.NCV; j += 32) a += dconv[f * d.NCV + j];
+    }
+    a = warp_sum(a);
+    if (lane == 0) atomicAdd(e < nwc ? p.g_conv_w + e : p.g_conv_b + (e - nwc), a);
+  }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(256) enc_lin_wgrad_kernel(const EncDims d, const EncPtrs<R> p) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.H * d.NLIN) return;
+  const int o = e / d.NLIN, i = e % d.NLIN;
+  R a = R(0);
+  for (int b = 0; b < d.B; ++b) a += p.d_pre[(size_t)b * d.H + o] * p.pooled[(size_t)b * d.NLIN + i];
+  p.g_lin_w[e] += a;
+}
+
+// device conditioner (vihds/ode.py:43-58, :99-116) including the reference's repeat/reshape quirk: sample n = b*IW + i
+// receives the conditioner output of individual n % B
+template <typename R>
+__global__ void conditioner_kernel(int B, int N, int D, int n_cond, const R* __restrict__ dev, const R* __restrict__ rel,
+                                   const R* __restrict__ w, const int* __restrict__ plus_one, R* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const R* d = dev + (size_t)(n % B) * D;
+  for (int k = 0; k < n_cond; ++k) {
+    R a = R(0);
+    for (int j = 0; j < D; ++j) a += w[k * D + j] * (d[j] * rel[k * D + j]);
+    a = a > R(0) ? a : R(0);
+    out[(size_t)k * N + n] = plus_one[k] ? R(1) + a : a;
+  }
+}
+
+static const char* fill_dims(const vh_encoder_desc* e, EncDims& d) {
+  if (!e) return "null descriptor";
+  d.B = e->B; d.T = e->T; d.NS = e->n_signals; d.F = e->n_filters; d.K = e->filter_size; d.PL = e->pool_size; d.H = e->n_hidden;
+  d.C = e->C; d.D = e->D; d.nl = e->n_local; d.ng = e->n_gcond; d.nglob = e->n_global; d.nconst = e->n_const;
+  d.P = d.nl + d.ng + d.nglob + d.nconst;
+  d.lt = e->local_cond_treatments; d.ld = e->local_cond_devices; d.gt = e->gcond_cond_treatments; d.gd = e->gcond_cond_devices;
+  d.L1 = d.T - 1;
+  d.NCV = d.L1 - (d.K - 1);
+  d.NP = d.NCV - (d.PL - 1);
+  d.NLIN = d.F * d.NP;
+  d.nin_l = d.H + (d.lt ? d.C : 0) + (d.ld ? d.D : 0);
+  d.nin_g = (d.gt ? d.C : 0) + (d.gd ? d.D : 0);
+  if (d.B <= 0 || d.NP <= 0 || d.H <= 0) return "encoder: B, n_hidden must be positive and T long enough for the conv + pool";
+  if (d.ng > 0 && d.nin_g == 0) return "encoder: global-conditioned parameters need a conditioning input";
+  return nullptr;
+}
+
+template <typename R>
+static void fill_ptrs(const vh_encoder_io* io, const vh_encoder_grads* g, EncPtrs<R>& p) {
+  p.obs = (const R*)io->observations; p.inputs = (const R*)io->inputs; p.dev = (const R*)io->dev_1hot;
+  p.conv_w = (const R*)io->conv_w; p.conv_b = (const R*)io->conv_b; p.lin_w = (const R*)io->lin_w; p.lin_b = (const R*)io->lin_b;
+  p.local_w = (const R*)io->local_w; p.local_b = (const R*)io->local_b; p.gcond_w = (const R*)io->gcond_w;
+  p.global_free = (const R*)io->global_free; p.const_values = (const R*)io->const_values;
+  p.q_mu = (R*)io->q_mu; p.q_prec = (R*)io->q_prec; p.pooled = (R*)io->pooled; p.enc = (R*)io->enc;
+  if (g) {
+    p.d_q_mu = (const R*)g->d_q_mu; p.d_q_prec = (const R*)g->d_q_prec;
+    p.g_conv_w = (R*)g->g_conv_w; p.g_conv_b = (R*)g->g_conv_b; p.g_lin_w = (R*)g->g_lin_w; p.g_lin_b = (R*)g->g_lin_b;
+    p.g_local_w = (R*)g->g_local_w; p.g_local_b = (R*)g->g_local_b; p.g_gcond_w = (R*)g->g_gcond_w;
+    p.g_global_free = (R*)g->g_global_free; p.d_pre = (R*)g->d_pre;
+  }
+}
+
+template <typename R>
+static int enc_fwd_t(const EncDims& d, const vh_encoder_io* io, cudaStream_t s) {
+  EncPtrs<R> p = {};
+  fill_ptrs<R>(io, nullptr, p);
+  const size_t smem = sizeof(R) * ((size_t)d.NS * d.L1 + (size_t)d.F * d.NCV + d.NLIN + d.nin_l + 2 * (d.nl + d.ng) +
+                                   (size_t)d.F * d.NS * d.K + d.F + 8);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(enc_fwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  enc_fwd_kernel<R><<<d.B, ENC_THREADS, smem, s>>>(d, p);
+  return 0;
+}
+
+template <typename R>
+static int enc_bwd_t(const EncDims& d, const vh_encoder_io* io, const vh_encoder_grads* g, cudaStream_t s) {
+  EncPtrs<R> p = {};
+  fill_ptrs<R>(io, g, p);
+  const size_t smem = sizeof(R) * ((size_t)d.NS * d.L1 + (size_t)d.F * d.NCV + d.NLIN + d.nin_l + 2 * (d.nl + d.ng + d.nglob) + d.H + 8);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(enc_bwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  enc_bwd_kernel<R><<<d.B, ENC_THREADS, smem, s>>>(d, p);
+  const int n = d.H * d.NLIN;
+  enc_lin_wgrad_kernel<R><<<(n + 255) / 256, 256, 0, s>>>(d, p);
+  return 0;
+}
+
+}  // namespace vh
+
+using namespace vh;
+
+extern "C" {
+
+int vh_encoder_fwd(const vh_encoder_desc* e, const vh_encoder_io* io, void* stream) {
+  EncDims d;
+  if (const char* err = fill_dims(e, d)) {
+    set_error("vh_encoder_fwd: %s", err);
+    return VH_ERR_INVALID;
+  }
+  if (!io || !io->observations || !io->conv_w || !io->lin_w || !io->q_mu || !io->q_prec || !io->pooled || !io->enc ||
+      (d.nl > 0 && (!io->local_w || !io->local_b)) || (d.ng > 0 && !io->gcond_w) || (d.nglob > 0 && !io->global_free) ||
+      (d.nconst > 0 && !io->const_values)) {
+    set_error("vh_encoder_fwd: missing buffer");
+    return VH_ERR_INVALID;
+  }
+  if (e->dtype == VH_F32) enc_fwd_t<float>(d, io, (cudaStream_t)stream);
+  else if (e->dtype == VH_F64) enc_fwd_t<double>(d, io, (cudaStream_t)stream);
+  else {
+    set_error("unknown dtype %d", e->dtype);
+    return VH_ERR_INVALID;
+  }
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    set_error("enc_fwd_kernel launch failed: %s", cudaGetErrorString(ce));
+    return VH_ERR_CUDA;
+  }
+  return VH_OK;
+}
+
+int vh_device_conditioner(int dtype, int B, int IW, int D, int n_cond, const void* dev_1hot, const void* rel, const void* w,
+                          const int* plus_one, void* out, void* stream) {
+  if (B <= 0 || IW <= 0 || D <= 0 || n_cond <= 0 || !dev_1hot || !rel || !w || !plus_one || !out) {
+    set_error("vh_device_conditioner: bad arguments");
+    return VH_ERR_INVALID;
+  }
+  const int N = B * IW, block = 128, grid = (N + block - 1) / block;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == VH_F32)
+    conditioner_kernel<float><<<grid, block, 0, s>>>(B, N, D, n_cond, (const float*)dev_1hot, (const float*)rel, (const float*)w, plus_one, (float*)out);
+  else if (dtype == VH_F64)
+    conditioner_kernel<double><<<grid, block, 0, s>>>(B, N, D, n_cond, (const double*)dev_1hot, (const double*)rel, (const double*)w, plus_one, (double*)out);
+  else {
+    set_error("unknown dtype %d", dtype);
+    return VH_ERR_INVALID;
+  }
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    set_error("conditioner_kernel launch failed: %s", cudaGetErrorString(ce));
+    return VH_ERR_CUDA;
+  }
+  return VH_OK;
+}
+
+int vh_encoder_bwd(const vh_encoder_desc* e, const vh_encoder_io* io, const vh_encoder_grads* g, void* stream) {
+  EncDims d;
+  if (const char* err = fill_dims(e, d)) {
+    set_error("vh_encoder_bwd: %s", err);
+    return VH_ERR_INVALID;
+  }
+  if (!io || !g || !g->d_q_mu || !g->d_q_prec || !g->g_conv_w || !g->g_conv_b || !g->g_lin_w || !g->g_lin_b || !g->d_pre ||
+      !io->q_prec || !io->pooled || !io->enc || (d.nl > 0 && (!g->g_local_w || !g->g_local_b)) || (d.ng > 0 && !g->g_gcond_w) ||
+      (d.nglob > 0 && !g->g_global_free)) {
+    set_error("vh_encoder_bwd: missing buffer");
+    return VH_ERR_INVALID;
+  }
+  if (e->dtype == VH_F32) enc_bwd_t<float>(d, io, g, (cudaStream_t)stream);
+  else if (e->dtype == VH_F64) enc_bwd_t<double>(d, io, g, (cudaStream_t)stream);
+  else {
+    set_error("unknown dtype %d", e->dtype);
+    return VH_ERR_INVALID;
+  }
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    set_error("enc_bwd_kernel launch failed: %s", cudaGetErrorString(ce));
+    return VH_ERR_CUDA;
+  }
+  return VH_OK;
+}
+
+}  // extern "C"

@@ -70,11 +70,14 @@ __global__ void __launch_bounds__(128) elbo_fwd_kernel(const Call<typename M::re
   if (n < a.N) traj_forward<M, TB>(a, n, w);
 }
 
-#ifndef VH_BWD_MINB
-#define VH_BWD_MINB 1
-#endif
+// 3 resident CTAs of 128 threads per SM (<= 168 registers) for the fp32 8-species models: measured faster than 2 CTAs
+// at 190 registers and than 4 CTAs with spills; the wider models keep the full register file.
+template <class M>
+struct BwdBounds {
+  static constexpr int min_blocks = (sizeof(typename M::real) == 4 && !M::DYN && !M::RELAY) ? 3 : 1;
+};
 template <class M, class TB>
-__global__ void __launch_bounds__(128, VH_BWD_MINB) elbo_bwd_kernel(const Call<typename M::real> a) {
+__global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel(const Call<typename M::real> a) {
   typedef typename M::real R;
   constexpr int NW = NetInfo<M>::NW;
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -16,8 +16,16 @@ VH_HD float vexp(float x) { return expf(x); }
 VH_HD double vexp(double x) { return exp(x); }
 VH_HD float vlog(float x) { return logf(x); }
 VH_HD double vlog(double x) { return log(x); }
-VH_HD float vpow(float x, float y) { return powf(x, y); }
-VH_HD double vpow(double x, double y) { return pow(x, y); }
+// powf / pow are ~150 SASS instructions inlined; they are only used in the per-trajectory set-up (Hill fractions) and
+// its chain rule, ~30 call sites: one out-of-line copy keeps the kernels' straight-line prologue / epilogue (which a
+// latency-bound launch executes with a cold instruction cache) small.
+#if defined(__CUDACC__)
+#define VH_HD_NOINLINE static __host__ __device__ __noinline__
+#else
+#define VH_HD_NOINLINE inline
+#endif
+VH_HD_NOINLINE float vpow(float x, float y) { return powf(x, y); }
+VH_HD_NOINLINE double vpow(double x, double y) { return pow(x, y); }
 VH_HD float vsqrt(float x) { return sqrtf(x); }
 VH_HD double vsqrt(double x) { return sqrt(x); }
 VH_HD float vtanh(float x) { return tanhf(x); }

@@ -67,6 +67,7 @@ struct Call {
   R bb_init_latent, bb_init_prec;
   int n_free;                    // theta columns no model slot reads (they still carry log-prob terms)
   int free_cols[VH_MAX_SLOTS];
+  int col_slot[VH_MAX_SLOTS];    // inverse of slot_src: the model slot column k feeds, or -1
   const R *times, *u, *q_mu, *q_prec, *p_mu, *p_prec, *clip_lo, *clip_hi, *extra, *treatments, *dev_1hot, *obs, *weights;
   const int* kind;
   R *theta, *x_states, *x_predict, *logp_species, *logp_theta, *logq_theta;
@@ -244,21 +245,25 @@ VH_HD R sample_column(const Call<R>& a, int n, int b, int k, R& lq, R& lp, bool 
   return th;
 }
 
+// ROLLED over the P sampled columns (one copy of sample_column in the instruction stream instead of one per slot):
+// values land in a small per-thread array indexed by slot (local memory, L1-resident), from which the model's slot
+// registers are filled with constant indices.
 template <class M>
 VH_HD void load_theta(const Call<typename M::real>& a, int n, int b, typename M::real* th, typename M::real& lq,
                       typename M::real& lp, bool store = true) {
   typedef typename M::real R;
-#pragma unroll
+  R loc[M::NSLOT];
   for (int s = 0; s < M::NSLOT; ++s) {
-    th[s] = R(0);
-    if (!M::uses(s)) continue;
     const int src = a.slot_src[s];
-    if (src >= 0)
-      th[s] = sample_column(a, n, b, src, lq, lp, store);
-    else if (src != VH_SLOT_UNUSED)
-      th[s] = a.extra[(size_t)(-1 - src) * a.N + n];
+    loc[s] = (src < 0 && src != VH_SLOT_UNUSED) ? a.extra[(size_t)(-1 - src) * a.N + n] : R(0);
   }
-  for (int j = 0; j < a.n_free; ++j) sample_column(a, n, b, a.free_cols[j], lq, lp, store);
+  for (int k = 0; k < a.P; ++k) {
+    const R v = sample_column(a, n, b, k, lq, lp, store);
+    const int s = a.col_slot[k];
+    if (s >= 0) loc[s] = v;
+  }
+#pragma unroll
+  for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? loc[s] : R(0);
 }
 
 // cotangent of one sampled column -> (d mu, d prec) of q for this trajectory
@@ -508,23 +513,22 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
       for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gprec[o];
     }
   }
-  // scatter slot cotangents: sampled columns -> (d q_mu, d q_prec); extras -> d_extra
+  // scatter slot cotangents: sampled columns -> (d q_mu, d q_prec); extras -> d_extra.  Rolled over the columns
+  // (one copy of column_vjp + the segmented warp reduction), reading the slot cotangents from a per-thread array.
+  R gloc[M::NSLOT];
 #pragma unroll
-  for (int s = 0; s < M::NSLOT; ++s) {
-    if (!M::uses(s)) continue;
-    const int src = a.slot_src[s];
-    if (src >= 0) {
-      R dmu = R(0), dprec = R(0);
-      if (active) column_vjp(a, n, b, src, gth[s], glq, glp, dmu, dprec);
-      red(b, src, dmu, dprec, active);
-    } else if (src != VH_SLOT_UNUSED && a.d_extra && active) {
-      a.d_extra[(size_t)(-1 - src) * N + n] = gth[s];
-    }
-  }
-  for (int j = 0; j < a.n_free; ++j) {
+  for (int s = 0; s < M::NSLOT; ++s) gloc[s] = M::uses(s) ? gth[s] : R(0);
+  for (int k = 0; k < a.P; ++k) {
+    const int s = a.col_slot[k];
     R dmu = R(0), dprec = R(0);
-    if (active) column_vjp(a, n, b, a.free_cols[j], R(0), glq, glp, dmu, dprec);
-    red(b, a.free_cols[j], dmu, dprec, active);
+    if (active) column_vjp(a, n, b, k, s >= 0 ? gloc[s] : R(0), glq, glp, dmu, dprec);
+    red(b, k, dmu, dprec, active);
+  }
+  if (a.d_extra && active) {
+    for (int s = 0; s < M::NSLOT; ++s) {
+      const int src = a.slot_src[s];
+      if (src < 0 && src != VH_SLOT_UNUSED) a.d_extra[(size_t)(-1 - src) * N + n] = gloc[s];
+    }
   }
 }
 

@@ -11,11 +11,65 @@ parameter the ``mu`` head and the ``log_prec`` head, then the global-conditioned
 the packed weights equal the reference's per-parameter layers -- tests/test_host_package.py pins this against the q
 parameters recorded from the reference.
 """
+import ctypes as C
+
 import torch
 from torch import nn
 
 from . import _lib as L
 from .distributions import ChainedDistribution
+
+
+def _ptr(t):
+    return None if t is None or t.numel() == 0 else C.c_void_p(t.data_ptr())
+
+
+class FusedEncoder(torch.autograd.Function):
+    """vh_encoder_fwd / vh_encoder_bwd behind autograd: (batch tensors, the encoder's 8 parameter tensors) ->
+    (q_mu, q_prec) [B, P].  One launch forward, two backward (see csrc/vh_encoder.cu)."""
+
+    @staticmethod
+    def forward(ctx, enc, obs, inputs, dev_1hot, conv_w, conv_b, lin_w, lin_b, local_w, local_b, gcond_w, global_free):
+        lib = L.load()
+        dt, dev = obs.dtype, obs.device
+        B = obs.shape[0]
+        desc = enc.descriptor(B, dt)
+        P = desc.n_local + desc.n_gcond + desc.n_global + desc.n_const
+        q_mu, q_prec = torch.empty(B, P, dtype=dt, device=dev), torch.empty(B, P, dtype=dt, device=dev)
+        pooled = torch.empty(B, lin_w.shape[1], dtype=dt, device=dev)
+        feats = torch.empty(B, lin_w.shape[0], dtype=dt, device=dev)
+        obs, inputs, dev_1hot = obs.contiguous(), inputs.contiguous(), dev_1hot.contiguous()
+        io = L.vh_encoder_io(observations=_ptr(obs), inputs=_ptr(inputs), dev_1hot=_ptr(dev_1hot), conv_w=_ptr(conv_w),
+                             conv_b=_ptr(conv_b), lin_w=_ptr(lin_w), lin_b=_ptr(lin_b), local_w=_ptr(local_w),
+                             local_b=_ptr(local_b), gcond_w=_ptr(gcond_w), global_free=_ptr(global_free),
+                             const_values=_ptr(enc.const_values), q_mu=_ptr(q_mu), q_prec=_ptr(q_prec), pooled=_ptr(pooled),
+                             enc=_ptr(feats))
+        L.check(lib.vh_encoder_fwd(C.byref(desc), C.byref(io), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        ctx.enc_module, ctx.desc = enc, desc
+        ctx.save_for_backward(obs, inputs, dev_1hot, conv_w, conv_b, lin_w, lin_b, local_w, local_b, gcond_w, global_free,
+                              q_prec, pooled, feats)
+        return q_mu, q_prec
+
+    @staticmethod
+    def backward(ctx, d_mu, d_prec):
+        (obs, inputs, dev_1hot, conv_w, conv_b, lin_w, lin_b, local_w, local_b, gcond_w, global_free, q_prec, pooled,
+         feats) = ctx.saved_tensors
+        lib = L.load()
+        z = torch.zeros_like
+        g = [z(conv_w), z(conv_b), z(lin_w), z(lin_b), z(local_w), z(local_b), z(gcond_w), z(global_free)]
+        d_mu = torch.zeros_like(q_prec) if d_mu is None else d_mu.contiguous()
+        d_prec = torch.zeros_like(q_prec) if d_prec is None else d_prec.contiguous()
+        d_pre = torch.empty_like(feats)
+        io = L.vh_encoder_io(observations=_ptr(obs), inputs=_ptr(inputs), dev_1hot=_ptr(dev_1hot), conv_w=_ptr(conv_w),
+                             conv_b=_ptr(conv_b), lin_w=_ptr(lin_w), lin_b=_ptr(lin_b), local_w=_ptr(local_w),
+                             local_b=_ptr(local_b), gcond_w=_ptr(gcond_w), global_free=_ptr(global_free),
+                             const_values=_ptr(ctx.enc_module.const_values), q_prec=_ptr(q_prec), pooled=_ptr(pooled),
+                             enc=_ptr(feats))
+        gr = L.vh_encoder_grads(d_q_mu=_ptr(d_mu), d_q_prec=_ptr(d_prec), g_conv_w=_ptr(g[0]), g_conv_b=_ptr(g[1]),
+                                g_lin_w=_ptr(g[2]), g_lin_b=_ptr(g[3]), g_local_w=_ptr(g[4]), g_local_b=_ptr(g[5]),
+                                g_gcond_w=_ptr(g[6]), g_global_free=_ptr(g[7]), d_pre=_ptr(d_pre))
+        L.check(lib.vh_encoder_bwd(C.byref(ctx.desc), C.byref(io), C.byref(gr), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        return (None, None, None, None) + tuple(g)
 
 
 class ConditionalEncoder(nn.Module):
@@ -102,6 +156,8 @@ class Encoder(nn.Module):
         self.kinds = [s.kind for s in specs]
         self.per_individual = [s.group in ("local", "global_conditioned") for s in specs]
         self.n_free = len(self.local) + len(self.gcond) + len(self.glob)
+        self.n_conditions, self.depth = n_conditions, depth
+        self.fused = True
         self._p = None
 
     # prior ------------------------------------------------------------------------------------------------------
@@ -117,8 +173,32 @@ class Encoder(nn.Module):
         return self._p
 
     # q ----------------------------------------------------------------------------------------------------------
+    def descriptor(self, B, dtype):
+        cv, pr = self.conditional, self.parameters.params_dict
+        return L.vh_encoder_desc(
+            dtype=L.VH_F64 if dtype == torch.float64 else L.VH_F32, B=B, T=self.n_times, n_signals=self.n_species,
+            n_filters=cv.conv.out_channels, filter_size=cv.conv.kernel_size[0], pool_size=cv.pool.kernel_size[0],
+            n_hidden=cv.n_outputs, C=self.n_conditions, D=self.depth, n_local=len(self.local), n_gcond=len(self.gcond),
+            n_global=len(self.glob), n_const=len(self.const), local_cond_treatments=int(self.local_cond[0]),
+            local_cond_devices=int(self.local_cond[1]), gcond_cond_treatments=int(self.gcond_cond[0]),
+            gcond_cond_devices=int(self.gcond_cond[1]))
+
+    def fused_parameters(self):
+        """The 8 parameter tensors in the order FusedEncoder / vh_encoder_* take them."""
+        cv = self.conditional
+        return (cv.conv.weight, cv.conv.bias, cv.lin.weight, cv.lin.bias, self.local_heads.weight, self.local_heads.bias,
+                self.gcond_heads.weight, self.global_free)
+
     def q_table(self, data):
-        """(q_mu [B,P], q_prec [B,P]) -- one GEMM per conditioned group, no per-parameter Python loop."""
+        """(q_mu [B,P], q_prec [B,P]).  On a CUDA device: the fused encoder kernels (one launch forward, two backward);
+        ``q_table_reference`` is the same computation in stock PyTorch ops (any device) -- the fp32 reference the fused
+        kernels are tested against."""
+        if self.fused and data.observations.is_cuda:
+            return FusedEncoder.apply(self, data.observations, data.inputs, data.dev_1hot, *self.fused_parameters())
+        return self.q_table_reference(data)
+
+    def q_table_reference(self, data):
+        """One GEMM per conditioned group, no per-parameter Python loop (stock PyTorch)."""
         obs = data.observations
         B = obs.shape[0]
         delta = obs[:, :, 1:self.n_times] - obs[:, :, :self.n_times - 1]

@@ -25,6 +25,11 @@ from .datasets import batch_of
 from .engine import FlatAdam, IwaeCost, _ptr, _stream, iw_moments
 
 
+def _nz(t):
+    """Pointer of a possibly empty tensor (None when it has no elements)."""
+    return None if t is None or t.numel() == 0 else _ptr(t)
+
+
 class Results(object):
     """Evaluation output (vihds/utils.py:65-99): importance-weighted trace moments, reduced on the device by
     vh_iw_moments so that the [B, IW, ., T] traces never travel to the host."""
@@ -158,6 +163,17 @@ class GraphedStep(object):
         self.cond_w = z(max(1, len(self.extras)), Dn)
         self.rel = [torch.as_tensor(np.asarray(ode.relevance[n])).to(device=dev, dtype=dt) for n in self.extras
                     if n in ode.relevance]
+        if self.rel:
+            self.rel_mat = torch.stack(self.rel).contiguous()
+            self.plus_one = torch.tensor([int(n in ode.default_devices) for n in self.extras], dtype=torch.int32, device=dev)
+            self.extra_static = z(len(self.extras), self.N)
+        # fused encoder: static activations + direct gradient pointers (no autograd on the encoder side)
+        self.fused_encoder = bool(getattr(enc, "fused", False))
+        if self.fused_encoder:
+            self.enc_desc = enc.descriptor(B, dt)
+            self.q_mu, self.q_prec = z(B, P), z(B, P)
+            self.enc_pooled = z(B, enc.conditional.lin.weight.shape[1])
+            self.enc_feats, self.enc_dpre = z(B, enc.conditional.n_outputs), z(B, enc.conditional.n_outputs)
         prior = m.prior_tables(dt)
         self.prob = ode.problem(enc.names, enc.kinds, prior, self.extras, dev, dt)
         S = self.prob.S
@@ -172,10 +188,21 @@ class GraphedStep(object):
 
     # -- the three segments -------------------------------------------------------------------------------------
     def _pre(self):
-        """encoder forward + device conditioning (stock PyTorch; captured)."""
+        """encoder forward + device conditioning + weight packing.  Fused path: two launches of libvihds_b200.so on
+        static buffers; otherwise stock PyTorch (captured either way)."""
         enc, ode = self.model.encoder, self.model.decoder.ode_model
-        self.q_mu, self.q_prec = enc.q_table(self.batch)
-        self.q_mu, self.q_prec = self.q_mu.contiguous(), self.q_prec.contiguous()
+        lib, s = self.prob.lib, _stream()
+        if self.fused_encoder:
+            pr = enc.fused_parameters()
+            self._enc_io = L.vh_encoder_io(
+                observations=_ptr(self.batch.observations), inputs=_ptr(self.batch.inputs), dev_1hot=_ptr(self.batch.dev_1hot),
+                conv_w=_ptr(pr[0]), conv_b=_ptr(pr[1]), lin_w=_ptr(pr[2]), lin_b=_ptr(pr[3]), local_w=_nz(pr[4]),
+                local_b=_nz(pr[5]), gcond_w=_nz(pr[6]), global_free=_nz(pr[7]), const_values=_nz(enc.const_values),
+                q_mu=_ptr(self.q_mu), q_prec=_ptr(self.q_prec), pooled=_ptr(self.enc_pooled), enc=_ptr(self.enc_feats))
+            L.check(lib.vh_encoder_fwd(C.byref(self.enc_desc), C.byref(self._enc_io), s))
+        else:
+            self.q_mu, self.q_prec = enc.q_table_reference(self.batch)
+            self.q_mu, self.q_prec = self.q_mu.contiguous(), self.q_prec.contiguous()
         self.extra_grad = False
         if self.extras and getattr(self, "extras_override", None) is not None:
             self.extra = self.extras_override  # tests: pin the (random, per-call) conditioner to recorded values
@@ -183,12 +210,10 @@ class GraphedStep(object):
             self.extra = ode.conditioned_extras(self.B, self.IW, self.batch.dev_1hot)  # trainable: gradient flows back
             self.extra_grad = True
         elif self.extras:
-            rows = []
-            for k, name in enumerate(self.extras):
-                cond = torch.relu((self.batch.dev_1hot * self.rel[k]) @ self.cond_w[k:k + 1].t())
-                cond = cond.repeat([self.IW, 1]).reshape(self.N)
-                rows.append(1.0 + cond if name in ode.default_devices else cond)
-            self.extra = torch.stack(rows).contiguous()
+            L.check(lib.vh_device_conditioner(self.prob.vh_dtype, self.B, self.IW, self.cond_w.shape[1], len(self.extras),
+                                              _ptr(self.batch.dev_1hot), _ptr(self.rel_mat), _ptr(self.cond_w),
+                                              _ptr(self.plus_one), _ptr(self.extra_static), s))
+            self.extra = self.extra_static
         else:
             self.extra = None
         w = ode.flat_weights()
@@ -228,14 +253,23 @@ class GraphedStep(object):
         """encoder backward, ONE gradient all-reduce, fused Adam (captured)."""
         opt = self.tr.optimizer
         opt.zero_grad()
-        outs, grads = [self.q_mu, self.q_prec], [self.buf.d_q_mu, self.buf.d_q_prec]
+        outs, grads = [], []
+        if self.fused_encoder:
+            g = [p.grad for p in self.model.encoder.fused_parameters()]
+            gr = L.vh_encoder_grads(d_q_mu=_ptr(self.buf.d_q_mu), d_q_prec=_ptr(self.buf.d_q_prec), g_conv_w=_ptr(g[0]),
+                                    g_conv_b=_ptr(g[1]), g_lin_w=_ptr(g[2]), g_lin_b=_ptr(g[3]), g_local_w=_nz(g[4]),
+                                    g_local_b=_nz(g[5]), g_gcond_w=_nz(g[6]), g_global_free=_nz(g[7]), d_pre=_ptr(self.enc_dpre))
+            L.check(self.prob.lib.vh_encoder_bwd(C.byref(self.enc_desc), C.byref(self._enc_io), C.byref(gr), _stream()))
+        else:
+            outs, grads = [self.q_mu, self.q_prec], [self.buf.d_q_mu, self.buf.d_q_prec]
         if self.weights is not None and self.weights.requires_grad:
             outs.append(self.weights)
             grads.append(self.d_weights)
         if self.extra_grad:
             outs.append(self.extra)
             grads.append(self.d_extra)
-        torch.autograd.backward(outs, grads)
+        if outs:
+            torch.autograd.backward(outs, grads)
         if self.pg is not None:
             torch.distributed.all_reduce(opt.grad, group=self.pg)
         opt.step()
