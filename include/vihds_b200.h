@@ -55,7 +55,11 @@ enum vh_model {
   VH_MODEL_RELAY_CONSTANT = 4,            /* models/relay_constant.py:137-196 */
   VH_MODEL_RELAY_CONSTANT_PRECISIONS = 5, /* models/relay_constant.py:199-263 */
   VH_MODEL_DR_BLACKBOX = 6,               /* models/dr_blackbox.py:61-125 */
-  VH_MODEL_COUNT = 7
+  VH_MODEL_AUTO_CONSTANT = 7,             /* models/auto_constant.py:63-90 */
+  VH_MODEL_AUTO_CONSTANT_PRECISIONS = 8,  /* models/auto_constant.py:93-132 */
+  VH_MODEL_PRPR_CONSTANT = 9,             /* models/prpr_constant.py:61-81 */
+  VH_MODEL_PRPR_CONSTANT_PRECISIONS = 10, /* models/prpr_constant.py:84-130 */
+  VH_MODEL_COUNT = 11
 };
 
 /* params.solver values (vihds/ode.py:75-81) */

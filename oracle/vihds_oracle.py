@@ -180,6 +180,37 @@ class DrConstantRHS:
         return dX
 
 
+class GrowthRHS:
+    """models/auto_constant.py:11-60 (4 species: OD, RFP, F530, F480) and models/prpr_constant.py:11-58 (6 species:
+    + constitutively expressed YFP, CFP): growth + dilution without receivers."""
+
+    def __init__(self, th, prpr, precisions=None):
+        cl = torch.clamp
+        self.r, self.K = cl(th["r"], 0.0, 4.0), cl(th["K"], 0.0, 4.0)
+        self.tlag, self.rc, self.a530, self.a480 = th["tlag"], th["rc"], th["a530"], th["a480"]
+        self.drfp = cl(th["drfp"], 1e-12, 2.0)
+        self.prpr = prpr
+        if prpr:
+            self.dyfp, self.dcfp = cl(th["dyfp"], 1e-12, 2.0), cl(th["dcfp"], 1e-12, 2.0)
+            self.aYFP, self.aCFP = th["aYFP_PR"], th["aCFP_PR"]
+        self.precisions = precisions
+
+    def __call__(self, t, state):
+        x, rfp = state[:, :, 0], state[:, :, 1]
+        gamma = self.r * torch.sigmoid(4.0 * (t - self.tlag)) * (1.0 - x / self.K)
+        d = [gamma * x, self.rc - (gamma + self.drfp) * rfp]
+        if self.prpr:
+            yfp, cfp, f530, f480 = (state[:, :, i] for i in (2, 3, 4, 5))
+            d += [self.rc * self.aYFP - (gamma + self.dyfp) * yfp, self.rc * self.aCFP - (gamma + self.dcfp) * cfp]
+        else:
+            f530, f480 = state[:, :, 2], state[:, :, 3]
+        d += [self.rc * self.a530 - gamma * f530, self.rc * self.a480 - gamma * f480]
+        dX = torch.stack(d, dim=2)
+        if self.precisions is not None:
+            return torch.cat([dX, self.precisions(t, state, None)], dim=2)
+        return dX
+
+
 class BlackboxRHS:
     """models/dr_blackbox.py:15-58 + vihds/ode.py:119-138 (NeuralStates)."""
 
@@ -253,6 +284,8 @@ MODEL_FAMILY = {
     "dr_constant_precisions": ("dr", 1, True), "dr_constant_precisions_v2": ("dr", 2, True),
     "relay_constant": ("relay", 1, False), "relay_constant_precisions": ("relay", 1, True),
     "dr_blackbox": ("blackbox", 0, True),
+    "auto_constant": ("auto", 1, False), "auto_constant_precisions": ("auto", 1, True),
+    "prpr_constant": ("prpr", 1, False), "prpr_constant_precisions": ("prpr", 1, True),
 }
 
 
@@ -278,6 +311,14 @@ def decode(model, solver, th, times, inputs, dev_1hot, weights=None, params=None
         if dyn_prec:
             x0 += [th["init_prec_x"], th["init_prec_rfp"], th["init_prec_yfp"], th["init_prec_cfp"]]
         f = DrConstantRHS(th, inputs, version=version, precisions=prec, relay=(family == "relay"))
+    elif family in ("auto", "prpr"):
+        prec = None
+        if dyn_prec:
+            prec = NeuralPrecisionsOracle({k[len("precisions."):]: v for k, v in weights.items()}, torch.tanh)
+        x0 = [th["init_x"], th["init_rfp"]] + ([th["init_yfp"], th["init_cfp"]] if family == "prpr" else []) + [zero, zero]
+        if dyn_prec:
+            x0 += [th["init_prec_x"], th["init_prec_rfp"], th["init_prec_yfp"], th["init_prec_cfp"]]
+        f = GrowthRHS(th, family == "prpr", precisions=prec)
     else:
         n_lat = params["n_latent_species"]
         x0 = [th["init_x"], th["init_rfp"], th["init_yfp"], th["init_cfp"]]
@@ -292,7 +333,7 @@ def decode(model, solver, th, times, inputs, dev_1hot, weights=None, params=None
         precisions = torch.stack([th[n] for n in ("prec_x", "prec_rfp", "prec_yfp", "prec_cfp")], dim=-1)
         precisions = precisions.unsqueeze(3).repeat(1, 1, 1, len(times))
     od = x_states[:, :, 0, :]
-    if family == "blackbox":
+    if family in ("blackbox", "auto"):  # models/dr_blackbox.py:112-121, models/auto_constant.py:81-89
         obs = [od, od * x_states[:, :, 1, :], od * x_states[:, :, 2, :], od * x_states[:, :, 3, :]]
     else:
         obs = [od, od * x_states[:, :, 1, :], od * (x_states[:, :, 2, :] + x_states[:, :, 4, :]),

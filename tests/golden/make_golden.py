@@ -175,10 +175,24 @@ def dump_dataset(spec, tag):
     print("==> %s: %d individuals, T=%d" % (tag, len(ds), ds.n_times))
 
 
-def main():
-    for spec in ("dr_constant_one", "dr_constant_icml", "dr_blackbox_icml", "relay_constant_precisions",
-                 "dr_constant_v2", "dr_constant_precisions", "dr_constant_precisions_v2"):
+SPECS = ("dr_constant_one", "dr_constant_icml", "dr_blackbox_icml", "relay_constant_precisions", "dr_constant_v2",
+         "dr_constant_precisions", "dr_constant_precisions_v2", "auto_constant", "auto_constant_precisions",
+         "prpr_constant", "prpr_constant_precisions")
+
+
+def small_models():
+    """auto_* / prpr_*: the remaining runnable specs of the reference (10 of 16 run)."""
+    for spec in ("auto_constant", "auto_constant_precisions", "prpr_constant", "prpr_constant_precisions"):
+        run_case(spec, "midpoint", "float32", 8, n_batch=12)
+    run_case("auto_constant_precisions", "midpoint", "float64", 8, n_batch=6)
+    run_case("prpr_constant", "modeuler", "float32", 8, n_batch=12)
+
+
+def main(group="all"):
+    for spec in SPECS:
         dump_spec(spec)
+    if group == "small":
+        return small_models()
     # config 1: every fixed-step solver, fp32; fp64 for the default and the in-repo solver
     for solver in ("midpoint", "rk4", "euler", "modeuler", "modeulerwhile"):
         run_case("dr_constant_one", solver, "float32", 5, n_batch=8)
@@ -197,9 +211,10 @@ def main():
     run_case("dr_constant_v2", "midpoint", "float32", 8, n_batch=12)
     run_case("dr_constant_precisions", "midpoint", "float32", 8, n_batch=12)
     run_case("dr_constant_precisions_v2", "midpoint", "float32", 8, n_batch=12)
+    small_models()
     dump_dataset("dr_constant_icml", "dataset_dr_icml")
     dump_dataset("relay_constant_precisions", "dataset_relay")
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else "all")

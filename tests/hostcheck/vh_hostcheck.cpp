@@ -108,7 +108,7 @@ int bwd_t(const vh_problem* p, const vh_bwd_io* io) {
     BbBwdRunner<R> f{&a};
     return bb_solver<BbRhs<R, 2, 25, 20, 21> >(p->solver, f);
   }
-  size_t nw = model_is_dyn(p->model) ? (size_t)2 * (4 * (model_species(p->model) + 1) + 4) : 0;
+  size_t nw = model_is_dyn(p->model) ? (size_t)2 * (4 * (model_species(p->model) + 1) + 4) : 0;  // LinPrecNet::NW
   BwdRunner<R> f{&a, nw};
   return dispatch_dr<R>(p->model, p->solver, f);
 }

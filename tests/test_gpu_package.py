@@ -68,6 +68,8 @@ def pin_conditioner(model, case):
     ("dr_constant_one_midpoint_f32_iw5", "dr_constant_one", (4, 100, 2, 1)),
     ("relay_constant_precisions_midpoint_f32_iw8", "relay_constant_precisions", None),
     ("dr_blackbox_icml_midpoint_f32_iw8", "dr_blackbox_icml", None),
+    ("auto_constant_precisions_midpoint_f32_iw8", "auto_constant_precisions", (4, 100, 1, 1)),
+    ("prpr_constant_midpoint_f32_iw8", "prpr_constant", (4, 200, 1, 1)),
 ])
 def test_model_forward_cost_backward_match_reference(case_name, spec, dims):
     case = load_case(case_name)
@@ -274,3 +276,17 @@ def test_device_conditioner_kernel_matches_reference_quirk():
     L.check(L.load().vh_device_conditioner(0, B, IW, D, 2, p(dev_1hot), p(rel), p(w), p(plus), p(out), None))
     torch.cuda.synchronize()
     assert torch.allclose(out, ref, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("spec", ["dr_constant_icml", "dr_blackbox_icml", "relay_constant_precisions"])
+def test_training_run_prints_finite_elbo(spec, capsys):
+    """tests/test_run_xval.py of the reference: a short run (2 epochs, IW = 10, evaluation every epoch) completes, prints
+    one 'iwae-elbo' line per evaluation, and the ELBO is finite."""
+    settings, par, model, training = build(spec, iw=10)
+    training.args.epochs, training.args.test_epoch, training.args.test_samples = 2, 1, 10
+    np.random.seed(0)
+    torch.manual_seed(0)
+    assert training.run(verbose=True) is True
+    lines = [l for l in capsys.readouterr().out.splitlines() if "iwae-elbo" in l]
+    assert len(lines) == 2
+    assert all(np.isfinite(float(l.split("=")[-1])) for l in lines)

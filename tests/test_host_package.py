@@ -122,3 +122,24 @@ def test_engine_refuses_cpu_tensors():
     th.add("r", torch.ones(2, 3))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.simulate(cfg, torch.linspace(0, 1, 5), th, torch.zeros(2, 2), torch.zeros(2, 1))
+
+
+def test_conditioner_weight_draw_matches_reference_construction():
+    """models._draw_conditioner_weight consumes the torch CPU RNG exactly like building the reference's
+    DeviceConditioner (vihds/ode.py:99-116): nn.Linear default init, xavier_uniform_, normal_(2, 1.5)."""
+    from torch import nn
+
+    from vihds_b200.models import _draw_conditioner_weight
+
+    for d in (7, 1, 12):
+        torch.manual_seed(11)
+        got = [_draw_conditioner_weight(d) for _ in range(3)]
+        after = torch.rand(1)
+        torch.manual_seed(11)
+        ref = []
+        for _ in range(3):
+            lin = nn.Linear(d, 1, False)
+            nn.init.xavier_uniform_(lin.weight)
+            nn.init.normal_(lin.weight, mean=2.0, std=1.5)
+            ref.append(lin.weight.detach().clone())
+        assert all(torch.equal(a, b) for a, b in zip(got, ref)) and torch.equal(after, torch.rand(1))

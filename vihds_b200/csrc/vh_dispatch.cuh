@@ -7,10 +7,15 @@
 
 namespace vh {
 
-inline bool model_is_dr_family(int model) { return model >= VH_MODEL_DR_CONSTANT && model <= VH_MODEL_RELAY_CONSTANT_PRECISIONS; }
+// white-box families (hand-written RHS + VJP templates): double receiver / relay (DrModel) and growth-only (GrowthModel)
+inline bool model_is_dr_family(int model) {
+  return (model >= VH_MODEL_DR_CONSTANT && model <= VH_MODEL_RELAY_CONSTANT_PRECISIONS) ||
+         (model >= VH_MODEL_AUTO_CONSTANT && model <= VH_MODEL_PRPR_CONSTANT_PRECISIONS);
+}
 inline bool model_is_dyn(int model) {
   return model == VH_MODEL_DR_CONSTANT_PRECISIONS || model == VH_MODEL_DR_CONSTANT_PRECISIONS_V2 ||
-         model == VH_MODEL_RELAY_CONSTANT_PRECISIONS || model == VH_MODEL_DR_BLACKBOX;
+         model == VH_MODEL_RELAY_CONSTANT_PRECISIONS || model == VH_MODEL_DR_BLACKBOX ||
+         model == VH_MODEL_AUTO_CONSTANT_PRECISIONS || model == VH_MODEL_PRPR_CONSTANT_PRECISIONS;
 }
 inline int model_species(int model) {
   switch (model) {
@@ -18,7 +23,12 @@ inline int model_species(int model) {
     case VH_MODEL_RELAY_CONSTANT_PRECISIONS:
       return 12;
     case VH_MODEL_DR_BLACKBOX:
+    case VH_MODEL_AUTO_CONSTANT:
+    case VH_MODEL_AUTO_CONSTANT_PRECISIONS:
       return 4;
+    case VH_MODEL_PRPR_CONSTANT:
+    case VH_MODEL_PRPR_CONSTANT_PRECISIONS:
+      return 6;
     default:
       return 8;
   }
@@ -32,7 +42,8 @@ inline const char* build_call(const vh_problem* p, const vh_fwd_io* io, const vh
   if (p->P < 0 || p->P > VH_MAX_SLOTS) return "P out of range (0..VH_MAX_SLOTS)";
   if ((long long)p->B * p->IW > 0x7fffffffLL) return "B*IW exceeds int32";
   a.B = p->B; a.IW = p->IW; a.N = p->B * p->IW; a.T = p->T; a.P = p->P; a.C = p->C; a.D = p->D; a.E = p->E;
-  if (p->C < 2) return "C (treatments) must be >= 2";
+  if (p->C < 2 && p->model >= VH_MODEL_DR_CONSTANT && p->model <= VH_MODEL_RELAY_CONSTANT_PRECISIONS)
+    return "C (treatments) must be >= 2 for the double-receiver / relay models (C6, C12)";
   a.bb_nlat = p->n_z + p->n_x + p->n_y;
   a.bb_ny = p->n_y;
   a.bb_noff = (p->model == VH_MODEL_DR_BLACKBOX && p->P > 0) ? p->E : 0;
@@ -112,6 +123,10 @@ inline int dispatch_dr(int model, int solver, F& f) {
     case VH_MODEL_DR_CONSTANT_PRECISIONS_V2: return dispatch_solver<DrModel<R, 2, false, true> >(solver, f);
     case VH_MODEL_RELAY_CONSTANT: return dispatch_solver<DrModel<R, 1, true, false> >(solver, f);
     case VH_MODEL_RELAY_CONSTANT_PRECISIONS: return dispatch_solver<DrModel<R, 1, true, true> >(solver, f);
+    case VH_MODEL_AUTO_CONSTANT: return dispatch_solver<GrowthModel<R, 4, false> >(solver, f);
+    case VH_MODEL_AUTO_CONSTANT_PRECISIONS: return dispatch_solver<GrowthModel<R, 4, true> >(solver, f);
+    case VH_MODEL_PRPR_CONSTANT: return dispatch_solver<GrowthModel<R, 6, false> >(solver, f);
+    case VH_MODEL_PRPR_CONSTANT_PRECISIONS: return dispatch_solver<GrowthModel<R, 6, true> >(solver, f);
     default: return VH_ERR_UNSUPPORTED;
   }
 }

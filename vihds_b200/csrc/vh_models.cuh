@@ -23,6 +23,7 @@ enum DrSlot : int {
   S_init_x, S_init_rfp, S_init_yfp, S_init_cfp, S_init_luxR, S_init_lasR,
   S_prec_x, S_prec_rfp, S_prec_yfp, S_prec_cfp,  // constant precisions: prec_*; dynamic: init_prec_*
   S_dlasI, S_dluxI, S_KC6, S_KC12, S_Klux, S_Klas, S_init_luxI, S_init_lasI,  // relay
+  S_aYFP_PR, S_aCFP_PR,                                                           // prpr_constant
   DR_NSLOT
 };
 
@@ -32,7 +33,8 @@ static const char* const kDrSlotNames[DR_NSLOT] = {
     "KR6", "KR12", "KS6", "KS12", "eS6", "eR12",
     "init_x", "init_rfp", "init_yfp", "init_cfp", "init_luxR", "init_lasR",
     "prec_x", "prec_rfp", "prec_yfp", "prec_cfp",
-    "dlasI", "dluxI", "KC6", "KC12", "Klux", "Klas", "init_luxI", "init_lasI"};
+    "dlasI", "dluxI", "KC6", "KC12", "Klux", "Klas", "init_luxI", "init_lasI",
+    "aYFP_PR", "aCFP_PR"};
 static const char* const kDrDynPrecNames[4] = {"init_prec_x", "init_prec_rfp", "init_prec_yfp", "init_prec_cfp"};
 
 // per-trajectory constants of the RHS (clamped parameters, Hill fractions, pre-multiplied production rates)
@@ -69,7 +71,7 @@ struct DrModel {
 
   VH_HD static constexpr bool uses(int s) {
     return (s <= S_nS) || (VERSION == 1 && s >= S_KR6 && s <= S_KS12) || (VERSION == 2 && (s == S_eS6 || s == S_eR12)) ||
-           (s >= S_init_x && s <= S_prec_cfp) || (RELAY && s >= S_dlasI);
+           (s >= S_init_x && s <= S_prec_cfp) || (RELAY && s >= S_dlasI && s <= S_init_lasI);
   }
 
   // treatments -> inducer concentrations, models/dr_constant.py:26
@@ -390,6 +392,186 @@ struct DrModel {
     gx[4] += gxp[2] * x[0];
     gx[3] += gxp[3] * x[0];
     gx[5] += gxp[3] * x[0];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Growth-only family: auto_constant (NSP = 4: OD, RFP, F530, F480; models/auto_constant.py:11-60) and prpr_constant
+// (NSP = 6: + YFP, CFP expressed constitutively; models/prpr_constant.py:11-58).  The double-receiver right-hand side
+// with the receiver / promoter terms removed; same slot names, same interface as DrModel.
+// ---------------------------------------------------------------------------------------------------------------
+enum GrConst : int { G_r = 0, G_K, G_tlag, G_rc, G_drfp, G_dyfp, G_dcfp, G_cY, G_cC, G_p530, G_p480, GR_NCONST };
+
+template <typename R, int NSP_, bool DYN_>
+struct GrowthModel {
+  typedef R real;
+  static constexpr bool DYN = DYN_, RELAY = false, BLACKBOX = false;
+  static constexpr bool PRPR = NSP_ == 6;
+  static constexpr int NSLOT = DR_NSLOT;
+  static constexpr int NS = NSP_;
+  static constexpr int S = NS + (DYN ? 4 : 0);
+  static constexpr int NC = GR_NCONST;
+  static constexpr int NIN = NS + 1;
+  static constexpr int I530 = PRPR ? 4 : 2, I480 = PRPR ? 5 : 3;  // state index of the autofluorescence species
+  static_assert(NSP_ == 4 || NSP_ == 6, "auto_constant has 4 species, prpr_constant 6");
+
+  struct Consts {
+    R v[NC];
+    R iK;
+  };
+  struct Mid {
+    R sg, gr, g, gam;
+  };
+
+  VH_HD static constexpr bool uses(int s) {
+    return s == S_r || s == S_K || s == S_tlag || s == S_rc || s == S_a530 || s == S_a480 || s == S_drfp || s == S_init_x ||
+           s == S_init_rfp || (s >= S_prec_x && s <= S_prec_cfp) ||
+           (PRPR && (s == S_dyfp || s == S_dcfp || s == S_aYFP_PR || s == S_aCFP_PR || s == S_init_yfp || s == S_init_cfp));
+  }
+  VH_HD static void treatments(const R*, R& c6, R& c12) { c6 = c12 = R(0); }  // treatments do not enter these models
+
+  VH_HD static void setup(const R* th, R, R, Consts& c) {
+    R* v = c.v;
+    v[G_r] = clampv(th[S_r], R(0), R(4));
+    v[G_K] = clampv(th[S_K], R(0), R(4));
+    v[G_tlag] = th[S_tlag];
+    v[G_rc] = th[S_rc];
+    v[G_drfp] = clampv(th[S_drfp], R(1e-12), R(2));
+    v[G_dyfp] = PRPR ? clampv(th[S_dyfp], R(1e-12), R(2)) : R(0);
+    v[G_dcfp] = PRPR ? clampv(th[S_dcfp], R(1e-12), R(2)) : R(0);
+    v[G_cY] = PRPR ? th[S_rc] * th[S_aYFP_PR] : R(0);
+    v[G_cC] = PRPR ? th[S_rc] * th[S_aCFP_PR] : R(0);
+    v[G_p530] = th[S_rc] * th[S_a530];
+    v[G_p480] = th[S_rc] * th[S_a480];
+    c.iK = R(1) / v[G_K];
+  }
+  VH_HD static void setup_vjp(const R* th, R, R, const Consts&, const Consts& gc, R* gth) {
+    const R* g = gc.v;
+    gth[S_r] += g[G_r] * clampmask(th[S_r], R(0), R(4));
+    gth[S_K] += g[G_K] * clampmask(th[S_K], R(0), R(4));
+    gth[S_tlag] += g[G_tlag];
+    gth[S_drfp] += g[G_drfp] * clampmask(th[S_drfp], R(1e-12), R(2));
+    R grc = g[G_rc] + g[G_p530] * th[S_a530] + g[G_p480] * th[S_a480];
+    gth[S_a530] += g[G_p530] * th[S_rc];
+    gth[S_a480] += g[G_p480] * th[S_rc];
+    if (PRPR) {
+      gth[S_dyfp] += g[G_dyfp] * clampmask(th[S_dyfp], R(1e-12), R(2));
+      gth[S_dcfp] += g[G_dcfp] * clampmask(th[S_dcfp], R(1e-12), R(2));
+      grc += g[G_cY] * th[S_aYFP_PR] + g[G_cC] * th[S_aCFP_PR];
+      gth[S_aYFP_PR] += g[G_cY] * th[S_rc];
+      gth[S_aCFP_PR] += g[G_cC] * th[S_rc];
+    }
+    gth[S_rc] += grc;
+  }
+
+  VH_HD static void init_state(const R* th, R, R, R* x) {
+    x[0] = th[S_init_x];
+    x[1] = th[S_init_rfp];
+    if (PRPR) {
+      x[2] = th[S_init_yfp];
+      x[3] = th[S_init_cfp];
+    }
+    x[I530] = R(0);
+    x[I480] = R(0);
+    if (DYN) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) x[NS + o] = th[S_prec_x + o];
+    }
+  }
+  VH_HD static void init_state_vjp(const R* gx, R* gth) {
+    gth[S_init_x] += gx[0];
+    gth[S_init_rfp] += gx[1];
+    if (PRPR) {
+      gth[S_init_yfp] += gx[2];
+      gth[S_init_cfp] += gx[3];
+    }
+    if (DYN) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gx[NS + o];
+    }
+  }
+
+  VH_HD static void mid(R t, const R* x, const Consts& c, Mid& m) {
+    m.sg = sigmoid(R(4) * (t - c.v[G_tlag]));
+    m.gr = c.v[G_r] * m.sg;
+    m.g = R(1) - x[0] * c.iK;
+    m.gam = m.gr * m.g;
+  }
+  VH_HD static void rhs_from(const R* x, const Consts& c, const Mid& m, R* dx) {
+    const R* v = c.v;
+    dx[0] = m.gam * x[0];
+    dx[1] = v[G_rc] - (m.gam + v[G_drfp]) * x[1];
+    if (PRPR) {
+      dx[2] = v[G_cY] - (m.gam + v[G_dyfp]) * x[2];
+      dx[3] = v[G_cC] - (m.gam + v[G_dcfp]) * x[3];
+    }
+    dx[I530] = v[G_p530] - m.gam * x[I530];
+    dx[I480] = v[G_p480] - m.gam * x[I480];
+  }
+  VH_HD static void rhs(R t, const R* x, const Consts& c, R* dx) {
+    Mid m;
+    mid(t, x, c, m);
+    rhs_from(x, c, m, dx);
+  }
+  VH_HD static void rhs_vjp_from(const R* x, const Consts& c, const Mid& m, const R* g, R* gx, Consts& gcs) {
+    const R* v = c.v;
+    R* gc = gcs.v;
+    R ggam = g[0] * x[0] - g[1] * x[1] - g[I530] * x[I530] - g[I480] * x[I480];
+    gx[0] += g[0] * m.gam;
+    gx[1] -= g[1] * (m.gam + v[G_drfp]);
+    gx[I530] -= g[I530] * m.gam;
+    gx[I480] -= g[I480] * m.gam;
+    gc[G_drfp] -= g[1] * x[1];
+    gc[G_rc] += g[1];
+    gc[G_p530] += g[I530];
+    gc[G_p480] += g[I480];
+    if (PRPR) {
+      ggam -= g[2] * x[2] + g[3] * x[3];
+      gx[2] -= g[2] * (m.gam + v[G_dyfp]);
+      gx[3] -= g[3] * (m.gam + v[G_dcfp]);
+      gc[G_dyfp] -= g[2] * x[2];
+      gc[G_dcfp] -= g[3] * x[3];
+      gc[G_cY] += g[2];
+      gc[G_cC] += g[3];
+    }
+    const R ggr = ggam * m.g, gg = ggam * m.gr;
+    gc[G_r] += ggr * m.sg;
+    gc[G_tlag] -= R(4) * ggr * v[G_r] * m.sg * (R(1) - m.sg);
+    gx[0] -= gg * c.iK;
+    gc[G_K] += gg * x[0] * (c.iK * c.iK);
+  }
+  VH_HD static void rhs_vjp(R t, const R* x, const Consts& c, const R* g, R* gx, Consts& gcs) {
+    Mid m;
+    mid(t, x, c, m);
+    rhs_vjp_from(x, c, m, g, gx, gcs);
+  }
+
+  // prpr: vihds/ode.py:84-93 (default observe); auto: models/auto_constant.py:81-89
+  VH_HD static void observe(const R* x, R* xp) {
+    xp[0] = x[0];
+    xp[1] = x[0] * x[1];
+    if (PRPR) {
+      xp[2] = x[0] * (x[2] + x[4]);
+      xp[3] = x[0] * (x[3] + x[5]);
+    } else {
+      xp[2] = x[0] * x[2];
+      xp[3] = x[0] * x[3];
+    }
+  }
+  VH_HD static void observe_vjp(const R* x, const R* gxp, R* gx) {
+    if (PRPR) {
+      gx[0] += gxp[0] + gxp[1] * x[1] + gxp[2] * (x[2] + x[4]) + gxp[3] * (x[3] + x[5]);
+      gx[1] += gxp[1] * x[0];
+      gx[2] += gxp[2] * x[0];
+      gx[4] += gxp[2] * x[0];
+      gx[3] += gxp[3] * x[0];
+      gx[5] += gxp[3] * x[0];
+    } else {
+      gx[0] += gxp[0] + gxp[1] * x[1] + gxp[2] * x[2] + gxp[3] * x[3];
+      gx[1] += gxp[1] * x[0];
+      gx[2] += gxp[2] * x[0];
+      gx[3] += gxp[3] * x[0];
+    }
   }
 };
 

@@ -81,12 +81,14 @@ class NeuralPrecisions(nn.Module):
 # ---------------------------------------------------------------------------------------------------------------
 def _draw_conditioner_weight(n_inputs):
     """The reference builds a FRESH ``DeviceConditioner`` on every call (vihds/ode.py:48, :99-116): a bias-free
-    Linear(n_inputs, 1) whose weight ends up N(2, 1.5), after the default and the xavier initialisers have consumed
-    their share of the torch CPU RNG stream.  Reproduced draw for draw so that a seeded run matches."""
-    lin = nn.Linear(n_inputs, 1, False)
-    nn.init.xavier_uniform_(lin.weight)
-    nn.init.normal_(lin.weight, mean=2.0, std=1.5)
-    return lin.weight.detach()
+    Linear(n_inputs, 1) whose weight ends up N(2, 1.5) after the default (kaiming-uniform) and the xavier-uniform
+    initialisers have each consumed n_inputs uniform draws of the torch CPU RNG stream.  Reproduced draw for draw --
+    two uniform_ fills and one normal_ -- without constructing the module (tests/test_host_package.py pins the
+    equality with the nn.Linear construction), so that a seeded run matches the reference."""
+    w = torch.empty(1, n_inputs)
+    w.uniform_(-1.0, 1.0)
+    w.uniform_(-1.0, 1.0)
+    return w.normal_(mean=2.0, std=1.5)
 
 
 class OdeModel(nn.Module):
@@ -275,6 +277,64 @@ class Relay_Constant_Precisions(Relay_Constant):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# growth-only models (models/auto_constant.py:63-132, models/prpr_constant.py:61-130)
+# ---------------------------------------------------------------------------------------------------------------
+class Auto_Constant(OdeModel):
+    kernel_model = "auto_constant"
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.precisions = ConstantPrecisions(["prec_x", "prec_rfp", "prec_yfp", "prec_cfp"])
+        self.species = ["OD", "RFP", "F530", "F480"]
+        self.n_species = 4
+
+    def initialize_state(self, theta, _treatments):
+        zero = torch.zeros_like(theta.init_x)
+        rows = [theta.init_x, theta.init_rfp, zero, zero]
+        if self.precisions.dynamic:
+            rows += [theta.init_prec_x, theta.init_prec_rfp, theta.init_prec_yfp, theta.init_prec_cfp]
+        return torch.stack(rows, dim=2)
+
+    @classmethod
+    def observe(cls, x_sample, _theta):
+        od = x_sample[:, :, 0, :]
+        return torch.stack([od, od * x_sample[:, :, 1, :], od * x_sample[:, :, 2, :], od * x_sample[:, :, 3, :]], dim=2)
+
+
+class Auto_Constant_Precisions(Auto_Constant):
+    kernel_model = "auto_constant_precisions"
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.precisions = NeuralPrecisions(self.n_species, config.params.n_hidden_decoder_precisions, 4)
+
+
+class PRPR_Constant(OdeModel):
+    kernel_model = "prpr_constant"
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.precisions = ConstantPrecisions(["prec_x", "prec_rfp", "prec_yfp", "prec_cfp"])
+        self.species = ["OD", "RFP", "YFP", "CFP", "F530", "F480"]
+        self.n_species = 6
+
+    def initialize_state(self, theta, _treatments):
+        zero = torch.zeros_like(theta.init_x)
+        rows = [theta.init_x, theta.init_rfp, theta.init_yfp, theta.init_cfp, zero, zero]
+        if self.precisions.dynamic:
+            rows += [theta.init_prec_x, theta.init_prec_rfp, theta.init_prec_yfp, theta.init_prec_cfp]
+        return torch.stack(rows, dim=2)
+
+
+class PRPR_Constant_Precisions(PRPR_Constant):
+    kernel_model = "prpr_constant_precisions"
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.precisions = NeuralPrecisions(self.n_species, config.params.n_hidden_decoder_precisions, 4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # black box (models/dr_blackbox.py:61-125, vihds/ode.py:119-138)
 # ---------------------------------------------------------------------------------------------------------------
 class NeuralStates(nn.Module):
@@ -361,6 +421,10 @@ class DR_Blackbox(OdeModel):
 
 
 LOOKUP = {
+    "auto_constant": Auto_Constant,
+    "auto_constant_precisions": Auto_Constant_Precisions,
+    "prpr_constant": PRPR_Constant,
+    "prpr_constant_precisions": PRPR_Constant_Precisions,
     "dr_blackbox": DR_Blackbox,
     "dr_constant": DR_Constant,
     "dr_constant_v2": DR_Constant_V2,
