@@ -78,7 +78,25 @@ def test_edge_shapes_dynamic_precisions_and_relay():
     assert _rel(r["d_weights"], gw_ref) < 3e-3
 
 
-def test_edge_shapes_blackbox():
+@pytest.mark.parametrize("wgrad", ["scalar", "mma"])
+def test_edge_shapes_blackbox(wgrad, monkeypatch):
+    """Both weight-gradient sinks of the black-box reverse kernel (scalar FMAs / mma.sync 3xTF32 on the tensor cores).
+    The mode is latched on the first black-box launch of a process, hence the subprocess for the non-default one."""
+    if wgrad == "mma":
+        import os
+        import subprocess
+        import sys
+
+        env = dict(os.environ, VIHDS_BB_WGRAD="mma")
+        code = ("import sys; sys.path[:0] = [%r, %r, %r]; import test_gpu_properties as t; "
+                "t._blackbox_edge_check()" % (H.ROOT, os.path.join(H.ROOT, "tests"), os.path.join(H.ROOT, "oracle")))
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return
+    _blackbox_edge_check()
+
+
+def _blackbox_edge_check():
     case = load_case("dr_blackbox_icml_midpoint_f32_iw8")
     sub = sub_case(case, [0, 1, 2, 3, 4], 7, 9)  # N = 35: the warp-level weight-gradient GEMM with idle lanes
     ref = O.elbo_step(sub)

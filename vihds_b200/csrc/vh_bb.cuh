@@ -56,14 +56,19 @@ VH_HD R relu_mask(R pre, R g) {
 //   [RS+H+HP, ROW)       cotangents of hc | hpc, accumulated over all evaluations of the reverse sweep
 template <int NST, int H, int HP, int NC>
 struct BbRow {
-  static constexpr int RS1 = 3 * NST + 2 * H, RS2 = 1 + NST + 2 * HP + 8;
+  // staging regions are padded to tensor-core tile multiples (8 for the n side, 32 for the m side); entry H of the
+  // hidden vector is a constant 1 so that the bias gradients fall out of the same GEMM, the rest of the padding is 0
+  static constexpr int XP = 8, HM = 32, GZ = 16, GZP = 8;
+  static_assert(NST <= XP && 1 + NST <= XP && H + 1 <= HM && HP + 1 <= HM && 2 * NST <= GZ, "tile padding");
+  // states staging
+  static constexpr int sX = 0, sHID = XP, sGPRE = XP + HM, sGZP = XP + 2 * HM, sGZD = sGZP + NST;
+  static constexpr int RS1 = XP + 2 * HM + GZ;
+  // precisions staging ([t, x] is one operand; gzp | gzd are contiguous: one 8-wide operand)
+  static constexpr int pT = 0, pX = 1, pHP = XP, pGPRE = XP + HM, pGZP = XP + 2 * HM, pGZD = pGZP + 4;
+  static constexpr int RS2 = XP + 2 * HM + GZP;
   static constexpr int RS = (RS1 > RS2 ? RS1 : RS2) > NC ? (RS1 > RS2 ? RS1 : RS2) : NC;
   static constexpr int HC = RS, HPC = RS + H, GHC = RS + H + HP, GHPC = RS + 2 * H + HP;
   static constexpr int ROW = (RS + 2 * (H + HP)) | 1;
-  // states staging
-  static constexpr int sX = 0, sHID = NST, sGPRE = NST + H, sGZP = NST + 2 * H, sGZD = 2 * NST + 2 * H;
-  // precisions staging
-  static constexpr int pT = 0, pX = 1, pHP = 1 + NST, pGPRE = 1 + NST + HP, pGZP = 1 + NST + 2 * HP, pGZD = 5 + NST + 2 * HP;
 };
 
 // The hidden layers are ROLLED loops over scratch in shared memory (small code, few registers); only the short
@@ -193,6 +198,17 @@ struct BbRhs {
 #pragma unroll
         for (int s = 0; s < NST; ++s) gx[s] += wr[s] * gh;
       }
+      // tile padding (the precision phase reuses this space): hidden unit H is the constant 1 of the bias
+      // gradients, everything else zero
+#pragma unroll
+      for (int i = NST; i < ROWL::XP; ++i) row[ROWL::sX + i] = R(0);
+#pragma unroll
+      for (int i = H; i < ROWL::HM; ++i) {
+        row[ROWL::sHID + i] = i == H ? R(1) : R(0);
+        row[ROWL::sGPRE + i] = R(0);
+      }
+#pragma unroll
+      for (int i = 2 * NST; i < ROWL::GZ; ++i) row[ROWL::sGZP + i] = R(0);
       gw.states(row);
     }
     {  // precision net
@@ -221,6 +237,13 @@ struct BbRhs {
         const R* q = w + L::Q1 + h * (L::nin + 1);
 #pragma unroll
         for (int s = 0; s < NST; ++s) gx[s] += q[1 + s] * gh;
+      }
+#pragma unroll
+      for (int i = 1 + NST; i < ROWL::XP; ++i) row[ROWL::pT + i] = R(0);
+#pragma unroll
+      for (int i = HP; i < ROWL::HM; ++i) {
+        row[ROWL::pHP + i] = i == HP ? R(1) : R(0);
+        row[ROWL::pGPRE + i] = R(0);
       }
       gw.precisions(row);
     }

@@ -9,6 +9,8 @@
 // in registers for the whole kernel (37 accumulators) -- so the per-step cost is shared-memory reads + FMAs, no
 // atomics; one atomicAdd per matrix element per warp at the very end.
 #include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "vh_bb.cuh"
 #include "vh_launch.cuh"
@@ -138,6 +140,174 @@ struct BbWarpWgrad {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// fp32 path: the same outer-product sums on the tensor cores.  Per reverse evaluation a warp holds two 32 x K operand
+// panels in its scratch rows (K = 32 trajectories): the GEMMs  dW[m][n] += sum_t A[t][m] * B[t][n]  have m = hidden
+// unit (padded to 32, unit H = constant 1 -> bias gradients), n = state / output index (padded to 8 or 16).  They run
+// as warp-level mma.sync.m16n8k8 TF32 tiles with the 3xTF32 split (a = hi + lo; lo*hi + hi*lo + hi*hi, fp32
+// accumulate), which keeps the products at fp32 accuracy: the gradient parity bar is 3e-3, plain TF32 would eat most
+// of it.  Accumulators stay in the C fragments (40 registers) for the whole kernel.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tf32_split(float v, unsigned& hi, unsigned& lo) {
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+  const float r = v - __uint_as_float(hi);
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma_tf32(float* c, const unsigned* a, const unsigned* b) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// c += A * B with A, B given as fp32 fragments (3xTF32)
+__device__ __forceinline__ void mma_3xtf32(float* c, const unsigned* ahi, const unsigned* alo, const unsigned* bhi,
+                                           const unsigned* blo) {
+  mma_tf32(c, alo, bhi);
+  mma_tf32(c, ahi, blo);
+  mma_tf32(c, ahi, bhi);
+}
+
+template <class F>
+struct BbWarpWgradMma {
+  typedef typename F::L L;
+  typedef typename F::ROWL RW;
+  static constexpr int NST = F::NST, H = F::H, HP = F::HP, NC = F::NC, ROW = RW::ROW;
+
+  const float* rows;
+  int lane, g, tg;
+  float cW1[2][4];      // dW1  [m-tile][frag]      m = hidden unit, n = state
+  float cWpd[2][2][4];  // dWp | dWd  [m-tile][n-tile]   n = o (Wp) , NST + o (Wd)
+  float cQ1[2][4];      // dQ1   n = [t, x]
+  float cQpd[2][4];     // dQp | dQd   n = o (Qp), 4 + o (Qd)
+  float* d;
+
+  __device__ void init(const float* warp_rows, float* d_weights) {
+    rows = warp_rows;
+    d = d_weights;
+    lane = threadIdx.x & 31;
+    g = lane >> 2;
+    tg = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        cW1[i][k] = cQ1[i][k] = cQpd[i][k] = 0.f;
+        cWpd[i][0][k] = cWpd[i][1][k] = 0.f;
+      }
+  }
+  __device__ void begin() const { __syncwarp(); }
+
+  // A fragment of operand column block [off + mt*16, +16) at k-step ks (rows = trajectories ks*8 .. ks*8+7)
+  __device__ __forceinline__ void load_a(int ks, int off, unsigned* hi, unsigned* lo) const {
+    const float* r0 = rows + (ks * 8 + tg) * ROW + off + g;
+    const float* r1 = r0 + 4 * ROW;
+    tf32_split(r0[0], hi[0], lo[0]);
+    tf32_split(r0[8], hi[1], lo[1]);
+    tf32_split(r1[0], hi[2], lo[2]);
+    tf32_split(r1[8], hi[3], lo[3]);
+  }
+  __device__ __forceinline__ void load_b(int ks, int off, unsigned* hi, unsigned* lo) const {
+    const float* r0 = rows + (ks * 8 + tg) * ROW + off + g;
+    tf32_split(r0[0], hi[0], lo[0]);
+    tf32_split(r0[4 * ROW], hi[1], lo[1]);
+  }
+
+  __device__ void states(const float*) {
+    __syncwarp();
+#pragma unroll 1
+    for (int ks = 0; ks < 4; ++ks) {
+      unsigned bxh[2], bxl[2], bzh[2][2], bzl[2][2];
+      load_b(ks, RW::sX, bxh, bxl);
+      load_b(ks, RW::sGZP, bzh[0], bzl[0]);
+      load_b(ks, RW::sGZP + 8, bzh[1], bzl[1]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        unsigned ah[4], al[4];
+        load_a(ks, RW::sGPRE + mt * 16, ah, al);
+        mma_3xtf32(cW1[mt], ah, al, bxh, bxl);
+        load_a(ks, RW::sHID + mt * 16, ah, al);
+        mma_3xtf32(cWpd[mt][0], ah, al, bzh[0], bzl[0]);
+        mma_3xtf32(cWpd[mt][1], ah, al, bzh[1], bzl[1]);
+      }
+    }
+  }
+
+  __device__ void precisions(const float*) {
+    __syncwarp();
+#pragma unroll 1
+    for (int ks = 0; ks < 4; ++ks) {
+      unsigned bxh[2], bxl[2], bzh[2], bzl[2];
+      load_b(ks, RW::pT, bxh, bxl);
+      load_b(ks, RW::pGZP, bzh, bzl);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        unsigned ah[4], al[4];
+        load_a(ks, RW::pGPRE + mt * 16, ah, al);
+        mma_3xtf32(cQ1[mt], ah, al, bxh, bxl);
+        load_a(ks, RW::pHP + mt * 16, ah, al);
+        mma_3xtf32(cQpd[mt], ah, al, bzh, bzl);
+      }
+    }
+  }
+
+  // once per trajectory: columns of W1 / Q1 that multiply the constants, and the hidden biases (scalar; off the hot loop)
+  __device__ void consts(const float*) {
+    __syncwarp();
+    constexpr int total = (H + HP) * (NC + 1);
+    for (int e = lane; e < total; e += 32) {
+      const int h = e / (NC + 1), j = e % (NC + 1);
+      const int gofs = h < H ? RW::GHC + h : RW::GHPC + (h - H);
+      float acc = 0.f;
+      for (int t = 0; t < 32; ++t) {
+        const float* r = rows + t * ROW;
+        acc += r[gofs] * (j < NC ? r[j] : 1.f);
+      }
+      int idx;
+      if (h < H)
+        idx = j < NC ? L::W1 + h * L::nin + NST + j : L::b1 + h;
+      else
+        idx = j < NC ? L::Q1 + (h - H) * (L::nin + 1) + 1 + NST + j : L::qb1 + (h - H);
+      atomicAdd(d + idx, acc);
+    }
+    __syncwarp();
+  }
+
+  // C fragment element k of tile row-block mt: (m, n) = (mt*16 + g + 8*(k>>1), 2*tg + (k&1))
+  __device__ void flush() {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int m = mt * 16 + g + 8 * (k >> 1), n = 2 * tg + (k & 1);
+        if (m < H && n < NST) atomicAdd(d + L::W1 + m * L::nin + n, cW1[mt][k]);
+        if (m < HP && n < 1 + NST) atomicAdd(d + L::Q1 + m * (L::nin + 1) + n, cQ1[mt][k]);
+        // precision outputs: n < 4 -> Qp / qbp, else Qd / qbd; hidden row HP is the bias
+        if (m <= HP) {
+          const int o = n & 3;
+          float* base = n < 4 ? (m < HP ? d + L::Qp + o * HP + m : d + L::qbp + o) : (m < HP ? d + L::Qd + o * HP + m : d + L::qbd + o);
+          atomicAdd(base, cQpd[mt][k]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int col = nt * 8 + n;  // 0..NST-1: Wp, NST..2NST-1: Wd
+          if (m <= H && col < 2 * NST) {
+            const int o = col < NST ? col : col - NST;
+            float* base = col < NST ? (m < H ? d + L::Wp + o * H + m : d + L::bp + o) : (m < H ? d + L::Wd + o * H + m : d + L::bd + o);
+            atomicAdd(base, cWpd[mt][nt][k]);
+          }
+        }
+      }
+  }
+};
+
+template <class F, bool MMA, typename R = typename F::real>
+struct BbSinkSelect {
+  typedef BbWarpWgrad<F> type;  // scalar outer products (fp64 always)
+};
+template <class F>
+struct BbSinkSelect<F, true, float> {
+  typedef BbWarpWgradMma<F> type;
+};
+
 #ifndef VH_BB_DIR
 #define VH_BB_DIR 2  // 0: forward kernels only, 1: reverse kernels only, 2: both (single translation unit)
 #endif
@@ -154,7 +324,7 @@ __global__ void __launch_bounds__(64) bb_fwd_kernel(const Call<typename F::real>
   if (n < a.N) bb_traj_forward<F, TB>(a, n, w, rows + threadIdx.x * F::ROWL::ROW);
 }
 
-template <class F, class TB>
+template <class F, class TB, bool MMA>
 __global__ void __launch_bounds__(64) bb_bwd_kernel(const Call<typename F::real> a) {
   typedef typename F::real R;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -166,7 +336,7 @@ __global__ void __launch_bounds__(64) bb_bwd_kernel(const Call<typename F::real>
   const bool active = n < a.N;
   const int nn = active ? n : a.N - 1;
   WarpSegRed<R> red(a.d_q_mu, a.d_q_prec, a.P, nn / a.IW, active);
-  BbWarpWgrad<F> sink;
+  typename BbSinkSelect<F, MMA>::type sink;
   sink.init(rows + (threadIdx.x & ~31) * F::ROWL::ROW, a.d_weights);
   bb_traj_backward<F, TB>(a, nn, active, w, rows + threadIdx.x * F::ROWL::ROW, sink, red);
   sink.flush();
@@ -184,7 +354,17 @@ struct BbLauncher {
     cudaError_t e = cudaSuccess;
     if (BWD) {
 #if VH_BB_DIR != 0
-      if (smem > 48 * 1024) e = cudaFuncSetAttribute(bb_bwd_kernel<F, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      // weight-gradient GEMM: tensor cores (mma.sync 3xTF32) in the throughput regime, scalar FMAs when the launch is
+      // latency-bound (one warp per scheduler: the HMMA dependency chains cost more than they save; measured 1.85 ms vs
+      // 1.62 ms at N = 7,200 and 4.44 ms vs 4.56 ms at N = 65,536).  VIHDS_BB_WGRAD=mma|scalar overrides (tests).
+      static const int wgrad_mode = [] {
+        const char* m = getenv("VIHDS_BB_WGRAD");
+        return !m ? 0 : (!strcmp(m, "mma") ? 1 : (!strcmp(m, "scalar") ? 2 : 0));
+      }();
+      const bool mma = sizeof(R) == 4 && (wgrad_mode == 1 || (wgrad_mode == 0 && a.N >= 32768));
+      if (smem > 48 * 1024)
+        e = mma ? cudaFuncSetAttribute(bb_bwd_kernel<F, TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                : cudaFuncSetAttribute(bb_bwd_kernel<F, TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
         return VH_ERR_CUDA;
@@ -194,7 +374,10 @@ struct BbLauncher {
         cudaMemsetAsync(a.d_q_prec, 0, sizeof(R) * (size_t)a.B * a.P, stream);
       }
       cudaMemsetAsync(a.d_weights, 0, sizeof(R) * F::L::total, stream);
-      bb_bwd_kernel<F, TB><<<grid, block, smem, stream>>>(a);
+      if (mma)
+        bb_bwd_kernel<F, TB, true><<<grid, block, smem, stream>>>(a);
+      else
+        bb_bwd_kernel<F, TB, false><<<grid, block, smem, stream>>>(a);
 #endif
     } else {
 #if VH_BB_DIR != 1
