@@ -48,6 +48,40 @@ VH_HD float vdiv(float a, float b) {
 }
 VH_HD double vdiv(double a, double b) { return a / b; }
 
+// Software prefetch of one cache line into L1 (no destination register: the compiler cannot sink it towards the use
+// the way it sinks an early register load under register pressure -- measured: 41 % of the reverse loop's stall samples
+// sat on the first use of the "prefetched" checkpoint).
+VH_HD void prefetch_l1(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+
+// A global load the compiler must issue where it is written.  Used for the one-step-ahead fetch of the small shared
+// inputs (observations, grid time): as plain loads ptxas sank them below the ~400-instruction adjoint body, right in
+// front of their first use, which exposed a full memory latency per time step (41 % of the reverse loop's stall
+// samples at the icml size sat on that one move).
+VH_HD float ld_early(const float* p) {
+#if defined(__CUDA_ARCH__)
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+#else
+  return *p;
+#endif
+}
+VH_HD double ld_early(const double* p) {
+#if defined(__CUDA_ARCH__)
+  double v;
+  asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#else
+  return *p;
+#endif
+}
+
 template <typename R>
 VH_HD R sigmoid(R z) {
   return vdiv(R(1), R(1) + vexp(-z));

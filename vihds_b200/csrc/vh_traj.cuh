@@ -352,9 +352,9 @@ VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M
     const int kn = k + 1 < T ? k + 1 : k;
     if (obs) {
 #pragma unroll
-      for (int o = 0; o < 4; ++o) obn[o] = obs[o * T + kn];
+      for (int o = 0; o < 4; ++o) obn[o] = ld_early(obs + o * T + kn);
     }
-    const R t2 = a.times[k + 2 < T ? k + 2 : T - 1];
+    const R t2 = ld_early(a.times + (k + 2 < T ? k + 2 : T - 1));
     if (xs) {
 #pragma unroll
       for (int q = 0; q < S; ++q) xs[(size_t)q * N] = x[q];
@@ -465,9 +465,9 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
       }
       if (obs) {
 #pragma unroll
-        for (int o = 0; o < 4; ++o) obp[o] = obs[o * T + kp];
+        for (int o = 0; o < 4; ++o) obp[o] = ld_early(obs + o * T + kp);
       }
-      const R tp = a.times[kp];
+      const R tp = ld_early(a.times + kp);
       if (k + 1 < T) rk_step_vjp<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, lam, gc, gw);
       // emission at time k
       R xp[4], gxp[4];
