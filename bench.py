@@ -431,10 +431,12 @@ def main():
                    "trajectories_per_step": N * world, "T": T, "state_width": S, "n_theta": P, "solver": settings.params.solver,
                    "parallelism": "dp%d (individuals sharded, one gradient all-reduce)" % world,
                    "cuda_graphs": not a.no_graphs, "l2": "flushed between timed steps (256 MiB memset)"},
-        "roofline": {"kernel": "elbo_bwd_kernel (discrete-adjoint reverse sweep)", "bound": "hbm", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes": bytes_bwd, "launch_us": bwd_s * 1e6,
-                     "note": "latency/issue-bound at this size: 7,200 trajectories = 225 warps on 148 SMs (see DESIGN.md)"},
+        "roofline": {"kernel": "%s (discrete-adjoint reverse sweep, the dominant launch)" % (
+                         "bb_bwd_kernel" if a.workload == "dr_blackbox_icml" else "elbo_bwd_kernel"),
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": bytes_bwd, "launch_us": bwd_s * 1e6,
+                     "note": ("latency-bound at this size: %d trajectories = %d warps on 148 SMs x 4 schedulers" % (N, (N + 31) // 32)
+                              if N < 148 * 4 * 32 * 4 else "FP32-issue-bound: ~440 instructions per 32 B of trace") + " (DESIGN.md section 5)"},
         "kernels": kern,
         "e2e": {"value": N * world / e2e_step, "unit": "traj/s", "ms_per_step": e2e_step * 1e3, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(cost_host.numel() * cost_host.element_size())},
