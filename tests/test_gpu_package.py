@@ -290,3 +290,25 @@ def test_training_run_prints_finite_elbo(spec, capsys):
     lines = [l for l in capsys.readouterr().out.splitlines() if "iwae-elbo" in l]
     assert len(lines) == 2
     assert all(np.isfinite(float(l.split("=")[-1])) for l in lines)
+
+
+def test_fused_encoder_large_batch_grouped_path():
+    """B = 601 (>= 4 x 148: four individuals per CTA, ragged last group) against the stock-PyTorch encoder."""
+    case = load_case("dr_constant_icml_midpoint_f32_iw8")
+    settings, par, model, training = build("dr_constant_icml")
+    enc = model.encoder
+    small = batch_from_case(case)
+    B = 601
+    idx = torch.arange(B, device="cuda") % small.inputs.shape[0]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    batch = Settings(times=small.times, inputs=small.inputs[idx].contiguous(), dev_1hot=small.dev_1hot[idx].contiguous(),
+                     observations=(small.observations[idx] + 0.01 * torch.randn(B, 4, small.times.numel(), device="cuda", generator=g)).contiguous())
+    mu1, pr1 = enc.q_table(batch)
+    mu0, pr0 = enc.q_table_reference(batch)
+    assert torch.allclose(mu1, mu0, rtol=2e-5, atol=1e-6) and torch.allclose(pr1, pr0, rtol=2e-5, atol=1e-6)
+    g_mu, g_pr = torch.randn(mu0.shape, device="cuda", generator=g), torch.randn(mu0.shape, device="cuda", generator=g)
+    params = [p for p in enc.fused_parameters() if p.numel()]
+    got = torch.autograd.grad([mu1, pr1], params, [g_mu, g_pr], allow_unused=True)
+    ref = torch.autograd.grad([mu0, pr0], params, [g_mu, g_pr], allow_unused=True)
+    for a, b, p in zip(got, ref, params):
+        assert _rel(a.cpu().numpy(), b.cpu().numpy()) < 5e-5, tuple(p.shape)

@@ -48,80 +48,103 @@ __device__ R warp_sum(R v) {
 // heads use one warp per row.
 #define ENC_THREADS 512
 #define ENC_OPW 4
-template <typename R>
+// G individuals per CTA: the hidden-layer weight matrix (H x NLIN, 1 MB at T = 500) is the only large operand and
+// every CTA streams all of it from L2; with G > 1 each weight is loaded once and used G times (large batches).
+template <typename R, int G>
 __global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, const EncPtrs<R> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* delta = reinterpret_cast<R*>(smem_raw);
   R* conv = delta + d.NS * d.L1;
-  R* pooled = conv + d.F * d.NCV;
-  R* xloc = pooled + d.NLIN;
-  R* freev = xloc + d.nin_l;  // 2*(nl+ng)
-  R* cw = freev + 2 * (d.nl + d.ng);  // conv weights [F][NS][K] + bias [F]
-  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  R* pooled = conv + d.F * d.NCV;                 // [G][NLIN]
+  R* xloc = pooled + (size_t)G * d.NLIN;          // [G][nin_l]
+  R* freev = xloc + G * d.nin_l;                  // [G][2*(nl+ng)]
+  R* cw = freev + G * 2 * (d.nl + d.ng);          // conv weights [F][NS][K] + bias [F]
+  const int tid = threadIdx.x, nt = blockDim.x;
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-  const R* obs = p.obs + (size_t)b * d.NS * d.T;
+  const int b0 = blockIdx.x * G;
+  const int ngr = min(G, d.B - b0);
   const int ncw = d.F * d.NS * d.K;
+  const int nfree = 2 * (d.nl + d.ng);
   for (int i = tid; i < ncw + d.F; i += nt) cw[i] = i < ncw ? p.conv_w[i] : p.conv_b[i - ncw];
-  for (int i = tid; i < d.NS * d.L1; i += nt) {
-    const int c = i / d.L1, j = i % d.L1;
-    delta[i] = obs[c * d.T + j + 1] - obs[c * d.T + j];
-  }
-  for (int i = tid; i < d.nin_l - d.H; i += nt)  // conditioning inputs of the local heads
-    xloc[d.H + i] = (d.lt && i < d.C) ? p.inputs[(size_t)b * d.C + i] : p.dev[(size_t)b * d.D + (i - (d.lt ? d.C : 0))];
-  __syncthreads();
-  for (int i = tid; i < d.F * d.NCV; i += nt) {
-    const int f = i / d.NCV, j = i % d.NCV;
-    R a = cw[ncw + f];
-    for (int c = 0; c < d.NS; ++c) {
-      const R* w = cw + (f * d.NS + c) * d.K;
-      const R* x = delta + c * d.L1 + j;
-      for (int k = 0; k < d.K; ++k) a += w[k] * x[k];
-    }
-    conv[i] = a;
-  }
-  __syncthreads();
   const R inv_pool = R(1) / R(d.PL);
-  for (int i = tid; i < d.NLIN; i += nt) {
-    const int f = i / d.NP, j = i % d.NP;
-    R a = R(0);
-    for (int k = 0; k < d.PL; ++k) a += conv[f * d.NCV + j + k];
-    a *= inv_pool;
-    pooled[i] = a;
-    p.pooled[(size_t)b * d.NLIN + i] = a;
+  for (int g = 0; g < ngr; ++g) {
+    const int b = b0 + g;
+    const R* obs = p.obs + (size_t)b * d.NS * d.T;
+    __syncthreads();  // delta / conv scratch of the previous individual fully consumed
+    for (int i = tid; i < d.NS * d.L1; i += nt) {
+      const int c = i / d.L1, j = i % d.L1;
+      delta[i] = obs[c * d.T + j + 1] - obs[c * d.T + j];
+    }
+    for (int i = tid; i < d.nin_l - d.H; i += nt)  // conditioning inputs of the local heads
+      xloc[g * d.nin_l + d.H + i] =
+          (d.lt && i < d.C) ? p.inputs[(size_t)b * d.C + i] : p.dev[(size_t)b * d.D + (i - (d.lt ? d.C : 0))];
+    __syncthreads();
+    for (int i = tid; i < d.F * d.NCV; i += nt) {
+      const int f = i / d.NCV, j = i % d.NCV;
+      R a = cw[ncw + f];
+      for (int c = 0; c < d.NS; ++c) {
+        const R* w = cw + (f * d.NS + c) * d.K;
+        const R* x = delta + c * d.L1 + j;
+        for (int k = 0; k < d.K; ++k) a += w[k] * x[k];
+      }
+      conv[i] = a;
+    }
+    __syncthreads();
+    for (int i = tid; i < d.NLIN; i += nt) {
+      const int f = i / d.NP, j = i % d.NP;
+      R a = R(0);
+      for (int k = 0; k < d.PL; ++k) a += conv[f * d.NCV + j + k];
+      a *= inv_pool;
+      pooled[(size_t)g * d.NLIN + i] = a;
+      p.pooled[(size_t)b * d.NLIN + i] = a;
+    }
   }
   __syncthreads();
-  // hidden layer: each warp owns outputs o0, o0 + nw, ... and accumulates ENC_OPW of them per pass over the inputs
+  // hidden layer: each warp owns outputs o0, o0 + nw, ... and accumulates ENC_OPW of them for all G individuals per
+  // pass over the inputs
   for (int o0 = warp; o0 < d.H; o0 += nw * ENC_OPW) {
-    R acc[ENC_OPW];
+    R acc[ENC_OPW][G];
 #pragma unroll
-    for (int q = 0; q < ENC_OPW; ++q) acc[q] = R(0);
+    for (int q = 0; q < ENC_OPW; ++q)
+#pragma unroll
+      for (int g = 0; g < G; ++g) acc[q][g] = R(0);
 #pragma unroll 2
     for (int i = lane; i < d.NLIN; i += 32) {
-      const R x = pooled[i];
+      R x[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) x[g] = pooled[(size_t)g * d.NLIN + i];
 #pragma unroll
       for (int q = 0; q < ENC_OPW; ++q) {
         const int o = o0 + q * nw;
-        if (o < d.H) acc[q] += p.lin_w[(size_t)o * d.NLIN + i] * x;
+        if (o < d.H) {
+          const R w = p.lin_w[(size_t)o * d.NLIN + i];
+#pragma unroll
+          for (int g = 0; g < G; ++g) acc[q][g] += w * x[g];
+        }
       }
     }
 #pragma unroll
     for (int q = 0; q < ENC_OPW; ++q) {
       const int o = o0 + q * nw;
-      const R a = warp_sum(acc[q]);
-      if (lane == 0 && o < d.H) {
-        const R e = vtanh(a + p.lin_b[o]);
-        xloc[o] = e;
-        p.enc[(size_t)b * d.H + o] = e;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const R a = warp_sum(acc[q][g]);
+        if (lane == 0 && o < d.H && g < ngr) {
+          const R e = vtanh(a + p.lin_b[o]);
+          xloc[g * d.nin_l + o] = e;
+          p.enc[(size_t)(b0 + g) * d.H + o] = e;
+        }
       }
     }
   }
   __syncthreads();
-  // packed heads: one warp per row, lanes over the inputs
-  for (int r = warp; r < 2 * (d.nl + d.ng); r += nw) {
+  // packed heads: one warp per (individual, row), lanes over the inputs
+  for (int e = warp; e < ngr * nfree; e += nw) {
+    const int g = e / nfree, r = e % nfree, b = b0 + g;
     R a = R(0);
     if (r < 2 * d.nl) {
       const R* w = p.local_w + (size_t)r * d.nin_l;
-      for (int i = lane; i < d.nin_l; i += 32) a += w[i] * xloc[i];
+      for (int i = lane; i < d.nin_l; i += 32) a += w[i] * xloc[g * d.nin_l + i];
     } else {
       const R* w = p.gcond_w + (size_t)(r - 2 * d.nl) * d.nin_g;
       for (int i = lane; i < d.nin_g; i += 32) {
@@ -130,16 +153,17 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, c
       }
     }
     a = warp_sum(a);
-    if (lane == 0) freev[r] = a + (r < 2 * d.nl ? p.local_b[r] : R(0));
+    if (lane == 0) freev[g * nfree + r] = a + (r < 2 * d.nl ? p.local_b[r] : R(0));
   }
   __syncthreads();
-  R* qm = p.q_mu + (size_t)b * d.P;
-  R* qp = p.q_prec + (size_t)b * d.P;
-  for (int k = tid; k < d.P; k += nt) {
+  for (int e = tid; e < ngr * d.P; e += nt) {
+    const int g = e / d.P, k = e % d.P;
+    R* qm = p.q_mu + (size_t)(b0 + g) * d.P;
+    R* qp = p.q_prec + (size_t)(b0 + g) * d.P;
     const int ncond = d.nl + d.ng;
     if (k < ncond) {
-      qm[k] = freev[2 * k];
-      qp[k] = vexp(freev[2 * k + 1]);
+      qm[k] = freev[g * nfree + 2 * k];
+      qp[k] = vexp(freev[g * nfree + 2 * k + 1]);
     } else if (k < ncond + d.nglob) {
       qm[k] = p.global_free[2 * (k - ncond)];
       qp[k] = vexp(p.global_free[2 * (k - ncond) + 1]);
@@ -150,23 +174,24 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, c
   }
 }
 
-// backward, one CTA per individual.  shared: delta | dconv [F][NCV] | dpool [NLIN] | xloc | dfree | dxloc | dpre
-template <typename R>
+// backward, G individuals per CTA.  shared: delta | dconv [F][NCV] | dpool [G][NLIN] | xloc [G][nin_l] | dfree [G][..] | dpre [G][H]
+template <typename R, int G>
 __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, const EncPtrs<R> p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* delta = reinterpret_cast<R*>(smem_raw);
   R* dconv = delta + d.NS * d.L1;
   R* dpool = dconv + d.F * d.NCV;
-  R* xloc = dpool + d.NLIN;
-  R* dfree = xloc + d.nin_l;
-  R* dpre = dfree + 2 * (d.nl + d.ng + d.nglob);
-  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-  const R* obs = p.obs + (size_t)b * d.NS * d.T;
-  for (int i = tid; i < d.NS * d.L1; i += nt) {
-    const int c = i / d.L1, j = i % d.L1;
-    delta[i] = obs[c * d.T + j + 1] - obs[c * d.T + j];
-  }
-  for (int i = tid; i < d.nin_l; i += nt) {
+  R* xloc = dpool + (size_t)G * d.NLIN;
+  const int ncond = d.nl + d.ng;
+  const int nfr = 2 * (ncond + d.nglob);
+  R* dfree = xloc + G * d.nin_l;
+  R* dpre = dfree + G * nfr;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+  const int b0 = blockIdx.x * G;
+  const int ngr = min(G, d.B - b0);
+  for (int e = tid; e < ngr * d.nin_l; e += nt) {
+    const int g = e / d.nin_l, i = e % d.nin_l, b = b0 + g;
     R v;
     if (i < d.H)
       v = p.enc[(size_t)b * d.H + i];
@@ -174,83 +199,145 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
       const int j = i - d.H;
       v = (d.lt && j < d.C) ? p.inputs[(size_t)b * d.C + j] : p.dev[(size_t)b * d.D + (j - (d.lt ? d.C : 0))];
     }
-    xloc[i] = v;
+    xloc[e] = v;
   }
-  const int ncond = d.nl + d.ng;
-  for (int k = tid; k < ncond + d.nglob; k += nt) {
-    dfree[2 * k] = p.d_q_mu[(size_t)b * d.P + k];
-    dfree[2 * k + 1] = p.d_q_prec[(size_t)b * d.P + k] * p.q_prec[(size_t)b * d.P + k];  // d exp(log_prec)
+  for (int e = tid; e < ngr * (ncond + d.nglob); e += nt) {
+    const int g = e / (ncond + d.nglob), k = e % (ncond + d.nglob), b = b0 + g;
+    dfree[g * nfr + 2 * k] = p.d_q_mu[(size_t)b * d.P + k];
+    dfree[g * nfr + 2 * k + 1] = p.d_q_prec[(size_t)b * d.P + k] * p.q_prec[(size_t)b * d.P + k];  // d exp(log_prec)
   }
   __syncthreads();
-  // global free parameters
-  for (int j = tid; j < 2 * d.nglob; j += nt) atomicAdd(p.g_global_free + j, dfree[2 * ncond + j]);
-  // packed heads: weight / bias gradients and the cotangent of the hidden features
-  for (int e = tid; e < 2 * d.nl * d.nin_l; e += nt) atomicAdd(p.g_local_w + e, dfree[e / d.nin_l] * xloc[e % d.nin_l]);
-  for (int r = tid; r < 2 * d.nl; r += nt) atomicAdd(p.g_local_b + r, dfree[r]);
+  // parameter gradients of the heads and the global free parameters: summed over the CTA's individuals, then one atomic
+  for (int j = tid; j < 2 * d.nglob; j += nt) {
+    R a = R(0);
+    for (int g = 0; g < ngr; ++g) a += dfree[g * nfr + 2 * ncond + j];
+    atomicAdd(p.g_global_free + j, a);
+  }
+  for (int e = tid; e < 2 * d.nl * d.nin_l; e += nt) {
+    R a = R(0);
+    for (int g = 0; g < ngr; ++g) a += dfree[g * nfr + e / d.nin_l] * xloc[g * d.nin_l + e % d.nin_l];
+    atomicAdd(p.g_local_w + e, a);
+  }
+  for (int r = tid; r < 2 * d.nl; r += nt) {
+    R a = R(0);
+    for (int g = 0; g < ngr; ++g) a += dfree[g * nfr + r];
+    atomicAdd(p.g_local_b + r, a);
+  }
   for (int e = tid; e < 2 * d.ng * d.nin_g; e += nt) {
     const int r = e / d.nin_g, i = e % d.nin_g;
-    const R x = (d.gt && i < d.C) ? p.inputs[(size_t)b * d.C + i] : p.dev[(size_t)b * d.D + (i - (d.gt ? d.C : 0))];
-    atomicAdd(p.g_gcond_w + e, dfree[2 * d.nl + r] * x);
-  }
-  for (int o = tid; o < d.H; o += nt) {
-    R g = R(0);
-    for (int r = 0; r < 2 * d.nl; ++r) g += p.local_w[(size_t)r * d.nin_l + o] * dfree[r];
-    const R e = xloc[o];
-    const R gp = g * (R(1) - e * e);  // tanh'
-    dpre[o] = gp;
-    p.d_pre[(size_t)b * d.H + o] = gp;
-    atomicAdd(p.g_lin_b + o, gp);
-  }
-  __syncthreads();
-  // cotangent of the pooled features: dpool[i] = sum_o W[o][i] dpre[o]   (coalesced over i)
-  for (int i = tid; i < d.NLIN; i += nt) {
-    R g0 = R(0), g1 = R(0);
-    int o = 0;
-#pragma unroll 5
-    for (; o + 1 < d.H; o += 2) {  // two accumulators, ten weight loads in flight
-      g0 += p.lin_w[(size_t)o * d.NLIN + i] * dpre[o];
-      g1 += p.lin_w[(size_t)(o + 1) * d.NLIN + i] * dpre[o + 1];
-    }
-    if (o < d.H) g0 += p.lin_w[(size_t)o * d.NLIN + i] * dpre[o];
-    dpool[i] = g0 + g1;
-  }
-  __syncthreads();
-  const R inv_pool = R(1) / R(d.PL);
-  for (int i = tid; i < d.F * d.NCV; i += nt) {
-    const int f = i / d.NCV, j = i % d.NCV;
-    R g = R(0);
-    for (int k = 0; k < d.PL; ++k) {
-      const int jp = j - k;
-      if (jp >= 0 && jp < d.NP) g += dpool[f * d.NP + jp];
-    }
-    dconv[i] = g * inv_pool;
-  }
-  __syncthreads();
-  // conv weight / bias gradients: one warp per weight, lanes over the NCV positions
-  const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
-  const int nwc = d.F * d.NS * d.K;
-  for (int e = warp; e < nwc + d.F; e += nw) {
     R a = R(0);
-    if (e < nwc) {
-      const int f = e / (d.NS * d.K), c = (e / d.K) % d.NS, k = e % d.K;
-      for (int j = lane; j < d.NCV; j += 32) a += dconv[f * d.NCV + j] * delta[c * d.L1 + j + k];
-    } else {
-      const int f = e - nwc;
-      for (int j = lane; j < d.NCV; j += 32) a += dconv[f * d.NCV + j];
+    for (int g = 0; g < ngr; ++g) {
+      const int b = b0 + g;
+      const R x = (d.gt && i < d.C) ? p.inputs[(size_t)b * d.C + i] : p.dev[(size_t)b * d.D + (i - (d.gt ? d.C : 0))];
+      a += dfree[g * nfr + 2 * d.nl + r] * x;
     }
-    a = warp_sum(a);
-    if (lane == 0) atomicAdd(e < nwc ? p.g_conv_w + e : p.g_conv_b + (e - nwc), a);
+    atomicAdd(p.g_gcond_w + e, a);
+  }
+  for (int e = tid; e < G * d.H; e += nt) {
+    const int g = e / d.H, o = e % d.H;
+    R gp = R(0);
+    if (g < ngr) {
+      R gg = R(0);
+      for (int r = 0; r < 2 * d.nl; ++r) gg += p.local_w[(size_t)r * d.nin_l + o] * dfree[g * nfr + r];
+      const R en = xloc[g * d.nin_l + o];
+      gp = gg * (R(1) - en * en);  // tanh'
+      p.d_pre[(size_t)(b0 + g) * d.H + o] = gp;
+    }
+    dpre[e] = gp;
+  }
+  __syncthreads();
+  for (int o = tid; o < d.H; o += nt) {
+    R a = R(0);
+    for (int g = 0; g < ngr; ++g) a += dpre[g * d.H + o];
+    atomicAdd(p.g_lin_b + o, a);
+  }
+  // cotangent of the pooled features: dpool[g][i] = sum_o W[o][i] dpre[g][o]   (each weight loaded once for G individuals)
+  for (int i = tid; i < d.NLIN; i += nt) {
+    R acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = R(0);
+#pragma unroll 8
+    for (int o = 0; o < d.H; ++o) {
+      const R w = p.lin_w[(size_t)o * d.NLIN + i];
+#pragma unroll
+      for (int g = 0; g < G; ++g) acc[g] += w * dpre[g * d.H + o];
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) dpool[(size_t)g * d.NLIN + i] = acc[g];
+  }
+  const R inv_pool = R(1) / R(d.PL);
+  const int nwc = d.F * d.NS * d.K;
+  for (int g = 0; g < ngr; ++g) {
+    const R* obs = p.obs + (size_t)(b0 + g) * d.NS * d.T;
+    __syncthreads();  // dpool complete / previous individual's delta + dconv consumed
+    for (int i = tid; i < d.NS * d.L1; i += nt) {
+      const int c = i / d.L1, j = i % d.L1;
+      delta[i] = obs[c * d.T + j + 1] - obs[c * d.T + j];
+    }
+    for (int i = tid; i < d.F * d.NCV; i += nt) {
+      const int f = i / d.NCV, j = i % d.NCV;
+      R a = R(0);
+      for (int k = 0; k < d.PL; ++k) {
+        const int jp = j - k;
+        if (jp >= 0 && jp < d.NP) a += dpool[(size_t)g * d.NLIN + f * d.NP + jp];
+      }
+      dconv[i] = a * inv_pool;
+    }
+    __syncthreads();
+    // conv weight / bias gradients: one warp per weight, lanes over the NCV positions
+    for (int e = warp; e < nwc + d.F; e += nw) {
+      R a = R(0);
+      if (e < nwc) {
+        const int f = e / (d.NS * d.K), c = (e / d.K) % d.NS, k = e % d.K;
+        for (int j = lane; j < d.NCV; j += 32) a += dconv[f * d.NCV + j] * delta[c * d.L1 + j + k];
+      } else {
+        const int f = e - nwc;
+        for (int j = lane; j < d.NCV; j += 32) a += dconv[f * d.NCV + j];
+      }
+      a = warp_sum(a);
+      if (lane == 0) atomicAdd(e < nwc ? p.g_conv_w + e : p.g_conv_b + (e - nwc), a);
+    }
   }
 }
 
+// dW_lin[o][i] += sum_b d_pre[b][o] * pooled[b][i].  One thread per input column i (coalesced reads of pooled), all H
+// outputs accumulated in registers, d_pre rows broadcast from shared memory; the individuals are split over
+// blockIdx.y so that large batches fill the machine (partial sums meet in the atomics).  HMAX bounds the register
+// tile; wider hidden layers take several passes.
+#define ENC_WG_HMAX 64
+#define ENC_WG_BCHUNK 32
 template <typename R>
-__global__ void __launch_bounds__(256) enc_lin_wgrad_kernel(const EncDims d, const EncPtrs<R> p) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= d.H * d.NLIN) return;
-  const int o = e / d.NLIN, i = e % d.NLIN;
-  R a = R(0);
-  for (int b = 0; b < d.B; ++b) a += p.d_pre[(size_t)b * d.H + o] * p.pooled[(size_t)b * d.NLIN + i];
-  p.g_lin_w[e] += a;
+__global__ void __launch_bounds__(128) enc_lin_wgrad_kernel(const EncDims d, const EncPtrs<R> p, int b_per_block) {
+  __shared__ R sh[ENC_WG_BCHUNK * ENC_WG_HMAX];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b0 = blockIdx.y * b_per_block, b1 = min(d.B, b0 + b_per_block);
+  for (int o0 = 0; o0 < d.H; o0 += ENC_WG_HMAX) {
+    const int nh = min(ENC_WG_HMAX, d.H - o0);
+    R acc[ENC_WG_HMAX];
+#pragma unroll
+    for (int o = 0; o < ENC_WG_HMAX; ++o) acc[o] = R(0);
+    for (int bb = b0; bb < b1; bb += ENC_WG_BCHUNK) {
+      const int nb = min(ENC_WG_BCHUNK, b1 - bb);
+      __syncthreads();
+      for (int e = threadIdx.x; e < nb * ENC_WG_HMAX; e += blockDim.x) {
+        const int r = e / ENC_WG_HMAX, o = e % ENC_WG_HMAX;
+        sh[e] = o < nh ? p.d_pre[(size_t)(bb + r) * d.H + o0 + o] : R(0);
+      }
+      __syncthreads();
+      if (i < d.NLIN) {
+        for (int r = 0; r < nb; ++r) {
+          const R x = p.pooled[(size_t)(bb + r) * d.NLIN + i];
+#pragma unroll
+          for (int o = 0; o < ENC_WG_HMAX; ++o) acc[o] += sh[r * ENC_WG_HMAX + o] * x;
+        }
+      }
+    }
+    if (i < d.NLIN) {
+#pragma unroll
+      for (int o = 0; o < ENC_WG_HMAX; ++o)
+        if (o < nh) atomicAdd(p.g_lin_w + (size_t)(o0 + o) * d.NLIN + i, acc[o]);
+    }
+  }
 }
 
 // device conditioner (vihds/ode.py:43-58, :99-116) including the reference's repeat/reshape quirk: sample n = b*IW + i
@@ -301,14 +388,35 @@ static void fill_ptrs(const vh_encoder_io* io, const vh_encoder_grads* g, EncPtr
   }
 }
 
+template <typename R, int G>
+static void enc_fwd_g(const EncDims& d, const EncPtrs<R>& p, cudaStream_t s) {
+  const size_t smem = sizeof(R) * ((size_t)d.NS * d.L1 + (size_t)d.F * d.NCV + (size_t)G * d.NLIN + G * d.nin_l +
+                                   G * 2 * (d.nl + d.ng) + (size_t)d.F * d.NS * d.K + d.F + 8);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(enc_fwd_kernel<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  enc_fwd_kernel<R, G><<<(d.B + G - 1) / G, ENC_THREADS, smem, s>>>(d, p);
+}
+template <typename R, int G>
+static void enc_bwd_g(const EncDims& d, const EncPtrs<R>& p, cudaStream_t s) {
+  const size_t smem = sizeof(R) * ((size_t)d.NS * d.L1 + (size_t)d.F * d.NCV + (size_t)G * d.NLIN + G * d.nin_l +
+                                   G * 2 * (d.nl + d.ng + d.nglob) + G * d.H + 8);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(enc_bwd_kernel<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  enc_bwd_kernel<R, G><<<(d.B + G - 1) / G, ENC_THREADS, smem, s>>>(d, p);
+}
+// individuals per CTA: 1 while the batch does not fill the machine anyway, 4 for large batches (if it fits shared memory)
+template <typename R>
+static int enc_group(const EncDims& d) {
+  const size_t smem4 = sizeof(R) * ((size_t)d.NS * d.L1 + (size_t)d.F * d.NCV + (size_t)4 * d.NLIN + 4 * (d.nin_l + 2 * d.P + d.H) + 1024);
+  return (d.B >= 4 * 148 && smem4 <= 200 * 1024) ? 4 : 1;
+}
+
 template <typename R>
 static int enc_fwd_t(const EncDims& d, const vh_encoder_io* io, cudaStream_t s) {
   EncPtrs<R> p = {};
   fill_ptrs<R>(io, nullptr, p);
-  const size_t smem = sizeof(R) * ((size_t)d.NS * d.L1 + (size_t)d.F * d.NCV + d.NLIN + d.nin_l + 2 * (d.nl + d.ng) +
-                                   (size_t)d.F * d.NS * d.K + d.F + 8);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(enc_fwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  enc_fwd_kernel<R><<<d.B, ENC_THREADS, smem, s>>>(d, p);
+  if (enc_group<R>(d) == 4)
+    enc_fwd_g<R, 4>(d, p, s);
+  else
+    enc_fwd_g<R, 1>(d, p, s);
   return 0;
 }
 
@@ -316,11 +424,19 @@ template <typename R>
 static int enc_bwd_t(const EncDims& d, const vh_encoder_io* io, const vh_encoder_grads* g, cudaStream_t s) {
   EncPtrs<R> p = {};
   fill_ptrs<R>(io, g, p);
-  const size_t smem = sizeof(R) * ((size_t)d.NS * d.L1 + (size_t)d.F * d.NCV + d.NLIN + d.nin_l + 2 * (d.nl + d.ng + d.nglob) + d.H + 8);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(enc_bwd_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  enc_bwd_kernel<R><<<d.B, ENC_THREADS, smem, s>>>(d, p);
-  const int n = d.H * d.NLIN;
-  enc_lin_wgrad_kernel<R><<<(n + 255) / 256, 256, 0, s>>>(d, p);
+  if (enc_group<R>(d) == 4)
+    enc_bwd_g<R, 4>(d, p, s);
+  else
+    enc_bwd_g<R, 1>(d, p, s);
+  // enough CTAs for ~2 per SM: columns x splits of the individuals
+  const int col_blocks = (d.NLIN + 127) / 128;
+  int splits = (2 * 148 + col_blocks - 1) / col_blocks;
+  const int max_splits = (d.B + ENC_WG_BCHUNK - 1) / ENC_WG_BCHUNK;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const int b_per_block = (((d.B + splits - 1) / splits) + ENC_WG_BCHUNK - 1) / ENC_WG_BCHUNK * ENC_WG_BCHUNK;
+  dim3 grid(col_blocks, (d.B + b_per_block - 1) / b_per_block);
+  enc_lin_wgrad_kernel<R><<<grid, 128, 0, s>>>(d, p, b_per_block);
   return 0;
 }
 
