@@ -440,7 +440,9 @@ def main():
         "kernels": kern,
         "e2e": {"value": N * world / e2e_step, "unit": "traj/s", "ms_per_step": e2e_step * 1e3, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(cost_host.numel() * cost_host.element_size())},
-        "gpu_launches": int(6 * a.steps),
+        # launches of libvihds_b200.so per step: enc_fwd, [conditioner,] elbo_fwd, iwae_fwd, iwae_bwd, elbo_bwd, enc_bwd,
+        # enc_lin_wgrad, adam, step_inc (the only other launch in the step is torch's memset of the flat gradient)
+        "gpu_launches": int((9 + (1 if gs.rel else 0)) * a.steps),
         "clocks": clocks, "cost_after_last_step": final_cost, "wall_s_timed_region": wall,
     }
     if not a.no_cpu_baseline and world == 1:

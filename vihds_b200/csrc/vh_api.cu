@@ -296,11 +296,11 @@ static int run_fwd(const vh_problem* p, const vh_fwd_io* io, void* stream) {
     return VH_ERR_UNSUPPORTED;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (p->model == VH_MODEL_DR_BLACKBOX) return launch_bb_fwd(p, io, s);
   if (p->dtype != VH_F32 && p->dtype != VH_F64) {
     set_error("unknown dtype %d", p->dtype);
     return VH_ERR_INVALID;
   }
+  if (p->model == VH_MODEL_DR_BLACKBOX) return launch_bb_fwd(p, io, s);
   if (!model_is_dr_family(p->model)) {
     set_error("model %d has no kernel", p->model);
     return VH_ERR_UNSUPPORTED;
@@ -318,11 +318,11 @@ static int run_bwd(const vh_problem* p, const vh_bwd_io* io, void* stream) {
     return VH_ERR_UNSUPPORTED;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (p->model == VH_MODEL_DR_BLACKBOX) return launch_bb_bwd(p, io, s);
   if (p->dtype != VH_F32 && p->dtype != VH_F64) {
     set_error("unknown dtype %d", p->dtype);
     return VH_ERR_INVALID;
   }
+  if (p->model == VH_MODEL_DR_BLACKBOX) return launch_bb_bwd(p, io, s);
   if (!model_is_dr_family(p->model)) {
     set_error("model %d has no kernel", p->model);
     return VH_ERR_UNSUPPORTED;

@@ -207,23 +207,27 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
     dfree[g * nfr + 2 * k + 1] = p.d_q_prec[(size_t)b * d.P + k] * p.q_prec[(size_t)b * d.P + k];  // d exp(log_prec)
   }
   __syncthreads();
+  // Small batches: gridDim.y CTAs share one individual, each taking the conv filters f = blockIdx.y (mod gridDim.y) and
+  // their pooled columns -- the heavy phases below (dpool, dconv, conv weight gradients) need no exchange between
+  // them; the cheap head part above is recomputed by each and only CTA y = 0 publishes its gradients.
+  const bool lead = blockIdx.y == 0;
   // parameter gradients of the heads and the global free parameters: summed over the CTA's individuals, then one atomic
-  for (int j = tid; j < 2 * d.nglob; j += nt) {
+  for (int j = tid; lead && j < 2 * d.nglob; j += nt) {
     R a = R(0);
     for (int g = 0; g < ngr; ++g) a += dfree[g * nfr + 2 * ncond + j];
     atomicAdd(p.g_global_free + j, a);
   }
-  for (int e = tid; e < 2 * d.nl * d.nin_l; e += nt) {
+  for (int e = tid; lead && e < 2 * d.nl * d.nin_l; e += nt) {
     R a = R(0);
     for (int g = 0; g < ngr; ++g) a += dfree[g * nfr + e / d.nin_l] * xloc[g * d.nin_l + e % d.nin_l];
     atomicAdd(p.g_local_w + e, a);
   }
-  for (int r = tid; r < 2 * d.nl; r += nt) {
+  for (int r = tid; lead && r < 2 * d.nl; r += nt) {
     R a = R(0);
     for (int g = 0; g < ngr; ++g) a += dfree[g * nfr + r];
     atomicAdd(p.g_local_b + r, a);
   }
-  for (int e = tid; e < 2 * d.ng * d.nin_g; e += nt) {
+  for (int e = tid; lead && e < 2 * d.ng * d.nin_g; e += nt) {
     const int r = e / d.nin_g, i = e % d.nin_g;
     R a = R(0);
     for (int g = 0; g < ngr; ++g) {
@@ -241,18 +245,22 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
       for (int r = 0; r < 2 * d.nl; ++r) gg += p.local_w[(size_t)r * d.nin_l + o] * dfree[g * nfr + r];
       const R en = xloc[g * d.nin_l + o];
       gp = gg * (R(1) - en * en);  // tanh'
-      p.d_pre[(size_t)(b0 + g) * d.H + o] = gp;
+      if (lead) p.d_pre[(size_t)(b0 + g) * d.H + o] = gp;
     }
     dpre[e] = gp;
   }
   __syncthreads();
-  for (int o = tid; o < d.H; o += nt) {
+  for (int o = tid; lead && o < d.H; o += nt) {
     R a = R(0);
     for (int g = 0; g < ngr; ++g) a += dpre[g * d.H + o];
     atomicAdd(p.g_lin_b + o, a);
   }
+  // this CTA's filters: f = fy, fy + nfy, ...;  local filter index lf = f / nfy
+  const int fy = blockIdx.y, nfy = gridDim.y;
+  const int nfl = (d.F - fy + nfy - 1) / nfy;  // number of filters handled here
   // cotangent of the pooled features: dpool[g][i] = sum_o W[o][i] dpre[g][o]   (each weight loaded once for G individuals)
-  for (int i = tid; i < d.NLIN; i += nt) {
+  for (int li = tid; li < nfl * d.NP; li += nt) {
+    const int i = (fy + (li / d.NP) * nfy) * d.NP + li % d.NP;
     R acc[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) acc[g] = R(0);
@@ -266,7 +274,6 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
     for (int g = 0; g < G; ++g) dpool[(size_t)g * d.NLIN + i] = acc[g];
   }
   const R inv_pool = R(1) / R(d.PL);
-  const int nwc = d.F * d.NS * d.K;
   for (int g = 0; g < ngr; ++g) {
     const R* obs = p.obs + (size_t)(b0 + g) * d.NS * d.T;
     __syncthreads();  // dpool complete / previous individual's delta + dconv consumed
@@ -274,28 +281,29 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
       const int c = i / d.L1, j = i % d.L1;
       delta[i] = obs[c * d.T + j + 1] - obs[c * d.T + j];
     }
-    for (int i = tid; i < d.F * d.NCV; i += nt) {
-      const int f = i / d.NCV, j = i % d.NCV;
+    for (int li = tid; li < nfl * d.NCV; li += nt) {
+      const int f = fy + (li / d.NCV) * nfy, j = li % d.NCV;
       R a = R(0);
       for (int k = 0; k < d.PL; ++k) {
         const int jp = j - k;
         if (jp >= 0 && jp < d.NP) a += dpool[(size_t)g * d.NLIN + f * d.NP + jp];
       }
-      dconv[i] = a * inv_pool;
+      dconv[f * d.NCV + j] = a * inv_pool;
     }
     __syncthreads();
-    // conv weight / bias gradients: one warp per weight, lanes over the NCV positions
-    for (int e = warp; e < nwc + d.F; e += nw) {
+    // conv weight / bias gradients of this CTA's filters: one warp per weight, lanes over the NCV positions
+    const int wpf = d.NS * d.K + 1;  // weights + bias per filter
+    for (int le = warp; le < nfl * wpf; le += nw) {
+      const int f = fy + (le / wpf) * nfy, r = le % wpf;
       R a = R(0);
-      if (e < nwc) {
-        const int f = e / (d.NS * d.K), c = (e / d.K) % d.NS, k = e % d.K;
+      if (r < d.NS * d.K) {
+        const int c = r / d.K, k = r % d.K;
         for (int j = lane; j < d.NCV; j += 32) a += dconv[f * d.NCV + j] * delta[c * d.L1 + j + k];
       } else {
-        const int f = e - nwc;
         for (int j = lane; j < d.NCV; j += 32) a += dconv[f * d.NCV + j];
       }
       a = warp_sum(a);
-      if (lane == 0) atomicAdd(e < nwc ? p.g_conv_w + e : p.g_conv_b + (e - nwc), a);
+      if (lane == 0) atomicAdd(r < d.NS * d.K ? p.g_conv_w + f * d.NS * d.K + r : p.g_conv_b + f, a);
     }
   }
 }
@@ -338,6 +346,22 @@ __global__ void __launch_bounds__(128) enc_lin_wgrad_kernel(const EncDims d, con
         if (o < nh) atomicAdd(p.g_lin_w + (size_t)(o0 + o) * d.NLIN + i, acc[o]);
     }
   }
+}
+
+// small batches: one thread per weight (H * NLIN threads fill the machine; the B-deep sum is short)
+template <typename R>
+__global__ void __launch_bounds__(256) enc_lin_wgrad_small_kernel(const EncDims d, const EncPtrs<R> p) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= d.H * d.NLIN) return;
+  const int o = e / d.NLIN, i = e % d.NLIN;
+  R a0 = R(0), a1 = R(0);
+  int b = 0;
+  for (; b + 1 < d.B; b += 2) {
+    a0 += p.d_pre[(size_t)b * d.H + o] * p.pooled[(size_t)b * d.NLIN + i];
+    a1 += p.d_pre[(size_t)(b + 1) * d.H + o] * p.pooled[(size_t)(b + 1) * d.NLIN + i];
+  }
+  if (b < d.B) a0 += p.d_pre[(size_t)b * d.H + o] * p.pooled[(size_t)b * d.NLIN + i];
+  p.g_lin_w[e] += a0 + a1;
 }
 
 // device conditioner (vihds/ode.py:43-58, :99-116) including the reference's repeat/reshape quirk: sample n = b*IW + i
@@ -400,7 +424,17 @@ static void enc_bwd_g(const EncDims& d, const EncPtrs<R>& p, cudaStream_t s) {
   const size_t smem = sizeof(R) * ((size_t)d.NS * d.L1 + (size_t)d.F * d.NCV + (size_t)G * d.NLIN + G * d.nin_l +
                                    G * 2 * (d.nl + d.ng + d.nglob) + G * d.H + 8);
   if (smem > 48 * 1024) cudaFuncSetAttribute(enc_bwd_kernel<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  enc_bwd_kernel<R, G><<<(d.B + G - 1) / G, ENC_THREADS, smem, s>>>(d, p);
+  // small batches: split every individual over up to 5 CTAs by conv filter so that the latency-bound phases spread over
+  // more SMs (36 individuals -> 180 CTAs)
+  int fsplit = 1;
+  if (G == 1) {
+    fsplit = (2 * 148) / (d.B > 0 ? d.B : 1);
+    if (fsplit > 5) fsplit = 5;
+    if (fsplit > d.F) fsplit = d.F;
+    if (fsplit < 1) fsplit = 1;
+  }
+  dim3 grid((d.B + G - 1) / G, fsplit);
+  enc_bwd_kernel<R, G><<<grid, ENC_THREADS, smem, s>>>(d, p);
 }
 // individuals per CTA: 1 while the batch does not fill the machine anyway, 4 for large batches (if it fits shared memory)
 template <typename R>
@@ -428,6 +462,11 @@ static int enc_bwd_t(const EncDims& d, const vh_encoder_io* io, const vh_encoder
     enc_bwd_g<R, 4>(d, p, s);
   else
     enc_bwd_g<R, 1>(d, p, s);
+  if (d.B <= 128) {
+    const int n = d.H * d.NLIN;
+    enc_lin_wgrad_small_kernel<R><<<(n + 255) / 256, 256, 0, s>>>(d, p);
+    return 0;
+  }
   // enough CTAs for ~2 per SM: columns x splits of the individuals
   const int col_blocks = (d.NLIN + 127) / 128;
   int splits = (2 * 148 + col_blocks - 1) / col_blocks;
