@@ -364,10 +364,7 @@ def main():
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
-        gs.load_batch(pinned)
-        gs.load_u(u_host[i % n_pool])
-        gs.draw_conditioner()
-        cost = gs.step()
+        cost = gs.step_from_host(pinned, u_host[i % n_pool])
         cost_host.copy_(cost, non_blocking=True)
         torch.cuda.synchronize()
         if torch.isnan(cost_host).any():

@@ -312,3 +312,29 @@ def test_fused_encoder_large_batch_grouped_path():
     ref = torch.autograd.grad([mu0, pr0], params, [g_mu, g_pr], allow_unused=True)
     for a, b, p in zip(got, ref, params):
         assert _rel(a.cpu().numpy(), b.cpu().numpy()) < 5e-5, tuple(p.shape)
+
+
+def test_step_from_host_equals_step():
+    """The end-to-end entry (host buffers, u on a copy stream) takes the same steps as load_* + step()."""
+    case = load_case("dr_constant_icml_midpoint_f32_iw8")
+    batch = batch_from_case(case)
+    host = Settings(**{k: v.cpu().pin_memory() for k, v in batch.items()})
+    B, IW, P = case["u"].shape
+    us = [torch.randn(B, IW, P, generator=torch.Generator().manual_seed(i)).pin_memory() for i in range(3)]
+    flats = []
+    for mode in ("host", "device"):
+        _, _, model, tr = build("dr_constant_icml")
+        gs = GraphedStep(tr, B, IW, batch.times.numel())
+        torch.manual_seed(5)  # conditioner weights are drawn from the torch CPU stream inside both paths
+        for u in us:
+            if mode == "host":
+                c = gs.step_from_host(host, u)
+            else:
+                gs.load_batch(batch)
+                gs.draw_conditioner()
+                gs.load_u(u.cuda())
+                c = gs.step()
+            assert torch.isfinite(c).all()
+        torch.cuda.synchronize()
+        flats.append(tr.optimizer.flat.cpu().numpy())
+    assert _rel(flats[0], flats[1]) < 1e-6

@@ -143,3 +143,18 @@ def test_conditioner_weight_draw_matches_reference_construction():
             nn.init.normal_(lin.weight, mean=2.0, std=1.5)
             ref.append(lin.weight.detach().clone())
         assert all(torch.equal(a, b) for a, b in zip(got, ref)) and torch.equal(after, torch.rand(1))
+
+
+def test_in_place_conditioner_draw_consumes_the_same_stream():
+    """GraphedStep.draw_conditioner fills rows of a staging buffer in place; same RNG consumption as the module build."""
+    from vihds_b200.models import _draw_conditioner_weight
+
+    torch.manual_seed(4)
+    ref = torch.cat([_draw_conditioner_weight(7) for _ in range(2)], 0)
+    torch.manual_seed(4)
+    host = torch.empty(2, 7)
+    for row in (host[0:1], host[1:2]):
+        row.uniform_(-1.0, 1.0)
+        row.uniform_(-1.0, 1.0)
+        row.normal_(mean=2.0, std=1.5)
+    assert torch.equal(host, ref)

@@ -104,7 +104,7 @@ def load():
 
 
 def check(status):
-    if status != 0:
+    if status:
         raise RuntimeError("libvihds_b200: %s (status %d)" % (load().vh_last_error().decode(), status))
 
 

@@ -233,19 +233,21 @@ class GraphedStep(object):
                                 g_logq_theta=_ptr(b.g_lq), d_q_mu=_ptr(b.d_q_mu), d_q_prec=_ptr(b.d_q_prec),
                                 d_extra=_ptr(self.d_extra), d_weights=_ptr(self.d_weights))
         self._bio.fwd.theta = None
+        vdt = self.prob.vh_dtype
+        self._iwae_fwd_args = (vdt, self.B, self.IW, self.b_total, _ptr(b.lpx), _ptr(b.lp), _ptr(b.lq), _ptr(b.cost),
+                               _ptr(b.log_w), _ptr(b.w))
+        self._iwae_bwd_args = (vdt, self.B, self.IW, self.b_total, _ptr(b.w), None, _ptr(b.g_lpx), _ptr(b.g_lp), _ptr(b.g_lq))
+        self._p_ref, self._fio_ref, self._bio_ref = C.byref(self._p), C.byref(self._fio), C.byref(self._bio)
 
     def _hot(self):
-        """The hot path: four launches of libvihds_b200.so on the current stream."""
-        lib, b, s = self.prob.lib, self.buf, _stream()
-        vdt = self.prob.vh_dtype
-        L.check(lib.vh_elbo_terms_fwd(C.byref(self._p), C.byref(self._fio), s))
-        L.check(lib.vh_iwae_fwd(vdt, self.B, self.IW, self.b_total, _ptr(b.lpx), _ptr(b.lp), _ptr(b.lq), _ptr(b.cost),
-                                _ptr(b.log_w), _ptr(b.w), s))
-        L.check(lib.vh_iwae_bwd(vdt, self.B, self.IW, self.b_total, _ptr(b.w), None, _ptr(b.g_lpx), _ptr(b.g_lp),
-                                _ptr(b.g_lq), s))
+        """The hot path: four launches of libvihds_b200.so on the current stream (arguments pre-built)."""
+        lib, s = self.prob.lib, _stream()
+        L.check(lib.vh_elbo_terms_fwd(self._p_ref, self._fio_ref, s))
+        L.check(lib.vh_iwae_fwd(*self._iwae_fwd_args, s))
+        L.check(lib.vh_iwae_bwd(*self._iwae_bwd_args, s))
         if self.ev_hot is not None:
             self.ev_hot[0].record()
-        L.check(lib.vh_elbo_terms_bwd(C.byref(self._p), C.byref(self._bio), s))
+        L.check(lib.vh_elbo_terms_bwd(self._p_ref, self._bio_ref, s))
         if self.ev_hot is not None:
             self.ev_hot[1].record()
 
@@ -309,18 +311,63 @@ class GraphedStep(object):
 
     def load_batch(self, batch, non_blocking=True):
         for k in ("times", "inputs", "dev_1hot", "observations"):
-            self.batch[k].copy_(batch[k], non_blocking=non_blocking)
+            src = batch[k]
+            if k == "times":  # the time grid belongs to the data set: skip the copy while the same tensor is handed in
+                tag = (id(src), src._version)
+                if getattr(self, "_times_tag", None) == tag:
+                    continue
+                self._times_tag = tag
+            self.batch[k].copy_(src, non_blocking=non_blocking)
 
     def load_u(self, u, non_blocking=True):
         self.u.copy_(u.reshape(self.N, self.P), non_blocking=non_blocking)
 
     def draw_conditioner(self):
-        """Fresh conditioner weights per step from the torch CPU RNG (reference quirk, vihds/ode.py:48)."""
-        from .models import _draw_conditioner_weight
+        """Fresh conditioner weights per step from the torch CPU RNG (reference quirk, vihds/ode.py:48): per parameter two
+        uniform fills and one normal fill of a [1, D] row -- the draws models._draw_conditioner_weight makes, done in
+        place on a pinned staging buffer -- then one asynchronous copy."""
+        if not self.rel:
+            return
+        if not hasattr(self, "_cond_host"):
+            self._cond_host = torch.empty(len(self.extras), self.cond_w.shape[1]).pin_memory()
+            self._cond_rows = [self._cond_host[k:k + 1] for k in range(len(self.extras))]
+        for row in self._cond_rows:
+            row.uniform_(-1.0, 1.0)
+            row.uniform_(-1.0, 1.0)
+            row.normal_(mean=2.0, std=1.5)
+        self.cond_w.copy_(self._cond_host, non_blocking=True)
 
-        if self.rel:
-            w = torch.cat([_draw_conditioner_weight(self.cond_w.shape[1]) for _ in self.extras], 0)
-            self.cond_w.copy_(w.to(self.cond_w.dtype), non_blocking=True)
+    def step_from_host(self, batch, u):
+        """The public end-to-end step: ``batch`` (times, inputs, dev_1hot, observations) and ``u`` [B, IW, P] are HOST
+        tensors (pinned for asynchronous copies).  The small batch tensors and the conditioner weights go first, the
+        encoder graph is launched, and the 1 MB of ``u`` -- which only the ODE kernel needs -- travels on a copy stream
+        underneath it.  Returns the cost (device tensor, no sync)."""
+        self.prepare()
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream()
+            self._u_ready, self._u_free = torch.cuda.Event(), torch.cuda.Event()
+            self._u_free.record(cur)
+        self.load_batch(batch)
+        self.draw_conditioner()
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._u_free)  # the previous step's reverse sweep still reads the old u
+            self.load_u(u)
+            self._u_ready.record(self._copy_stream)
+        if self.use_graphs:
+            self.g_pre.replay()
+        else:
+            self._pre()
+            self._build_descriptors()
+        cur.wait_event(self._u_ready)
+        self._hot()
+        self._u_free.record(cur)
+        if self.use_graphs:
+            self.g_post.replay()
+        else:
+            self._post()
+        self.steps_done += 1
+        return self.buf.cost
 
     def step(self):
         """One step on whatever the static buffers hold.  Returns the cost (device tensor, no sync)."""
