@@ -169,6 +169,7 @@ struct BbRhs {
     }
   }
   VH_HD void eval_keep(R t, const R* x, R* dx, Kept&) const { eval(t, x, dx); }  // eval() never writes the row
+  VH_HD void keep_only(R, const R*, Kept&) const {}
 
   // g: cotangent of dx  ->  gx (accumulated); the staged rows go to the weight-gradient sink gw
   template <typename GW>

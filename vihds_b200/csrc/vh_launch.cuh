@@ -6,6 +6,7 @@
 // dependent chain, so the parallel axis is trajectories, not species.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "vh_dispatch.cuh"
 
@@ -107,6 +108,224 @@ __global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-specialised reverse sweep for latency-bound launches (N small enough that every scheduler holds at most one
+// warp).  A CTA is a PAIR of warps over the same 32 trajectories:
+//   warp 0 (producer)  loads checkpoint x(k) and re-evaluates the stages of step k -> k+1 (rk_stages_forward): this
+//                      needs the checkpoint only, so it runs ahead of the adjoint;
+//   warp 1 (consumer)  takes x(k), the stage derivatives and the kept RHS intermediates from a two-slot shared-memory
+//                      ring and does the part that is serial in lambda: rk_step_adjoint + the emission adjoint.
+// The two halves of a time step (~200 and ~260 instructions) run on two schedulers instead of one after the other on
+// one.  Hand-off: named barriers (full / empty per slot, bar.arrive on one side, bar.sync on the other), data laid out
+// [item][lane] (conflict-free).  fp32 / fp64, constant-precision models (no weight-gradient accumulators to share).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+
+template <class M, class TB>
+struct WsRing {
+  typedef typename M::real R;
+  typedef StageData<Rhs<M>, TB> SD;
+  static constexpr int KN = sizeof(typename M::Mid) / sizeof(R);
+  static constexpr int NITEM = M::S + SD::nk * M::S + TB::s * KN;
+  static constexpr int SLOT = NITEM * 32;  // elements per ring slot
+  __device__ static void put(R* slot, int lane, const R* x, const SD& sd) {
+    int it = 0;
+#pragma unroll
+    for (int q = 0; q < M::S; ++q) slot[(it++) * 32 + lane] = x[q];
+#pragma unroll
+    for (int i = 0; i < SD::nk; ++i)
+#pragma unroll
+      for (int q = 0; q < M::S; ++q) slot[(it++) * 32 + lane] = sd.k[i][q];
+#pragma unroll
+    for (int i = 0; i < TB::s; ++i) {
+      const R* m = reinterpret_cast<const R*>(&sd.kept[i]);
+#pragma unroll
+      for (int j = 0; j < KN; ++j) slot[(it++) * 32 + lane] = m[j];
+    }
+  }
+  __device__ static void get(const R* slot, int lane, R* x, SD& sd) {
+    int it = 0;
+#pragma unroll
+    for (int q = 0; q < M::S; ++q) x[q] = slot[(it++) * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < SD::nk; ++i)
+#pragma unroll
+      for (int q = 0; q < M::S; ++q) sd.k[i][q] = slot[(it++) * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < TB::s; ++i) {
+      R* m = reinterpret_cast<R*>(&sd.kept[i]);
+#pragma unroll
+      for (int j = 0; j < KN; ++j) m[j] = slot[(it++) * 32 + lane];
+    }
+  }
+};
+
+template <class M, class TB>
+__global__ void __launch_bounds__(64) elbo_bwd_ws_kernel(const Call<typename M::real> a) {
+  typedef typename M::real R;
+  typedef WsRing<M, TB> Ring;
+  constexpr int S = M::S;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  R* ring = reinterpret_cast<R*>(smem_raw);
+  const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * 32 + lane;
+  const bool active = n0 < a.N;
+  const int n = active ? n0 : a.N - 1;  // every lane runs (the named barriers count 64 threads)
+  const int b = n / a.IW;
+  const size_t N = a.N;
+  const int T = a.T;
+  enum { FULL0 = 1, EMPTY0 = 3 };
+  // both roles need the RHS constants
+  Rhs<M> f;
+  f.w = nullptr;
+  R prec[4], iprec[4];
+  {
+    R th[M::NSLOT];
+    R lq = R(0), lp = R(0), c6, c12;
+    load_theta<M, true>(a, n, b, th, lq, lp, false);
+    M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
+    M::setup(th, c6, c12, f.c);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      prec[o] = th[S_prec_x + o];
+      iprec[o] = R(1) / prec[o];
+    }
+  }
+  const R h0 = a.times[1] - a.times[0];
+  const size_t slab = (size_t)S * N;
+  if (role == 0) {
+    // ---------------- producer: checkpoints + stage re-evaluation, one step ahead ----------------
+    const R* xs = a.x_states + (size_t)(T - 2) * slab + n;
+    R x[S], xn[S];
+#pragma unroll
+    for (int q = 0; q < S; ++q) x[q] = xs[(size_t)q * N];
+    R t1 = a.times[T - 1], t0 = a.times[T - 2];
+    for (int k = T - 2; k >= 0; --k) {
+      const int it = T - 2 - k, slot = it & 1;
+      const int kp = k > 0 ? k - 1 : 0;
+      if (k > 0) xs -= slab;
+#pragma unroll
+      for (int q = 0; q < S; ++q) xn[q] = xs[(size_t)q * N];  // next checkpoint, consumed next iteration
+      const R tp = ld_early(a.times + kp);
+      typename Ring::SD sd;
+      rk_stages_forward<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd);
+      if (it >= 2) named_bar_sync(EMPTY0 + slot);  // the consumer has released this slot
+      Ring::put(ring + slot * Ring::SLOT, lane, x, sd);
+      __threadfence_block();
+      named_bar_arrive(FULL0 + slot);
+#pragma unroll
+      for (int q = 0; q < S; ++q) x[q] = xn[q];
+      t1 = t0;
+      t0 = tp;
+    }
+    return;
+  }
+  // ---------------- consumer: everything that is serial in lambda ----------------
+  R gl[4], gprec[4];
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    gprec[o] = R(0);
+    gl[o] = (a.g_logp_species && active) ? a.g_logp_species[(size_t)n * 4 + o] : R(0);
+  }
+  const R glq = (a.g_logq_theta && active) ? a.g_logq_theta[n] : R(0);
+  const R glp = (a.g_logp_theta && active) ? a.g_logp_theta[n] : R(0);
+  const R* obs = a.obs ? a.obs + (size_t)b * 4 * T : nullptr;
+  const R* gxs = a.g_x_states ? a.g_x_states + (size_t)(T - 1) * slab + n : nullptr;
+  const R* gxpr = a.g_x_predict ? a.g_x_predict + (size_t)(T - 1) * 4 * N + n : nullptr;
+  typename M::Consts gc;
+#pragma unroll
+  for (int i = 0; i < M::NC; ++i) gc.v[i] = R(0);
+  NoGW<R> nogw;
+  R lam[S], x[S];
+  R ob[4] = {R(0), R(0), R(0), R(0)}, obp[4] = {R(0), R(0), R(0), R(0)};
+#pragma unroll
+  for (int q = 0; q < S; ++q) {
+    lam[q] = R(0);
+    x[q] = a.x_states[(size_t)(T - 1) * slab + (size_t)q * N + n];
+  }
+  if (obs) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) ob[o] = obs[o * T + T - 1];
+  }
+  R t1 = a.times[T - 1], t0 = t1;
+  for (int k = T - 1; k >= 0; --k) {
+    const int kp = k > 0 ? k - 1 : 0;
+    if (obs) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) obp[o] = ld_early(obs + o * T + kp);
+    }
+    const R tp = ld_early(a.times + kp);
+    if (k + 1 < T) {
+      const int it = T - 2 - k, slot = it & 1;
+      typename Ring::SD sd;
+      named_bar_sync(FULL0 + slot);
+      Ring::get(ring + slot * Ring::SLOT, lane, x, sd);
+      if (k >= 2) {  // slot will be refilled with step k-2; the last two fills are never waited for
+        __threadfence_block();
+        named_bar_arrive(EMPTY0 + slot);
+      }
+      rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd, lam, gc, nogw);
+    }
+    // emission at time k
+    R xp[4], gxp[4];
+    M::observe(x, xp);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      gxp[o] = (gxpr && active) ? gxpr[(size_t)o * N] : R(0);
+      if (obs) {
+        const R d = xp[o] - ob[o];
+        gxp[o] -= gl[o] * prec[o] * d;
+        gprec[o] += gl[o] * R(0.5) * (iprec[o] - d * d);
+      }
+    }
+    M::observe_vjp(x, gxp, lam);
+    if (gxs) {
+      if (active) {
+#pragma unroll
+        for (int q = 0; q < S; ++q) lam[q] += gxs[(size_t)q * N];
+      }
+      gxs -= slab;
+    }
+    if (gxpr) gxpr -= (size_t)4 * N;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) ob[o] = obp[o];
+    t1 = t0;
+    t0 = tp;
+  }
+  // chain rule back to theta + scatter (as traj_backward)
+  R gth[M::NSLOT];
+#pragma unroll
+  for (int s = 0; s < M::NSLOT; ++s) gth[s] = R(0);
+  {
+    R th[M::NSLOT];
+    R lq = R(0), lp = R(0), c6, c12;
+    load_theta<M, true>(a, n, b, th, lq, lp, false);
+    M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
+    M::init_state_vjp(lam, gth);
+    M::setup_vjp(th, c6, c12, f.c, gc, gth);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gprec[o];
+  }
+  WarpSegRed<R> red(a.d_q_mu, a.d_q_prec, a.P, b, active);
+  R gloc[M::NSLOT];
+#pragma unroll
+  for (int s = 0; s < M::NSLOT; ++s) gloc[s] = M::uses(s) ? gth[s] : R(0);
+#pragma unroll 5
+  for (int k = 0; k < a.P; ++k) {
+    const int s = a.col_slot[k];
+    R dmu = R(0), dprec = R(0);
+    if (active) column_vjp(a, n, b, k, s >= 0 ? gloc[s] : R(0), glq, glp, dmu, dprec);
+    red(b, k, dmu, dprec, active);
+  }
+  if (a.d_extra && active) {
+    for (int s = 0; s < M::NSLOT; ++s) {
+      const int src = a.slot_src[s];
+      if (src < 0 && src != VH_SLOT_UNUSED) a.d_extra[(size_t)(-1 - src) * N + n] = gloc[s];
+    }
+  }
+}
+
 inline int pick_block(int N) {
   // small batches are latency-bound: spread warps over as many SMs as possible (148 SMs x 4 schedulers)
   if (N <= 148 * 4 * 32) return 32;
@@ -137,6 +356,26 @@ template <typename R>
 struct BwdLauncher {
   Call<R> a;
   cudaStream_t stream;
+  // warp-specialised pair kernel: latency-bound launches (the 32-thread-CTA regime) of constant-precision models.
+  // VIHDS_BWD_WS=0|1 overrides (tests / measurements).
+  template <class M>
+  static bool use_ws(int block) {
+    static const int mode = [] {
+      const char* m = getenv("VIHDS_BWD_WS");
+      return !m ? -1 : atoi(m);
+    }();
+    if (M::DYN) return false;
+    return mode >= 0 ? mode != 0 : block == 32;
+  }
+  template <class M, class TB>
+  void launch_bwd_variant(bool ws, int grid, int block, size_t smem) {
+    if (ws) {
+      const size_t ring = sizeof(R) * 2 * WsRing<M, TB>::SLOT;
+      elbo_bwd_ws_kernel<M, TB><<<(a.N + 31) / 32, 64, ring, stream>>>(a);
+    } else {
+      elbo_bwd_kernel<M, TB><<<grid, block, smem, stream>>>(a);
+    }
+  }
   template <class M, class TB>
   int run() {
     constexpr int NW = NetInfo<M>::NW;
@@ -145,7 +384,8 @@ struct BwdLauncher {
     const int grid = (a.N + block - 1) / block;
     const size_t smem = sizeof(R) * NW * (block + 1);
     cudaError_t e;
-    if (smem > 48 * 1024) {
+    const bool ws = use_ws<M>(block);
+    if (!ws && smem > 48 * 1024) {
       e = cudaFuncSetAttribute(elbo_bwd_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
@@ -157,7 +397,7 @@ struct BwdLauncher {
       cudaMemsetAsync(a.d_q_prec, 0, sizeof(R) * (size_t)a.B * a.P, stream);
     }
     if (NW > 0) cudaMemsetAsync(a.d_weights, 0, sizeof(R) * NW, stream);
-    elbo_bwd_kernel<M, TB><<<grid, block, smem, stream>>>(a);
+    launch_bwd_variant<M, TB>(ws, grid, block, smem);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error("elbo_bwd_kernel launch failed: %s", cudaGetErrorString(e));

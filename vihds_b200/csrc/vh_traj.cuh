@@ -110,6 +110,8 @@ struct Rhs {
     M::rhs_from(x, c, m, dx);
     if (M::DYN) LinPrecNet<R, M::NIN>::rhs(t, x, x + M::NS, w, dx + M::NS);
   }
+  // intermediates only (last stage of a step: its derivative is not needed to rebuild any stage state)
+  VH_HD void keep_only(R t, const R* x, Mid& m) const { M::mid(t, x, c, m); }
   template <typename GW>
   VH_HD void vjp_kept(R t, const R* x, const Mid& m, const R* g, R* gx, typename M::Consts& gc, GW& gw) const {
     M::rhs_vjp_from(x, c, m, g, gx, gc);
@@ -157,6 +159,86 @@ VH_HD void rk_step(const F& f, typename F::real t0, typename F::real t1, typenam
 #pragma unroll
       for (int q = 0; q < S; ++q) x[q] += hb * k[i][q];
     }
+}
+
+// The reverse of one step has two phases.  Phase 1 (rk_stages_forward) re-evaluates the stages from the checkpoint
+// x(t0): it depends on the checkpoint only, NOT on the adjoint state.  Phase 2 (rk_step_adjoint) is linear in lam and
+// uses only the kept intermediates.  rk_step_vjp runs them back to back in one thread; the warp-specialised reverse
+// kernel (vh_launch.cuh, elbo_bwd_ws_kernel) gives phase 1 to a producer warp that runs one step ahead of the
+// consumer warp doing phase 2.
+template <class F, class TB>
+struct StageData {
+  typedef typename F::real R;
+  static constexpr int s = TB::s;
+  static constexpr int nk = s > 1 ? s - 1 : 1;
+  R k[nk][F::S];                 // stage derivatives 0 .. s-2 (the last one is never needed to rebuild a stage state)
+  typename F::Kept kept[TB::s];  // RHS intermediates of every stage, reused by its vjp
+};
+
+template <class F, class TB>
+VH_HD void rk_stages_forward(const F& f, typename F::real t0, typename F::real t1, typename F::real h,
+                             const typename F::real* x, StageData<F, TB>& sd) {
+  typedef typename F::real R;
+  constexpr int S = F::S;
+  constexpr int s = TB::s;
+#pragma unroll
+  for (int i = 0; i < s; ++i) {
+    R X[S];
+#pragma unroll
+    for (int q = 0; q < S; ++q) X[q] = x[q];
+#pragma unroll
+    for (int j = 0; j < i; ++j)
+      if (TB::a(i, j) != R(0)) {
+        const R ha = h * TB::a(i, j);
+#pragma unroll
+        for (int q = 0; q < S; ++q) X[q] += ha * sd.k[j][q];
+      }
+    if (i + 1 < s)
+      f.eval_keep(stage_time<TB, R>(i, t0, t1), X, sd.k[i], sd.kept[i]);
+    else
+      f.keep_only(stage_time<TB, R>(i, t0, t1), X, sd.kept[i]);
+  }
+}
+
+// lam: in = dL/dx(t1), out = dL/dx(t0);  x = state at t0;  gc/gw accumulate parameter cotangents
+template <class F, class TB, typename GW>
+VH_HD void rk_step_adjoint(const F& f, typename F::real t0, typename F::real t1, typename F::real h,
+                           const typename F::real* x, const StageData<F, TB>& sd, typename F::real* lam,
+                           typename F::Grad& gc, GW& gw) {
+  typedef typename F::real R;
+  constexpr int S = F::S;
+  constexpr int s = TB::s;
+  R gk[s][S];
+#pragma unroll
+  for (int i = 0; i < s; ++i)
+#pragma unroll
+    for (int q = 0; q < S; ++q) gk[i][q] = (h * TB::b(i)) * lam[q];
+#pragma unroll
+  for (int i = s - 1; i >= 0; --i) {
+    R X[S], gX[S];
+#pragma unroll
+    for (int q = 0; q < S; ++q) {
+      X[q] = x[q];
+      gX[q] = R(0);
+    }
+#pragma unroll
+    for (int j = 0; j < i; ++j)
+      if (TB::a(i, j) != R(0)) {
+        const R ha = h * TB::a(i, j);
+#pragma unroll
+        for (int q = 0; q < S; ++q) X[q] += ha * sd.k[j][q];
+      }
+    f.vjp_kept(stage_time<TB, R>(i, t0, t1), X, sd.kept[i], gk[i], gX, gc, gw);
+#pragma unroll
+    for (int q = 0; q < S; ++q) lam[q] += gX[q];
+#pragma unroll
+    for (int j = 0; j < i; ++j)
+      if (TB::a(i, j) != R(0)) {
+        const R ha = h * TB::a(i, j);
+#pragma unroll
+        for (int q = 0; q < S; ++q) gk[j][q] += ha * gX[q];
+      }
+  }
 }
 
 // lam: in = dL/dx(t1), out = dL/dx(t0);  x = state at t0;  gc/gw accumulate parameter cotangents
@@ -248,7 +330,7 @@ VH_HD R sample_column(const Call<R>& a, int n, int b, int k, R& lq, R& lp, bool 
 // ROLLED over the P sampled columns (one copy of sample_column in the instruction stream instead of one per slot):
 // values land in a small per-thread array indexed by slot (local memory, L1-resident), from which the model's slot
 // registers are filled with constant indices.
-template <class M>
+template <class M, bool UNROLL = false>
 VH_HD void load_theta(const Call<typename M::real>& a, int n, int b, typename M::real* th, typename M::real& lq,
                       typename M::real& lp, bool store = true) {
   typedef typename M::real R;
@@ -257,10 +339,23 @@ VH_HD void load_theta(const Call<typename M::real>& a, int n, int b, typename M:
     const int src = a.slot_src[s];
     loc[s] = (src < 0 && src != VH_SLOT_UNUSED) ? a.extra[(size_t)(-1 - src) * a.N + n] : R(0);
   }
-  for (int k = 0; k < a.P; ++k) {
-    const R v = sample_column(a, n, b, k, lq, lp, store);
-    const int s = a.col_slot[k];
-    if (s >= 0) loc[s] = v;
+  // The columns are independent: partial unrolling lets the ~8 dependent-latency loads of several columns overlap.
+  // Used by the reverse kernels, where at the icml size this prologue (run twice) and the matching epilogue had grown
+  // to 58 % of the samples; the forward kernels keep the rolled loop (unrolled it costs 8 % at N = 131,072).
+  if (UNROLL) {
+#pragma unroll 5
+    for (int k = 0; k < a.P; ++k) {
+      const R v = sample_column(a, n, b, k, lq, lp, store);
+      const int s = a.col_slot[k];
+      if (s >= 0) loc[s] = v;
+    }
+  } else {
+#pragma unroll 1
+    for (int k = 0; k < a.P; ++k) {
+      const R v = sample_column(a, n, b, k, lq, lp, store);
+      const int s = a.col_slot[k];
+      if (s >= 0) loc[s] = v;
+    }
   }
 #pragma unroll
   for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? loc[s] : R(0);
@@ -416,7 +511,7 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
     {
       R th[M::NSLOT];
       R lq = R(0), lp = R(0), c6, c12;
-      load_theta<M>(a, n, b, th, lq, lp, false);  // never rewrite theta in the reverse pass
+      load_theta<M, true>(a, n, b, th, lq, lp, false);  // never rewrite theta in the reverse pass
       M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
       M::setup(th, c6, c12, f.c);
 #pragma unroll
@@ -504,7 +599,7 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
     // chain rule back to theta: re-derive theta (cheap) rather than keep it live across the loop
     R th[M::NSLOT];
     R lq = R(0), lp = R(0), c6, c12;
-    load_theta<M>(a, n, b, th, lq, lp, false);
+    load_theta<M, true>(a, n, b, th, lq, lp, false);
     M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
     M::init_state_vjp(lam, gth);
     M::setup_vjp(th, c6, c12, f.c, gc, gth);
@@ -518,6 +613,7 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
   R gloc[M::NSLOT];
 #pragma unroll
   for (int s = 0; s < M::NSLOT; ++s) gloc[s] = M::uses(s) ? gth[s] : R(0);
+#pragma unroll 5
   for (int k = 0; k < a.P; ++k) {
     const int s = a.col_slot[k];
     R dmu = R(0), dprec = R(0);
