@@ -127,7 +127,9 @@ typedef struct vh_fwd_io {
 /* Backward (discrete adjoint of the exact stepper; what autograd's replay of the unrolled solve computes in the
  * reference, vihds/training.py:334).  Re-reads the x_states trace written by the forward call as its checkpoint. */
 typedef struct vh_bwd_io {
-  vh_fwd_io fwd;                 /* the forward call's inputs and its x_states output (x_predict/log* unused) */
+  vh_fwd_io fwd;                 /* the forward call's inputs and its x_states output (x_predict/log* unused);
+                                  * fwd.theta, if non-NULL, must be the forward call's theta OUTPUT: the reverse sweep
+                                  * then reads it back (P coalesced loads) instead of re-sampling from u */
   const void* g_logp_by_species; /* [N][4] upstream gradients, any may be NULL (= zero) */
   const void* g_logp_theta;      /* [N] */
   const void* g_logq_theta;      /* [N] */

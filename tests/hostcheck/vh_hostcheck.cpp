@@ -25,7 +25,9 @@ struct FwdRunner {
   const Call<R>* a;
   template <class M, class TB>
   int run() {
-    for (int n = 0; n < a->N; ++n) traj_forward<M, TB>(*a, n, a->weights);
+    std::vector<R> scratch(M::NSLOT);
+    SlotScratch<R> sc{scratch.data(), 1};
+    for (int n = 0; n < a->N; ++n) traj_forward<M, TB>(*a, n, a->weights, sc);
     return 0;
   }
 };
@@ -43,7 +45,9 @@ struct BwdRunner {
     for (int n = 0; n < a->N; ++n) {
       for (size_t i = 0; i < nw; ++i) gw[i] = R(0);
       StridedGW<R> h{gw.data(), 1};
-      traj_backward<M, TB>(*a, n, true, a->weights, h, red);
+      std::vector<R> scratch(M::NSLOT);
+      SlotScratch<R> sc{scratch.data(), 1};
+      traj_backward<M, TB>(*a, n, true, a->weights, h, red, sc);
       for (size_t i = 0; i < nw; ++i) a->d_weights[i] += gw[i];
     }
     return 0;

@@ -80,7 +80,13 @@ def test_host_math_matches_reference(hc, name):
                  d_weights=None if w is None else np.zeros_like(w, dtype=dt),
                  d_extra=None if extra is None else np.zeros_like(extra))
     bio = L.vh_bwd_io(fwd=io, **{k: _ptr(v) for k, v in bkeep.items()})
-    assert hc.hc_bwd(C.byref(p), C.byref(bio)) == 0
+    assert hc.hc_bwd(C.byref(p), C.byref(bio)) == 0  # fwd.theta handed back: the reverse sweep re-reads theta
+    first = {k: v.copy() for k, v in bkeep.items() if k.startswith("d_") and v is not None}
+    io2 = L.vh_fwd_io(**{k: _ptr(v) for k, v in keep.items() if k != "theta"})
+    bio2 = L.vh_bwd_io(fwd=io2, **{k: _ptr(v) for k, v in bkeep.items()})
+    assert hc.hc_bwd(C.byref(p), C.byref(bio2)) == 0  # fwd.theta == NULL: re-sampled from u; same gradients
+    for k, v in first.items():
+        assert _rel(bkeep[k], v) < (1e-12 if f64 else 2e-5), k
     gtol = 1e-6 if f64 else 3e-3
     per_ind = case["per_individual"].astype(bool)
     sel = case["kinds"] != 0

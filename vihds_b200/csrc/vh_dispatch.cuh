@@ -88,6 +88,8 @@ inline const char* build_call(const vh_problem* p, const vh_fwd_io* io, const vh
     a.g_x_states = (const R*)bio->g_x_states; a.g_x_predict = (const R*)bio->g_x_predict;
     a.d_q_mu = (R*)bio->d_q_mu; a.d_q_prec = (R*)bio->d_q_prec; a.d_extra = (R*)bio->d_extra; a.d_weights = (R*)bio->d_weights;
     if (!a.x_states) return "backward needs the forward x_states trace";
+    a.theta_in = a.theta;  // the forward call's theta output, if handed back: reused instead of re-sampling
+    a.theta = nullptr;     // never written by the reverse sweep
     if (p->P > 0 && (!a.d_q_mu || !a.d_q_prec)) return "backward with P > 0 needs d_q_mu and d_q_prec";
     if (model_is_dyn(p->model) && !a.d_weights) return "backward of a dynamic-precision model needs d_weights";
   }

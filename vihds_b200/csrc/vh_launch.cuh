@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(128) elbo_fwd_kernel(const Call<typename M::re
     __syncthreads();
   }
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n < a.N) traj_forward<M, TB>(a, n, w);
+  const SlotScratch<R> sc{w + ((NetInfo<M>::NW + 3) & ~3) + threadIdx.x, (int)blockDim.x};
+  if (n < a.N) traj_forward<M, TB>(a, n, w, sc);
 }
 
 // 3 resident CTAs of 128 threads per SM (<= 168 registers) for the fp32 8-species models: measured faster than 2 CTAs
@@ -93,9 +94,10 @@ __global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel
   const bool active = n < a.N;
   const int nn = active ? n : a.N - 1;
   WarpSegRed<R> red(a.d_q_mu, a.d_q_prec, a.P, nn / a.IW, active);
+  const SlotScratch<R> sc{w + ((NW * ((int)blockDim.x + 1) + 3) & ~3) + threadIdx.x, (int)blockDim.x};
   if (M::DYN) {
     StridedGW<R> h{gw + threadIdx.x, (int)blockDim.x};
-    traj_backward<M, TB>(a, nn, active, w, h, red);
+    traj_backward<M, TB>(a, nn, active, w, h, red, sc);
     __syncthreads();
     for (int k = threadIdx.x; k < NW; k += blockDim.x) {
       R s = R(0);
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel
     }
   } else {
     NoGW<R> nogw;
-    traj_backward<M, TB>(a, nn, active, w, nogw, red);
+    traj_backward<M, TB>(a, nn, active, w, nogw, red, sc);
   }
 }
 
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(64) elbo_bwd_ws_kernel(const Call<typename M::
   const size_t N = a.N;
   const int T = a.T;
   enum { FULL0 = 1, EMPTY0 = 3 };
+  const SlotScratch<R> sc{ring + 2 * Ring::SLOT + threadIdx.x, 64};
   // both roles need the RHS constants
   Rhs<M> f;
   f.w = nullptr;
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(64) elbo_bwd_ws_kernel(const Call<typename M::
   {
     R th[M::NSLOT];
     R lq = R(0), lp = R(0), c6, c12;
-    load_theta<M, true>(a, n, b, th, lq, lp, false);
+    load_theta<M, true>(a, n, b, th, lq, lp, sc, false);
     M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
     M::setup(th, c6, c12, f.c);
 #pragma unroll
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(64) elbo_bwd_ws_kernel(const Call<typename M::
   {
     R th[M::NSLOT];
     R lq = R(0), lp = R(0), c6, c12;
-    load_theta<M, true>(a, n, b, th, lq, lp, false);
+    load_theta<M, true>(a, n, b, th, lq, lp, sc, false);
     M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
     M::init_state_vjp(lam, gth);
     M::setup_vjp(th, c6, c12, f.c, gc, gth);
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(64) elbo_bwd_ws_kernel(const Call<typename M::
     for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gprec[o];
   }
   WarpSegRed<R> red(a.d_q_mu, a.d_q_prec, a.P, b, active);
-  R gloc[M::NSLOT];
+  const SlotScratch<R>& gloc = sc;
 #pragma unroll
   for (int s = 0; s < M::NSLOT; ++s) gloc[s] = M::uses(s) ? gth[s] : R(0);
 #pragma unroll 5
@@ -341,7 +344,8 @@ struct FwdLauncher {
   int run() {
     const int block = pick_block(a.N);
     const int grid = (a.N + block - 1) / block;
-    const size_t smem = sizeof(R) * NetInfo<M>::NW;
+    const size_t smem = sizeof(R) * (((NetInfo<M>::NW + 3) & ~3) + (size_t)M::NSLOT * block);  // weights | slot scratch
+    if (smem > 48 * 1024) cudaFuncSetAttribute(elbo_fwd_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     elbo_fwd_kernel<M, TB><<<grid, block, smem, stream>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -370,7 +374,7 @@ struct BwdLauncher {
   template <class M, class TB>
   void launch_bwd_variant(bool ws, int grid, int block, size_t smem) {
     if (ws) {
-      const size_t ring = sizeof(R) * 2 * WsRing<M, TB>::SLOT;
+      const size_t ring = sizeof(R) * (2 * WsRing<M, TB>::SLOT + (size_t)M::NSLOT * 64);  // ring | slot scratch
       elbo_bwd_ws_kernel<M, TB><<<(a.N + 31) / 32, 64, ring, stream>>>(a);
     } else {
       elbo_bwd_kernel<M, TB><<<grid, block, smem, stream>>>(a);
@@ -380,9 +384,9 @@ struct BwdLauncher {
   int run() {
     constexpr int NW = NetInfo<M>::NW;
     int block = pick_block(a.N);
-    if (NW > 0 && sizeof(R) * NW * (block + 1) > 200 * 1024) block = 64;
+    if (NW > 0 && sizeof(R) * (NW * (block + 1) + M::NSLOT * block) > 200 * 1024) block = 64;
     const int grid = (a.N + block - 1) / block;
-    const size_t smem = sizeof(R) * NW * (block + 1);
+    const size_t smem = sizeof(R) * (((NW * (block + 1) + 3) & ~3) + (size_t)M::NSLOT * block);  // w | gw | slot scratch
     cudaError_t e;
     const bool ws = use_ws<M>(block);
     if (!ws && smem > 48 * 1024) {

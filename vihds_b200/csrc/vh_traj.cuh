@@ -71,6 +71,7 @@ struct Call {
   const R *times, *u, *q_mu, *q_prec, *p_mu, *p_prec, *clip_lo, *clip_hi, *extra, *treatments, *dev_1hot, *obs, *weights;
   const int* kind;
   R *theta, *x_states, *x_predict, *logp_species, *logp_theta, *logq_theta;
+  const R* theta_in;  // reverse only: the forward call's theta planes [P][N] (NULL: re-sample from u)
   // reverse only
   const R *g_logp_species, *g_logp_theta, *g_logq_theta, *g_theta, *g_x_states, *g_x_predict;
   R *d_q_mu, *d_q_prec, *d_extra, *d_weights;
@@ -330,14 +331,35 @@ VH_HD R sample_column(const Call<R>& a, int n, int b, int k, R& lq, R& lp, bool 
 // ROLLED over the P sampled columns (one copy of sample_column in the instruction stream instead of one per slot):
 // values land in a small per-thread array indexed by slot (local memory, L1-resident), from which the model's slot
 // registers are filled with constant indices.
+// Per-thread array indexed by a RUN-TIME slot number.  It must live in addressable memory (shared memory on the
+// device, element s of thread t at p[s * stride]): as a register array ptxas turned every dynamic access into a chain of
+// ~47 compare + predicated-move pairs, ~100 instructions per theta column (measured: the rolled prologue / epilogue
+// was 58 % of the reverse kernel's samples at the icml size).
+template <typename R>
+struct SlotScratch {
+  R* p;
+  int stride;
+  VH_HD R& operator[](int s) const { return p[s * stride]; }
+};
+
 template <class M, bool UNROLL = false>
 VH_HD void load_theta(const Call<typename M::real>& a, int n, int b, typename M::real* th, typename M::real& lq,
-                      typename M::real& lp, bool store = true) {
+                      typename M::real& lp, const SlotScratch<typename M::real>& loc, bool store = true) {
   typedef typename M::real R;
-  R loc[M::NSLOT];
   for (int s = 0; s < M::NSLOT; ++s) {
     const int src = a.slot_src[s];
     loc[s] = (src < 0 && src != VH_SLOT_UNUSED) ? a.extra[(size_t)(-1 - src) * a.N + n] : R(0);
+  }
+  if (a.theta_in) {  // reverse sweep with the forward's theta at hand: P coalesced loads instead of re-sampling
+#pragma unroll 5
+    for (int k = 0; k < a.P; ++k) {
+      const int s = a.col_slot[k];
+      const R v = a.theta_in[(size_t)k * a.N + n];
+      if (s >= 0) loc[s] = v;
+    }
+#pragma unroll
+    for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? loc[s] : R(0);
+    return;
   }
   // The columns are independent: partial unrolling lets the ~8 dependent-latency loads of several columns overlap.
   // Used by the reverse kernels, where at the icml size this prologue (run twice) and the matching epilogue had grown
@@ -376,10 +398,19 @@ VH_HD void column_vjp(const Call<R>& a, int n, int b, int k, R gth, R glq, R glp
   const R prec = a.q_prec[b * a.P + k];
   const R sigma = R(1) / vsqrt(prec);
   const R uu = a.u[(size_t)n * a.P + k];
-  const R sv = mu + sigma * uu;
-  const R raw = kind == VH_KIND_LOGNORMAL ? vexp(sv) : sv;
   const R lo = a.clip_lo[k], hi = a.clip_hi[k];
-  const R th = clampv(raw, lo, hi);
+  R raw, th;
+  bool have = false;
+  if (a.theta_in) {  // strictly inside the clip interval the clamp was the identity: raw == theta, no exp needed
+    th = a.theta_in[(size_t)k * a.N + n];
+    raw = th;
+    have = th > lo && th < hi;
+  }
+  if (!have) {
+    const R sv = mu + sigma * uu;
+    raw = kind == VH_KIND_LOGNORMAL ? vexp(sv) : sv;
+    th = clampv(raw, lo, hi);
+  }
   const R pm = a.p_mu[k], pp = a.p_prec[k];
   R x, gx_to_th;
   if (kind == VH_KIND_LOGNORMAL) {
@@ -406,7 +437,8 @@ VH_HD void column_vjp(const Call<R>& a, int n, int b, int k, R gth, R glq, R glp
 // and no exposed load latency.
 // ---------------------------------------------------------------------------------------------------------------
 template <class M, class TB>
-VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M::real* w) {
+VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M::real* w,
+                        const SlotScratch<typename M::real>& sc) {
   typedef typename M::real R;
   constexpr int S = M::S, NS = M::NS;
   const int b = n / a.IW;
@@ -419,7 +451,7 @@ VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M
   R lq = R(0), lp = R(0);
   {
     R th[M::NSLOT];
-    load_theta<M>(a, n, b, th, lq, lp);
+    load_theta<M>(a, n, b, th, lq, lp, sc);
     R c6, c12;
     M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
     M::setup(th, c6, c12, f.c);
@@ -494,7 +526,8 @@ VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M
 // cotangents.
 // ---------------------------------------------------------------------------------------------------------------
 template <class M, class TB, typename GW, typename RED>
-VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, const typename M::real* w, GW& gw, RED& red) {
+VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, const typename M::real* w, GW& gw, RED& red,
+                         const SlotScratch<typename M::real>& sc) {
   typedef typename M::real R;
   constexpr int S = M::S, NS = M::NS;
   const int b = n / a.IW;
@@ -511,7 +544,7 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
     {
       R th[M::NSLOT];
       R lq = R(0), lp = R(0), c6, c12;
-      load_theta<M, true>(a, n, b, th, lq, lp, false);  // never rewrite theta in the reverse pass
+      load_theta<M, true>(a, n, b, th, lq, lp, sc, false);  // never rewrite theta in the reverse pass
       M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
       M::setup(th, c6, c12, f.c);
 #pragma unroll
@@ -599,7 +632,7 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
     // chain rule back to theta: re-derive theta (cheap) rather than keep it live across the loop
     R th[M::NSLOT];
     R lq = R(0), lp = R(0), c6, c12;
-    load_theta<M, true>(a, n, b, th, lq, lp, false);
+    load_theta<M, true>(a, n, b, th, lq, lp, sc, false);
     M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
     M::init_state_vjp(lam, gth);
     M::setup_vjp(th, c6, c12, f.c, gc, gth);
@@ -610,7 +643,7 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
   }
   // scatter slot cotangents: sampled columns -> (d q_mu, d q_prec); extras -> d_extra.  Rolled over the columns
   // (one copy of column_vjp + the segmented warp reduction), reading the slot cotangents from a per-thread array.
-  R gloc[M::NSLOT];
+  const SlotScratch<R>& gloc = sc;
 #pragma unroll
   for (int s = 0; s < M::NSLOT; ++s) gloc[s] = M::uses(s) ? gth[s] : R(0);
 #pragma unroll 5

@@ -146,7 +146,7 @@ class FusedElboTerms(torch.autograd.Function):
                          logp_theta=_ptr(lp), logq_theta=_ptr(lq))
         L.check(prob.lib.vh_elbo_terms_fwd(C.byref(p), C.byref(io), _stream()))
         ctx.prob, ctx.dims = prob, (B, IW, T, P, N)
-        ctx.save_for_backward(q_mu, q_prec, u, extra, weights, times, treatments, dev_1hot, observations, x_states)
+        ctx.save_for_backward(q_mu, q_prec, u, extra, weights, times, treatments, dev_1hot, observations, x_states, theta)
         ctx.set_materialize_grads(False)
         if x_predict is None:
             x_predict = torch.empty(0, dtype=dt, device=dev)
@@ -157,7 +157,7 @@ class FusedElboTerms(torch.autograd.Function):
     def backward(ctx, g_lpx, g_lp, g_lq, g_theta, g_xs, g_xp):
         prob = ctx.prob
         B, IW, T, P, N = ctx.dims
-        q_mu, q_prec, u, extra, weights, times, treatments, dev_1hot, observations, x_states = ctx.saved_tensors
+        q_mu, q_prec, u, extra, weights, times, treatments, dev_1hot, observations, x_states, theta = ctx.saved_tensors
         dt, dev = prob.dtype, q_mu.device
         g_lpx, g_lp, g_lq = _c(g_lpx, dt), _c(g_lp, dt), _c(g_lq, dt)
         g_theta, g_xs = _c(g_theta, dt), _c(g_xs, dt)
@@ -170,7 +170,8 @@ class FusedElboTerms(torch.autograd.Function):
         fio = L.vh_fwd_io(times=_ptr(times), u=_ptr(u), q_mu=_ptr(q_mu), q_prec=_ptr(q_prec), p_mu=_ptr(prob.p_mu),
                           p_prec=_ptr(prob.p_prec), clip_lo=_ptr(prob.clip_lo), clip_hi=_ptr(prob.clip_hi),
                           kind=_ptr(prob.kind), extra=_ptr(extra), treatments=_ptr(treatments), dev_1hot=_ptr(dev_1hot),
-                          observations=_ptr(observations), weights=_ptr(weights), x_states=_ptr(x_states))
+                          observations=_ptr(observations), weights=_ptr(weights), x_states=_ptr(x_states),
+                          theta=_ptr(theta))
         bio = L.vh_bwd_io(fwd=fio, g_logp_by_species=_ptr(g_lpx), g_logp_theta=_ptr(g_lp), g_logq_theta=_ptr(g_lq),
                           g_theta=_ptr(g_theta), g_x_states=_ptr(g_xs), g_x_predict=_ptr(g_xp), d_q_mu=_ptr(d_mu),
                           d_q_prec=_ptr(d_prec), d_extra=_ptr(d_extra), d_weights=_ptr(d_w))

@@ -232,7 +232,6 @@ class GraphedStep(object):
         self._bio = L.vh_bwd_io(fwd=self._fio, g_logp_by_species=_ptr(b.g_lpx), g_logp_theta=_ptr(b.g_lp),
                                 g_logq_theta=_ptr(b.g_lq), d_q_mu=_ptr(b.d_q_mu), d_q_prec=_ptr(b.d_q_prec),
                                 d_extra=_ptr(self.d_extra), d_weights=_ptr(self.d_weights))
-        self._bio.fwd.theta = None
         vdt = self.prob.vh_dtype
         self._iwae_fwd_args = (vdt, self.B, self.IW, self.b_total, _ptr(b.lpx), _ptr(b.lp), _ptr(b.lq), _ptr(b.cost),
                                _ptr(b.log_w), _ptr(b.w))
