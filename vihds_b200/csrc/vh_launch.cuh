@@ -78,6 +78,55 @@ template <class M>
 struct BwdBounds {
   static constexpr int min_blocks = (sizeof(typename M::real) == 4 && !M::DYN && !M::RELAY) ? 3 : 1;
 };
+// Latency-bound launches (fewer warps than schedulers): FWD_TEAM warps share one group of 32 trajectories for the
+// sample / clip / log-prob prologue -- warp r takes theta columns r, r + FWD_TEAM, ... and leaves values (by slot) and
+// its partial log q / log p in shared memory -- then warp 0 integrates alone.  Column k of slot s is written only by
+// the warp that owns column k, slots without a column only by the warp that owns slot s (build_call guarantees one
+// column per slot), so the prologue needs a single barrier.  fp32 / fp64, constant-precision models.
+#ifndef VH_FWD_TEAM
+#define VH_FWD_TEAM 4
+#endif
+constexpr int FWD_TEAM = VH_FWD_TEAM;
+template <class M, class TB>
+__global__ void __launch_bounds__(FWD_TEAM * 32) elbo_fwd_team_kernel(const Call<typename M::real> a) {
+  typedef typename M::real R;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  R* sm = reinterpret_cast<R*>(smem_raw);
+  const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * 32 + lane;
+  const bool active = n0 < a.N;
+  const int n = active ? n0 : a.N - 1;
+  const int b = n / a.IW;
+  const SlotScratch<R> loc{sm + lane, 32};
+  R* part = sm + M::NSLOT * 32;  // [2][FWD_TEAM][32]
+  for (int s = role; s < M::NSLOT; s += FWD_TEAM) {
+    const int src = a.slot_src[s];
+    if (src < 0) loc[s] = src != VH_SLOT_UNUSED ? a.extra[(size_t)(-1 - src) * a.N + n] : R(0);
+  }
+  R lq = R(0), lp = R(0);
+#pragma unroll 3
+  for (int k = role; k < a.P; k += FWD_TEAM) {
+    const R v = sample_column(a, n, b, k, lq, lp, active);
+    const int s = a.col_slot[k];
+    if (s >= 0) loc[s] = v;
+  }
+  part[role * 32 + lane] = lq;
+  part[(FWD_TEAM + role) * 32 + lane] = lp;
+  __syncthreads();
+  if (role != 0 || !active) return;
+  lq = R(0);
+  lp = R(0);
+#pragma unroll
+  for (int r = 0; r < FWD_TEAM; ++r) {
+    lq += part[r * 32 + lane];
+    lp += part[(FWD_TEAM + r) * 32 + lane];
+  }
+  R th[M::NSLOT];
+#pragma unroll
+  for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? loc[s] : R(0);
+  traj_forward_from<M, TB>(a, n, nullptr, th, lq, lp);
+}
+
 template <class M, class TB>
 __global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel(const Call<typename M::real> a) {
   typedef typename M::real R;
@@ -163,8 +212,19 @@ struct WsRing {
   }
 };
 
+// WS_WARPS warps per CTA share one group of 32 trajectories: warp 0 = producer, warp 1 = consumer, the others sleep on
+// a named barrier until the lambda recurrence is finished and then take their share of the theta columns of the
+// chain-rule epilogue (35 columns x ~260 instructions were 42 % of the consumer warp's time when it did them alone).
+#ifndef VH_WS_WARPS
+#define VH_WS_WARPS 4
+#endif
+constexpr int WS_WARPS = VH_WS_WARPS;
+__device__ __forceinline__ void named_bar_sync_all(int id) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(WS_WARPS * 32) : "memory");
+}
+
 template <class M, class TB>
-__global__ void __launch_bounds__(64) elbo_bwd_ws_kernel(const Call<typename M::real> a) {
+__global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<typename M::real> a) {
   typedef typename M::real R;
   typedef WsRing<M, TB> Ring;
   constexpr int S = M::S;
@@ -173,156 +233,159 @@ __global__ void __launch_bounds__(64) elbo_bwd_ws_kernel(const Call<typename M::
   const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * 32 + lane;
   const bool active = n0 < a.N;
-  const int n = active ? n0 : a.N - 1;  // every lane runs (the named barriers count 64 threads)
+  const int n = active ? n0 : a.N - 1;  // every lane runs (the named barriers count whole warps)
   const int b = n / a.IW;
   const size_t N = a.N;
   const int T = a.T;
-  enum { FULL0 = 1, EMPTY0 = 3 };
-  const SlotScratch<R> sc{ring + 2 * Ring::SLOT + threadIdx.x, 64};
-  // both roles need the RHS constants
-  Rhs<M> f;
-  f.w = nullptr;
-  R prec[4], iprec[4];
-  {
-    R th[M::NSLOT];
-    R lq = R(0), lp = R(0), c6, c12;
-    load_theta<M, true>(a, n, b, th, lq, lp, sc, false);
-    M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
-    M::setup(th, c6, c12, f.c);
+  enum { FULL0 = 1, EMPTY0 = 3, EPILOGUE = 5 };
+  const SlotScratch<R> sc{ring + 2 * Ring::SLOT + (role & 1) * 32 + lane, 64};  // producer / consumer columns
+  const SlotScratch<R> gloc{ring + 2 * Ring::SLOT + 32 + lane, 64};            // the consumer's, read by every warp
+  const R glq = (a.g_logq_theta && active) ? a.g_logq_theta[n] : R(0);
+  const R glp = (a.g_logp_theta && active) ? a.g_logp_theta[n] : R(0);
+  if (role < 2) {
+    // both roles need the RHS constants
+    Rhs<M> f;
+    f.w = nullptr;
+    R prec[4], iprec[4];
+    {
+      R th[M::NSLOT];
+      R lq = R(0), lp = R(0), c6, c12;
+      load_theta<M, true>(a, n, b, th, lq, lp, sc, false);
+      M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
+      M::setup(th, c6, c12, f.c);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        prec[o] = th[S_prec_x + o];
+        iprec[o] = R(1) / prec[o];
+      }
+    }
+    const R h0 = a.times[1] - a.times[0];
+    const size_t slab = (size_t)S * N;
+    if (role == 0) {
+      // ---------------- producer: checkpoints + stage re-evaluation, one step ahead ----------------
+      const R* xs = a.x_states + (size_t)(T - 2) * slab + n;
+      R x[S], xn[S];
+#pragma unroll
+      for (int q = 0; q < S; ++q) x[q] = xs[(size_t)q * N];
+      R t1 = a.times[T - 1], t0 = a.times[T - 2];
+      for (int k = T - 2; k >= 0; --k) {
+        const int it = T - 2 - k, slot = it & 1;
+        const int kp = k > 0 ? k - 1 : 0;
+        if (k > 0) xs -= slab;
+#pragma unroll
+        for (int q = 0; q < S; ++q) xn[q] = xs[(size_t)q * N];  // next checkpoint, consumed next iteration
+        const R tp = ld_early(a.times + kp);
+        typename Ring::SD sd;
+        rk_stages_forward<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd);
+        if (it >= 2) named_bar_sync(EMPTY0 + slot);  // the consumer has released this slot
+        Ring::put(ring + slot * Ring::SLOT, lane, x, sd);
+        __threadfence_block();
+        named_bar_arrive(FULL0 + slot);
+#pragma unroll
+        for (int q = 0; q < S; ++q) x[q] = xn[q];
+        t1 = t0;
+        t0 = tp;
+      }
+    } else {
+    // ---------------- consumer: everything that is serial in lambda ----------------
+    R gl[4], gprec[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
-      prec[o] = th[S_prec_x + o];
-      iprec[o] = R(1) / prec[o];
+      gprec[o] = R(0);
+      gl[o] = (a.g_logp_species && active) ? a.g_logp_species[(size_t)n * 4 + o] : R(0);
     }
-  }
-  const R h0 = a.times[1] - a.times[0];
-  const size_t slab = (size_t)S * N;
-  if (role == 0) {
-    // ---------------- producer: checkpoints + stage re-evaluation, one step ahead ----------------
-    const R* xs = a.x_states + (size_t)(T - 2) * slab + n;
-    R x[S], xn[S];
+    const R* obs = a.obs ? a.obs + (size_t)b * 4 * T : nullptr;
+    const R* gxs = a.g_x_states ? a.g_x_states + (size_t)(T - 1) * slab + n : nullptr;
+    const R* gxpr = a.g_x_predict ? a.g_x_predict + (size_t)(T - 1) * 4 * N + n : nullptr;
+    typename M::Consts gc;
 #pragma unroll
-    for (int q = 0; q < S; ++q) x[q] = xs[(size_t)q * N];
-    R t1 = a.times[T - 1], t0 = a.times[T - 2];
-    for (int k = T - 2; k >= 0; --k) {
-      const int it = T - 2 - k, slot = it & 1;
+    for (int i = 0; i < M::NC; ++i) gc.v[i] = R(0);
+    NoGW<R> nogw;
+    R lam[S], x[S];
+    R ob[4] = {R(0), R(0), R(0), R(0)}, obp[4] = {R(0), R(0), R(0), R(0)};
+#pragma unroll
+    for (int q = 0; q < S; ++q) {
+      lam[q] = R(0);
+      x[q] = a.x_states[(size_t)(T - 1) * slab + (size_t)q * N + n];
+    }
+    if (obs) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) ob[o] = obs[o * T + T - 1];
+    }
+    R t1 = a.times[T - 1], t0 = t1;
+    for (int k = T - 1; k >= 0; --k) {
       const int kp = k > 0 ? k - 1 : 0;
-      if (k > 0) xs -= slab;
+      if (obs) {
 #pragma unroll
-      for (int q = 0; q < S; ++q) xn[q] = xs[(size_t)q * N];  // next checkpoint, consumed next iteration
+        for (int o = 0; o < 4; ++o) obp[o] = ld_early(obs + o * T + kp);
+      }
       const R tp = ld_early(a.times + kp);
-      typename Ring::SD sd;
-      rk_stages_forward<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd);
-      if (it >= 2) named_bar_sync(EMPTY0 + slot);  // the consumer has released this slot
-      Ring::put(ring + slot * Ring::SLOT, lane, x, sd);
-      __threadfence_block();
-      named_bar_arrive(FULL0 + slot);
+      if (k + 1 < T) {
+        const int it = T - 2 - k, slot = it & 1;
+        typename Ring::SD sd;
+        named_bar_sync(FULL0 + slot);
+        Ring::get(ring + slot * Ring::SLOT, lane, x, sd);
+        if (k >= 2) {  // slot will be refilled with step k-2; the last two fills are never waited for
+          __threadfence_block();
+          named_bar_arrive(EMPTY0 + slot);
+        }
+        rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd, lam, gc, nogw);
+      }
+      // emission at time k
+      R xp[4], gxp[4];
+      M::observe(x, xp);
 #pragma unroll
-      for (int q = 0; q < S; ++q) x[q] = xn[q];
+      for (int o = 0; o < 4; ++o) {
+        gxp[o] = (gxpr && active) ? gxpr[(size_t)o * N] : R(0);
+        if (obs) {
+          const R d = xp[o] - ob[o];
+          gxp[o] -= gl[o] * prec[o] * d;
+          gprec[o] += gl[o] * R(0.5) * (iprec[o] - d * d);
+        }
+      }
+      M::observe_vjp(x, gxp, lam);
+      if (gxs) {
+        if (active) {
+#pragma unroll
+          for (int q = 0; q < S; ++q) lam[q] += gxs[(size_t)q * N];
+        }
+        gxs -= slab;
+      }
+      if (gxpr) gxpr -= (size_t)4 * N;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) ob[o] = obp[o];
       t1 = t0;
       t0 = tp;
     }
-    return;
-  }
-  // ---------------- consumer: everything that is serial in lambda ----------------
-  R gl[4], gprec[4];
+    // chain rule back to theta + scatter (as traj_backward)
+    R gth[M::NSLOT];
 #pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    gprec[o] = R(0);
-    gl[o] = (a.g_logp_species && active) ? a.g_logp_species[(size_t)n * 4 + o] : R(0);
-  }
-  const R glq = (a.g_logq_theta && active) ? a.g_logq_theta[n] : R(0);
-  const R glp = (a.g_logp_theta && active) ? a.g_logp_theta[n] : R(0);
-  const R* obs = a.obs ? a.obs + (size_t)b * 4 * T : nullptr;
-  const R* gxs = a.g_x_states ? a.g_x_states + (size_t)(T - 1) * slab + n : nullptr;
-  const R* gxpr = a.g_x_predict ? a.g_x_predict + (size_t)(T - 1) * 4 * N + n : nullptr;
-  typename M::Consts gc;
+    for (int s = 0; s < M::NSLOT; ++s) gth[s] = R(0);
+    {
+      R th[M::NSLOT];
+      R lq = R(0), lp = R(0), c6, c12;
+      load_theta<M, true>(a, n, b, th, lq, lp, sc, false);
+      M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
+      M::init_state_vjp(lam, gth);
+      M::setup_vjp(th, c6, c12, f.c, gc, gth);
 #pragma unroll
-  for (int i = 0; i < M::NC; ++i) gc.v[i] = R(0);
-  NoGW<R> nogw;
-  R lam[S], x[S];
-  R ob[4] = {R(0), R(0), R(0), R(0)}, obp[4] = {R(0), R(0), R(0), R(0)};
-#pragma unroll
-  for (int q = 0; q < S; ++q) {
-    lam[q] = R(0);
-    x[q] = a.x_states[(size_t)(T - 1) * slab + (size_t)q * N + n];
-  }
-  if (obs) {
-#pragma unroll
-    for (int o = 0; o < 4; ++o) ob[o] = obs[o * T + T - 1];
-  }
-  R t1 = a.times[T - 1], t0 = t1;
-  for (int k = T - 1; k >= 0; --k) {
-    const int kp = k > 0 ? k - 1 : 0;
-    if (obs) {
-#pragma unroll
-      for (int o = 0; o < 4; ++o) obp[o] = ld_early(obs + o * T + kp);
+      for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gprec[o];
     }
-    const R tp = ld_early(a.times + kp);
-    if (k + 1 < T) {
-      const int it = T - 2 - k, slot = it & 1;
-      typename Ring::SD sd;
-      named_bar_sync(FULL0 + slot);
-      Ring::get(ring + slot * Ring::SLOT, lane, x, sd);
-      if (k >= 2) {  // slot will be refilled with step k-2; the last two fills are never waited for
-        __threadfence_block();
-        named_bar_arrive(EMPTY0 + slot);
-      }
-      rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd, lam, gc, nogw);
-    }
-    // emission at time k
-    R xp[4], gxp[4];
-    M::observe(x, xp);
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      gxp[o] = (gxpr && active) ? gxpr[(size_t)o * N] : R(0);
-      if (obs) {
-        const R d = xp[o] - ob[o];
-        gxp[o] -= gl[o] * prec[o] * d;
-        gprec[o] += gl[o] * R(0.5) * (iprec[o] - d * d);
-      }
-    }
-    M::observe_vjp(x, gxp, lam);
-    if (gxs) {
-      if (active) {
-#pragma unroll
-        for (int q = 0; q < S; ++q) lam[q] += gxs[(size_t)q * N];
-      }
-      gxs -= slab;
-    }
-    if (gxpr) gxpr -= (size_t)4 * N;
-#pragma unroll
-    for (int o = 0; o < 4; ++o) ob[o] = obp[o];
-    t1 = t0;
-    t0 = tp;
-  }
-  // chain rule back to theta + scatter (as traj_backward)
-  R gth[M::NSLOT];
-#pragma unroll
-  for (int s = 0; s < M::NSLOT; ++s) gth[s] = R(0);
-  {
-    R th[M::NSLOT];
-    R lq = R(0), lp = R(0), c6, c12;
-    load_theta<M, true>(a, n, b, th, lq, lp, sc, false);
-    M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
-    M::init_state_vjp(lam, gth);
-    M::setup_vjp(th, c6, c12, f.c, gc, gth);
-#pragma unroll
-    for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gprec[o];
-  }
+    for (int s = 0; s < M::NSLOT; ++s) gloc[s] = M::uses(s) ? gth[s] : R(0);
+    }  // consumer
+  }    // producer / consumer
+  named_bar_sync_all(EPILOGUE);  // gloc is complete (bar.sync orders the shared-memory writes)
   WarpSegRed<R> red(a.d_q_mu, a.d_q_prec, a.P, b, active);
-  const SlotScratch<R>& gloc = sc;
-#pragma unroll
-  for (int s = 0; s < M::NSLOT; ++s) gloc[s] = M::uses(s) ? gth[s] : R(0);
-#pragma unroll 5
-  for (int k = 0; k < a.P; ++k) {
+#pragma unroll 3
+  for (int k = role; k < a.P; k += WS_WARPS) {
     const int s = a.col_slot[k];
     R dmu = R(0), dprec = R(0);
     if (active) column_vjp(a, n, b, k, s >= 0 ? gloc[s] : R(0), glq, glp, dmu, dprec);
     red(b, k, dmu, dprec, active);
   }
   if (a.d_extra && active) {
-    for (int s = 0; s < M::NSLOT; ++s) {
+    for (int s = role; s < M::NSLOT; s += WS_WARPS) {
       const int src = a.slot_src[s];
       if (src < 0 && src != VH_SLOT_UNUSED) a.d_extra[(size_t)(-1 - src) * N + n] = gloc[s];
     }
@@ -340,13 +403,29 @@ template <typename R>
 struct FwdLauncher {
   Call<R> a;
   cudaStream_t stream;
+  // VIHDS_FWD_TEAM=0|1 overrides (tests / measurements)
+  template <class M>
+  static bool use_team(int block) {
+    static const int mode = [] {
+      const char* m = getenv("VIHDS_FWD_TEAM");
+      return !m ? -1 : atoi(m);
+    }();
+    if (M::DYN) return false;
+    return mode >= 0 ? mode != 0 : block == 32;
+  }
   template <class M, class TB>
   int run() {
     const int block = pick_block(a.N);
     const int grid = (a.N + block - 1) / block;
     const size_t smem = sizeof(R) * (((NetInfo<M>::NW + 3) & ~3) + (size_t)M::NSLOT * block);  // weights | slot scratch
-    if (smem > 48 * 1024) cudaFuncSetAttribute(elbo_fwd_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    elbo_fwd_kernel<M, TB><<<grid, block, smem, stream>>>(a);
+    if (use_team<M>(block)) {
+      const size_t tsm = sizeof(R) * ((size_t)M::NSLOT * 32 + 2 * FWD_TEAM * 32);  // slot values | partial log-probs
+      elbo_fwd_team_kernel<M, TB><<<(a.N + 31) / 32, FWD_TEAM * 32, tsm, stream>>>(a);
+    } else {
+      if (smem > 48 * 1024)
+        cudaFuncSetAttribute(elbo_fwd_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      elbo_fwd_kernel<M, TB><<<grid, block, smem, stream>>>(a);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
       set_error("elbo_fwd_kernel launch failed: %s", cudaGetErrorString(e));
@@ -375,7 +454,9 @@ struct BwdLauncher {
   void launch_bwd_variant(bool ws, int grid, int block, size_t smem) {
     if (ws) {
       const size_t ring = sizeof(R) * (2 * WsRing<M, TB>::SLOT + (size_t)M::NSLOT * 64);  // ring | slot scratch
-      elbo_bwd_ws_kernel<M, TB><<<(a.N + 31) / 32, 64, ring, stream>>>(a);
+      if (ring > 48 * 1024)
+        cudaFuncSetAttribute(elbo_bwd_ws_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
+      elbo_bwd_ws_kernel<M, TB><<<(a.N + 31) / 32, WS_WARPS * 32, ring, stream>>>(a);
     } else {
       elbo_bwd_kernel<M, TB><<<grid, block, smem, stream>>>(a);
     }

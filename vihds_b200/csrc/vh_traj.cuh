@@ -436,9 +436,10 @@ VH_HD void column_vjp(const Call<R>& a, int n, int b, int k, R gth, R glq, R glp
 // step's observations / grid time are fetched one iteration ahead, so the loop carries no 64-bit index arithmetic
 // and no exposed load latency.
 // ---------------------------------------------------------------------------------------------------------------
+// th: the model's slot values (sampled, clipped); lq / lp: log q(theta), log p(theta) of this trajectory
 template <class M, class TB>
-VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M::real* w,
-                        const SlotScratch<typename M::real>& sc) {
+VH_HD void traj_forward_from(const Call<typename M::real>& a, int n, const typename M::real* w,
+                             const typename M::real* th, typename M::real lq, typename M::real lp) {
   typedef typename M::real R;
   constexpr int S = M::S, NS = M::NS;
   const int b = n / a.IW;
@@ -448,10 +449,7 @@ VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M
   f.w = w;
   R x[S];
   R prec[4], lprec[4], ll[4];
-  R lq = R(0), lp = R(0);
   {
-    R th[M::NSLOT];
-    load_theta<M>(a, n, b, th, lq, lp, sc);
     R c6, c12;
     M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
     M::setup(th, c6, c12, f.c);
@@ -515,6 +513,16 @@ VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M
   }
   if (a.logp_theta) a.logp_theta[n] = lp;
   if (a.logq_theta) a.logq_theta[n] = lq;
+}
+
+template <class M, class TB>
+VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M::real* w,
+                        const SlotScratch<typename M::real>& sc) {
+  typedef typename M::real R;
+  R th[M::NSLOT];
+  R lq = R(0), lp = R(0);
+  load_theta<M>(a, n, n / a.IW, th, lq, lp, sc);
+  traj_forward_from<M, TB>(a, n, w, th, lq, lp);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
