@@ -173,6 +173,19 @@ __global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel
 __device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
 
+constexpr int WS_PF = 4;  // checkpoint prefetch distance of the producer warp (time steps)
+__device__ __forceinline__ void cp_async_elem(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(double* dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NN>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(NN) : "memory");
+}
+
 template <class M, class TB>
 struct WsRing {
   typedef typename M::real R;
@@ -263,17 +276,35 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
     const size_t slab = (size_t)S * N;
     if (role == 0) {
       // ---------------- producer: checkpoints + stage re-evaluation, one step ahead ----------------
+      // Checkpoints x_k come through a cp.async staging ring WS_PF steps ahead: with a one-step register prefetch
+      // the producer sat 58 % of its time on the long scoreboard (one warp per scheduler cannot hide an L2 / HBM
+      // round trip behind ~190 instructions) and the consumer, in turn, 46 % of its loop on the FULL barrier.
+      // Each thread reads back only what it copied itself, so cp.async.wait_group is all the synchronisation needed.
+      R* ck = ring + 2 * Ring::SLOT + M::NSLOT * 64 + lane;  // [WS_PF + 1][S][32]
       const R* xs = a.x_states + (size_t)(T - 2) * slab + n;
-      R x[S], xn[S];
+      int kw = T - 2, sw = 0, sr = 0;  // step / ring slot of the next copy, ring slot of the next read
+      auto issue = [&]() {
+        if (kw >= 0) {
 #pragma unroll
-      for (int q = 0; q < S; ++q) x[q] = xs[(size_t)q * N];
+          for (int q = 0; q < S; ++q) cp_async_elem(ck + (sw * S + q) * 32, xs + (size_t)q * N);
+          xs -= slab;
+        }
+        cp_async_commit();
+        --kw;
+        sw = sw == WS_PF ? 0 : sw + 1;
+      };
+#pragma unroll
+      for (int d = 0; d < WS_PF; ++d) issue();
+      R x[S];
       R t1 = a.times[T - 1], t0 = a.times[T - 2];
       for (int k = T - 2; k >= 0; --k) {
         const int it = T - 2 - k, slot = it & 1;
         const int kp = k > 0 ? k - 1 : 0;
-        if (k > 0) xs -= slab;
+        issue();  // refills the slot that was read one iteration ago
+        cp_async_wait<WS_PF>();
 #pragma unroll
-        for (int q = 0; q < S; ++q) xn[q] = xs[(size_t)q * N];  // next checkpoint, consumed next iteration
+        for (int q = 0; q < S; ++q) x[q] = ck[(sr * S + q) * 32];
+        sr = sr == WS_PF ? 0 : sr + 1;
         const R tp = ld_early(a.times + kp);
         typename Ring::SD sd;
         rk_stages_forward<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd);
@@ -281,8 +312,6 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
         Ring::put(ring + slot * Ring::SLOT, lane, x, sd);
         __threadfence_block();
         named_bar_arrive(FULL0 + slot);
-#pragma unroll
-        for (int q = 0; q < S; ++q) x[q] = xn[q];
         t1 = t0;
         t0 = tp;
       }
@@ -453,7 +482,8 @@ struct BwdLauncher {
   template <class M, class TB>
   void launch_bwd_variant(bool ws, int grid, int block, size_t smem) {
     if (ws) {
-      const size_t ring = sizeof(R) * (2 * WsRing<M, TB>::SLOT + (size_t)M::NSLOT * 64);  // ring | slot scratch
+      // hand-off ring | slot scratch | checkpoint staging ring
+      const size_t ring = sizeof(R) * (2 * WsRing<M, TB>::SLOT + (size_t)M::NSLOT * 64 + (size_t)(WS_PF + 1) * M::S * 32);
       if (ring > 48 * 1024)
         cudaFuncSetAttribute(elbo_bwd_ws_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
       elbo_bwd_ws_kernel<M, TB><<<(a.N + 31) / 32, WS_WARPS * 32, ring, stream>>>(a);
