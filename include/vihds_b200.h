@@ -172,6 +172,13 @@ int vh_iwae_fwd(int dtype, int B, int IW, int b_total, const void* logp_by_speci
 int vh_iwae_bwd(int dtype, int B, int IW, int b_total, const void* w, const void* g, void* g_logp_by_species,
                 void* g_logp_theta, void* g_logq_theta, void* stream);
 
+/* The training step's pair in ONE launch: vh_iwae_fwd followed by vh_iwae_bwd with g = 1 (elbo.backward() of
+ * vihds/training.py:334 starts from a unit upstream gradient).  Same outputs; log_w, w and any of the three gradient
+ * arrays may be NULL. */
+int vh_iwae_fwd_bwd(int dtype, int B, int IW, int b_total, const void* logp_by_species, const void* logp_theta,
+                    const void* logq_theta, void* cost, void* log_w, void* w, void* g_logp_by_species,
+                    void* g_logp_theta, void* g_logq_theta, void* stream);
+
 /* Evaluation path (vihds/utils.py:79-99, Results.init): importance-weighted moments of the traces, reduced over IW
  * on the device so the [B,IW,.,T] traces never leave HBM.
  *   iw_predict_mu [B][4][T], iw_predict_std [B][4][T], iw_states [B][S][T], iw_variance [B][4][T]
@@ -184,10 +191,12 @@ int vh_iw_moments(const vh_problem* p, const void* w, const void* x_states, cons
 int vh_adam_step(int dtype, size_t n, void* param, const void* grad, void* exp_avg, void* exp_avg_sq, double lr,
                  double beta1, double beta2, double eps, int step, void* stream);
 /* Same update with the hyper-parameters and the step counter ON THE DEVICE, so that the launch can be captured in a
- * CUDA graph and replayed: hyper = double[4] {lr, beta1, beta2, eps}; step = int64[1], the number of updates done so
- * far (the call uses step+1 for the bias correction and then increments it). */
-int vh_adam_step_dev(int dtype, size_t n, void* param, const void* grad, void* exp_avg, void* exp_avg_sq,
-                     const void* hyper, void* step, void* stream);
+ * CUDA graph and replayed: hyper = double[4] {lr, beta1, beta2, eps}; step = int64[2]: step[0] = the number of updates
+ * done so far (the call uses step[0]+1 for the bias correction and increments it when its last thread block retires),
+ * step[1] = scratch ticket counter, zero on entry and on exit.  zero_grad != 0: grad is cleared once it has been
+ * consumed (optimizer.zero_grad() of the next step, training.py:333, without a launch of its own). */
+int vh_adam_step_dev(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq, const void* hyper,
+                     void* step, int zero_grad, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Fused amortised encoder q(theta | x, d) (vihds/encoders.py:16-55 ConditionalEncoder, :126-253 Q_Local / Q_Global_Cond

@@ -47,7 +47,8 @@ struct BwdRunner {
       StridedGW<R> h{gw.data(), 1};
       std::vector<R> scratch(M::NSLOT);
       SlotScratch<R> sc{scratch.data(), 1};
-      traj_backward<M, TB>(*a, n, true, a->weights, h, red, sc);
+      DirectCk<R, M::S> ck;
+      traj_backward<M, TB>(*a, n, true, a->weights, h, red, sc, ck);
       for (size_t i = 0; i < nw; ++i) a->d_weights[i] += gw[i];
     }
     return 0;

@@ -239,3 +239,52 @@ def test_iwae_kernel_edges():
     cost = torch.zeros(1, device="cuda")
     L.check(lib.vh_iwae_fwd(0, 1, 4, 1, _p(lpx), _p(z), _p(z), _p(cost), None, None, None))
     assert float(cost) == float("inf")
+
+
+def test_iwae_fused_matches_the_two_launches():
+    """vh_iwae_fwd_bwd (one launch, the training step's entry) against vh_iwae_fwd + vh_iwae_bwd with g = 1: fp32 and
+    fp64, IW below / above the block size, outputs overwritten (not accumulated), NaN contract."""
+    lib = L.load()
+    for vdt, dt in ((0, torch.float32), (1, torch.float64)):
+        for B, IW in ((1, 1), (3, 1000), (36, 200), (70, 33)):
+            g = torch.Generator().manual_seed(B * 1000 + IW)
+            lpx = (torch.randn(B * IW, 4, generator=g, dtype=dt) * 50).cuda()
+            lp, lq = (torch.randn(B * IW, generator=g, dtype=dt) * 10).cuda(), (torch.randn(B * IW, generator=g, dtype=dt) * 10).cuda()
+            z = lambda *s: torch.full(s, 7.0, device="cuda", dtype=dt)  # noqa: E731  (outputs must be overwritten)
+            c0, lw0, w0, g0 = z(1), z(B * IW), z(B * IW), (z(B * IW, 4), z(B * IW), z(B * IW))
+            c1, lw1, w1, g1 = z(1), z(B * IW), z(B * IW), (z(B * IW, 4), z(B * IW), z(B * IW))
+            L.check(lib.vh_iwae_fwd(vdt, B, IW, B + 1, _p(lpx), _p(lp), _p(lq), _p(c0), _p(lw0), _p(w0), None))
+            L.check(lib.vh_iwae_bwd(vdt, B, IW, B + 1, _p(w0), None, _p(g0[0]), _p(g0[1]), _p(g0[2]), None))
+            L.check(lib.vh_iwae_fwd_bwd(vdt, B, IW, B + 1, _p(lpx), _p(lp), _p(lq), _p(c1), _p(lw1), _p(w1), _p(g1[0]),
+                                        _p(g1[1]), _p(g1[2]), None))
+            tol = 1e-5 if dt == torch.float32 else 1e-12
+            assert abs(float(c0) - float(c1)) <= tol * abs(float(c0)), (B, IW, float(c0), float(c1))
+            assert torch.equal(lw0, lw1)
+            for a_, b_ in ((w0, w1), (g0[0], g1[0]), (g0[1], g1[1]), (g0[2], g1[2])):
+                assert torch.allclose(a_, b_, rtol=tol * 10, atol=1e-30), (B, IW)
+    lpx = torch.zeros(8, 4, device="cuda")
+    lpx[5, 2] = float("nan")
+    zz, cost = torch.zeros(8, device="cuda"), torch.zeros(1, device="cuda")
+    L.check(lib.vh_iwae_fwd_bwd(0, 2, 4, 2, _p(lpx), _p(zz), _p(zz), _p(cost), None, None, None, None, None, None))
+    assert np.isnan(float(cost))
+
+
+def test_adam_dev_counts_steps_and_clears_the_gradient():
+    """vh_adam_step_dev: same update as vh_adam_step, the device-side step counter advances by one per call (bumped by
+    the last thread block, ticket scratch back to zero) and zero_grad clears the consumed gradient."""
+    lib = L.load()
+    for n in (1, 255, 256, 100003):
+        g = torch.Generator().manual_seed(n)
+        p0 = torch.randn(n, generator=g).cuda()
+        pa, pb = p0.clone(), p0.clone()
+        ma, va, mb, vb = (torch.zeros(n, device="cuda") for _ in range(4))
+        hyper = torch.tensor([0.01, 0.9, 0.999, 1e-8], dtype=torch.float64, device="cuda")
+        step = torch.zeros(2, dtype=torch.int64, device="cuda")
+        for it in range(1, 4):
+            gr = torch.randn(n, generator=g).cuda()
+            ga = gr.clone()
+            L.check(lib.vh_adam_step_dev(0, n, _p(pa), _p(ga), _p(ma), _p(va), _p(hyper), _p(step), it % 2, None))
+            L.check(lib.vh_adam_step(0, n, _p(pb), _p(gr), _p(mb), _p(vb), 0.01, 0.9, 0.999, 1e-8, it, None))
+            assert step.tolist() == [it, 0]
+            assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-7)
+            assert torch.equal(ga, torch.zeros_like(ga) if it % 2 else gr)

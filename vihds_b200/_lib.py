@@ -93,7 +93,8 @@ def load():
     lib.vh_iw_moments.argtypes = [C.POINTER(vh_problem)] + [C.c_void_p] * 9
     lib.vh_adam_step.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                  C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
-    lib.vh_adam_step_dev.argtypes = [C.c_int, C.c_size_t] + [C.c_void_p] * 7
+    lib.vh_adam_step_dev.argtypes = [C.c_int, C.c_size_t] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+    lib.vh_iwae_fwd_bwd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 10
     lib.vh_device_conditioner.argtypes = [C.c_int] * 5 + [C.c_void_p] * 6
     lib.vh_encoder_fwd.argtypes = [C.POINTER(vh_encoder_desc), C.POINTER(vh_encoder_io), C.c_void_p]
     lib.vh_encoder_bwd.argtypes = [C.POINTER(vh_encoder_desc), C.POINTER(vh_encoder_io), C.POINTER(vh_encoder_grads), C.c_void_p]

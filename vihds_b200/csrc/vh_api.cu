@@ -68,7 +68,7 @@ __device__ R block_reduce(R v, bool is_max, R* sh) {
 
 template <typename R>
 __global__ void iwae_fwd_kernel(int IW, R inv_b_total, const R* __restrict__ lpx, const R* __restrict__ lp,
-                                const R* __restrict__ lq, R* cost, R* log_w, R* w) {
+                                const R* __restrict__ lq, R* cost, R* log_w, R* w, R* g_lpx, R* g_lp, R* g_lq) {
   __shared__ R sh[32];
   const int b = blockIdx.x;
   const R NEG = -INFINITY;
@@ -93,11 +93,20 @@ __global__ void iwae_fwd_kernel(int IW, R inv_b_total, const R* __restrict__ lpx
   se = block_reduce(se, false, sh);
   R lse = vlog(se) + shift;
   if (nanflag > R(0)) lse = NAN;  // NaN contract: an ELBO term that is NaN must surface in the cost (training.py:331)
-  if (w) {
+  if (w || g_lpx || g_lp || g_lq) {
+    // normalised importance weights and (vh_iwae_fwd_bwd) the gradient of the cost for a unit upstream gradient
     for (int i = threadIdx.x; i < IW; i += blockDim.x) {
       const size_t n = (size_t)b * IW + i;
       const R v = ((lpx[n * 4 + 0] + lpx[n * 4 + 1]) + (lpx[n * 4 + 2] + lpx[n * 4 + 3])) + lp[n] - lq[n];
-      w[n] = vexp(v - lse);
+      const R wn = vexp(v - lse);
+      if (w) w[n] = wn;
+      const R g = -wn * inv_b_total;
+      if (g_lpx) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) g_lpx[n * 4 + o] = g;
+      }
+      if (g_lp) g_lp[n] = g;
+      if (g_lq) g_lq[n] = -g;
     }
   }
   if (threadIdx.x == 0) atomicAdd(cost, -(lse - vlog(R(IW))) * inv_b_total);
@@ -185,24 +194,37 @@ __global__ void adam_kernel(size_t n, R* __restrict__ p, const R* __restrict__ g
   p[i] -= (lr / bc1) * (mi / denom);
 }
 
-// graph-capturable variant: hyper-parameters and step counter are read from device memory
+// graph-capturable variant: hyper-parameters and step counter are read from device memory.  step[0] = updates done so
+// far, step[1] = ticket counter: every CTA reads step[0] before it takes a ticket, the last one bumps the counter
+// (no separate increment launch).  zero_grad: the gradient is cleared once consumed (no separate fill launch).
 template <typename R>
-__global__ void adam_dev_kernel(size_t n, R* __restrict__ p, const R* __restrict__ g, R* __restrict__ m, R* __restrict__ v,
-                                const double* __restrict__ hyper, const long long* __restrict__ step) {
+__global__ void adam_dev_kernel(size_t n, R* __restrict__ p, R* __restrict__ g, R* __restrict__ m, R* __restrict__ v,
+                                const double* __restrict__ hyper, long long* step, int zero_grad) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const double t = (double)(step[0] + 1);
-  const double lr = hyper[0], b1d = hyper[1], b2d = hyper[2];
-  const R b1 = (R)b1d, b2 = (R)b2d, eps = (R)hyper[3];
-  const R bc1 = (R)(1.0 - pow(b1d, t));
-  const R bc2_sqrt = (R)sqrt(1.0 - pow(b2d, t));
-  const R gi = g[i];
-  const R mi = m[i] + (gi - m[i]) * (R(1) - b1);
-  const R vi = b2 * v[i] + (R(1) - b2) * gi * gi;
-  m[i] = mi;
-  v[i] = vi;
-  const R denom = vsqrt(vi) / bc2_sqrt + eps;
-  p[i] -= ((R)lr / bc1) * (mi / denom);
+  const double t = (double)(*(volatile long long*)step + 1);
+  if (i < n) {
+    const double lr = hyper[0], b1d = hyper[1], b2d = hyper[2];
+    const R b1 = (R)b1d, b2 = (R)b2d, eps = (R)hyper[3];
+    const R bc1 = (R)(1.0 - pow(b1d, t));
+    const R bc2_sqrt = (R)sqrt(1.0 - pow(b2d, t));
+    const R gi = g[i];
+    const R mi = m[i] + (gi - m[i]) * (R(1) - b1);
+    const R vi = b2 * v[i] + (R(1) - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const R denom = vsqrt(vi) / bc2_sqrt + eps;
+    p[i] -= ((R)lr / bc1) * (mi / denom);
+    if (zero_grad) g[i] = R(0);
+  }
+  __syncthreads();  // every thread of this CTA has read step[0]
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd((unsigned long long*)(step + 1), 1ULL);
+    if (ticket == (unsigned long long)gridDim.x - 1) {
+      step[1] = 0;
+      step[0] += 1;
+    }
+  }
 }
 __global__ void step_inc_kernel(long long* step) { step[0] += 1; }
 
@@ -348,10 +370,10 @@ int vh_simulate_bwd(const vh_problem* p, const vh_bwd_io* io, void* stream) {
   return run_bwd(p, io, stream);
 }
 
-int vh_iwae_fwd(int dtype, int B, int IW, int b_total, const void* lpx, const void* lp, const void* lq, void* cost,
-                void* log_w, void* w, void* stream) {
+static int iwae_fwd_launch(const char* who, int dtype, int B, int IW, int b_total, const void* lpx, const void* lp,
+                           const void* lq, void* cost, void* log_w, void* w, void* g_lpx, void* g_lp, void* g_lq, void* stream) {
   if (B <= 0 || IW <= 0 || b_total <= 0 || !lpx || !lp || !lq || !cost) {
-    set_error("vh_iwae_fwd: bad arguments");
+    set_error("%s: bad arguments", who);
     return VH_ERR_INVALID;
   }
   cudaStream_t s = (cudaStream_t)stream;
@@ -359,16 +381,28 @@ int vh_iwae_fwd(int dtype, int B, int IW, int b_total, const void* lpx, const vo
   if (dtype == VH_F32) {
     cudaMemsetAsync(cost, 0, sizeof(float), s);
     iwae_fwd_kernel<float><<<B, block, 0, s>>>(IW, 1.0f / (float)b_total, (const float*)lpx, (const float*)lp,
-                                                (const float*)lq, (float*)cost, (float*)log_w, (float*)w);
+                                                (const float*)lq, (float*)cost, (float*)log_w, (float*)w, (float*)g_lpx,
+                                                (float*)g_lp, (float*)g_lq);
   } else if (dtype == VH_F64) {
     cudaMemsetAsync(cost, 0, sizeof(double), s);
     iwae_fwd_kernel<double><<<B, block, 0, s>>>(IW, 1.0 / (double)b_total, (const double*)lpx, (const double*)lp,
-                                                 (const double*)lq, (double*)cost, (double*)log_w, (double*)w);
+                                                 (const double*)lq, (double*)cost, (double*)log_w, (double*)w, (double*)g_lpx,
+                                                 (double*)g_lp, (double*)g_lq);
   } else {
     set_error("unknown dtype %d", dtype);
     return VH_ERR_INVALID;
   }
   return check_launch("iwae_fwd_kernel");
+}
+
+int vh_iwae_fwd(int dtype, int B, int IW, int b_total, const void* lpx, const void* lp, const void* lq, void* cost,
+                void* log_w, void* w, void* stream) {
+  return iwae_fwd_launch("vh_iwae_fwd", dtype, B, IW, b_total, lpx, lp, lq, cost, log_w, w, nullptr, nullptr, nullptr, stream);
+}
+
+int vh_iwae_fwd_bwd(int dtype, int B, int IW, int b_total, const void* lpx, const void* lp, const void* lq, void* cost,
+                    void* log_w, void* w, void* g_lpx, void* g_lp, void* g_lq, void* stream) {
+  return iwae_fwd_launch("vh_iwae_fwd_bwd", dtype, B, IW, b_total, lpx, lp, lq, cost, log_w, w, g_lpx, g_lp, g_lq, stream);
 }
 
 int vh_iwae_bwd(int dtype, int B, int IW, int b_total, const void* w, const void* g, void* g_lpx, void* g_lp, void* g_lq,
@@ -447,28 +481,29 @@ int vh_adam_step(int dtype, size_t n, void* param, const void* grad, void* exp_a
   return check_launch("adam_kernel");
 }
 
-int vh_adam_step_dev(int dtype, size_t n, void* param, const void* grad, void* exp_avg, void* exp_avg_sq, const void* hyper,
-                     void* step, void* stream) {
+int vh_adam_step_dev(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq, const void* hyper,
+                     void* step, int zero_grad, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper || !step) {
     set_error("vh_adam_step_dev: bad arguments");
     return VH_ERR_INVALID;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  if (n > 0) {
-    const int block = 256;
-    const unsigned grid = (unsigned)((n + block - 1) / block);
-    if (dtype == VH_F32)
-      adam_dev_kernel<float><<<grid, block, 0, s>>>(n, (float*)param, (const float*)grad, (float*)exp_avg, (float*)exp_avg_sq,
-                                                     (const double*)hyper, (const long long*)step);
-    else if (dtype == VH_F64)
-      adam_dev_kernel<double><<<grid, block, 0, s>>>(n, (double*)param, (const double*)grad, (double*)exp_avg,
-                                                      (double*)exp_avg_sq, (const double*)hyper, (const long long*)step);
-    else {
-      set_error("unknown dtype %d", dtype);
-      return VH_ERR_INVALID;
-    }
+  if (n == 0) {
+    step_inc_kernel<<<1, 1, 0, s>>>((long long*)step);
+    return check_launch("step_inc_kernel");
   }
-  step_inc_kernel<<<1, 1, 0, s>>>((long long*)step);
+  const int block = 256;
+  const unsigned grid = (unsigned)((n + block - 1) / block);
+  if (dtype == VH_F32)
+    adam_dev_kernel<float><<<grid, block, 0, s>>>(n, (float*)param, (float*)grad, (float*)exp_avg, (float*)exp_avg_sq,
+                                                   (const double*)hyper, (long long*)step, zero_grad);
+  else if (dtype == VH_F64)
+    adam_dev_kernel<double><<<grid, block, 0, s>>>(n, (double*)param, (double*)grad, (double*)exp_avg, (double*)exp_avg_sq,
+                                                    (const double*)hyper, (long long*)step, zero_grad);
+  else {
+    set_error("unknown dtype %d", dtype);
+    return VH_ERR_INVALID;
+  }
   return check_launch("adam_dev_kernel");
 }
 

@@ -72,6 +72,20 @@ __global__ void __launch_bounds__(128) elbo_fwd_kernel(const Call<typename M::re
   if (n < a.N) traj_forward<M, TB>(a, n, w, sc);
 }
 
+constexpr int WS_PF = 4;  // checkpoint prefetch distance of the producer warp (time steps)
+__device__ __forceinline__ void cp_async_elem(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(double* dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int NN>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(NN) : "memory");
+}
+
+
 // 3 resident CTAs of 128 threads per SM (<= 168 registers) for the fp32 8-species models: measured faster than 2 CTAs
 // at 190 registers and than 4 CTAs with spills; the wider models keep the full register file.
 template <class M>
@@ -146,7 +160,8 @@ __global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel
   const SlotScratch<R> sc{w + ((NW * ((int)blockDim.x + 1) + 3) & ~3) + threadIdx.x, (int)blockDim.x};
   if (M::DYN) {
     StridedGW<R> h{gw + threadIdx.x, (int)blockDim.x};
-    traj_backward<M, TB>(a, nn, active, w, h, red, sc);
+    DirectCk<R, M::S> ck;
+    traj_backward<M, TB>(a, nn, active, w, h, red, sc, ck);
     __syncthreads();
     for (int k = threadIdx.x; k < NW; k += blockDim.x) {
       R s = R(0);
@@ -155,7 +170,10 @@ __global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel
     }
   } else {
     NoGW<R> nogw;
-    traj_backward<M, TB>(a, nn, active, w, nogw, red, sc);
+    // (a cp.async staging ring as in the warp-specialised kernel was measured here too: 1.340 vs 1.306 ms at
+    // N = 131,072 -- with 12 resident warps per SM the one-step register prefetch already hides the latency)
+    DirectCk<R, M::S> ck;
+    traj_backward<M, TB>(a, nn, active, w, nogw, red, sc, ck);
   }
 }
 
@@ -172,19 +190,6 @@ __global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
-
-constexpr int WS_PF = 4;  // checkpoint prefetch distance of the producer warp (time steps)
-__device__ __forceinline__ void cp_async_elem(float* dst, const float* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_elem(double* dst, const double* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int NN>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(NN) : "memory");
-}
 
 template <class M, class TB>
 struct WsRing {
@@ -508,8 +513,13 @@ struct BwdLauncher {
       }
     }
     if (a.d_q_mu && a.P > 0) {
-      cudaMemsetAsync(a.d_q_mu, 0, sizeof(R) * (size_t)a.B * a.P, stream);
-      cudaMemsetAsync(a.d_q_prec, 0, sizeof(R) * (size_t)a.B * a.P, stream);
+      const size_t nq = (size_t)a.B * a.P;
+      if (a.d_q_prec == a.d_q_mu + nq) {  // adjacent tables: one memset node
+        cudaMemsetAsync(a.d_q_mu, 0, sizeof(R) * 2 * nq, stream);
+      } else {
+        cudaMemsetAsync(a.d_q_mu, 0, sizeof(R) * nq, stream);
+        cudaMemsetAsync(a.d_q_prec, 0, sizeof(R) * nq, stream);
+      }
     }
     if (NW > 0) cudaMemsetAsync(a.d_weights, 0, sizeof(R) * NW, stream);
     launch_bwd_variant<M, TB>(ws, grid, block, smem);

@@ -533,9 +533,36 @@ VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M
 // alive across it; the loop itself carries x, the prefetched previous checkpoint, lambda, the constants and their
 // cotangents.
 // ---------------------------------------------------------------------------------------------------------------
-template <class M, class TB, typename GW, typename RED>
+// Source of the checkpoints x_k for the reverse sweep, newest first: plain loads, register-prefetched one step ahead.
+// (The warp-specialised kernel has its own source: a cp.async ring in shared memory, vh_launch.cuh.)
+template <typename R, int S>
+struct DirectCk {
+  const R* xs;
+  size_t N;
+  int k;
+  R nx[S];
+  VH_HD void start(const R* x_states, int n, size_t N_, int T) {
+    N = N_;
+    k = T - 1;
+    xs = x_states + (size_t)k * S * N + n;
+#pragma unroll
+    for (int q = 0; q < S; ++q) nx[q] = xs[(size_t)q * N];
+  }
+  VH_HD void next(R* x) {
+#pragma unroll
+    for (int q = 0; q < S; ++q) x[q] = nx[q];
+    if (k > 0) {
+      xs -= (size_t)S * N;
+#pragma unroll
+      for (int q = 0; q < S; ++q) nx[q] = xs[(size_t)q * N];
+    }
+    --k;
+  }
+};
+
+template <class M, class TB, typename GW, typename RED, typename CKS>
 VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, const typename M::real* w, GW& gw, RED& red,
-                         const SlotScratch<typename M::real>& sc) {
+                         const SlotScratch<typename M::real>& sc, CKS& ck) {
   typedef typename M::real R;
   constexpr int S = M::S, NS = M::NS;
   const int b = n / a.IW;
@@ -575,30 +602,22 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
     const R h0 = a.times[1] - a.times[0];
     const R* obs = a.obs ? a.obs + (size_t)b * 4 * T : nullptr;
     const size_t slab = (size_t)S * N;
-    const R* xs = a.x_states + (size_t)(T - 1) * slab + n;             // checkpoint at time k
     const R* gxs = a.g_x_states ? a.g_x_states + (size_t)(T - 1) * slab + n : nullptr;
     const R* gxpr = a.g_x_predict ? a.g_x_predict + (size_t)(T - 1) * 4 * N + n : nullptr;
-    R lam[S], x[S], xprev[S];
+    R lam[S], x[S];
     R ob[4] = {R(0), R(0), R(0), R(0)}, obp[4] = {R(0), R(0), R(0), R(0)};
 #pragma unroll
-    for (int q = 0; q < S; ++q) {
-      lam[q] = R(0);
-      x[q] = xs[(size_t)q * N];
-      xprev[q] = x[q];
-    }
+    for (int q = 0; q < S; ++q) lam[q] = R(0);
+    ck.start(a.x_states, n, N, T);
     if (obs) {
 #pragma unroll
       for (int o = 0; o < 4; ++o) ob[o] = obs[o * T + T - 1];
     }
     R t0 = a.times[T - 1], t1 = t0;  // interval [t0, t1] = [times[k], times[k+1]]; unused at k = T-1
     for (int k = T - 1; k >= 0; --k) {
-      // prefetch what iteration k-1 consumes while this step's adjoint is computed
+      // checkpoint x_k (and the fetch of what later iterations consume while this step's adjoint is computed)
       const int kp = k > 0 ? k - 1 : 0;
-      if (k > 0) {
-        xs -= slab;
-#pragma unroll
-        for (int q = 0; q < S; ++q) xprev[q] = xs[(size_t)q * N];
-      }
+      ck.next(x);
       if (obs) {
 #pragma unroll
         for (int o = 0; o < 4; ++o) obp[o] = ld_early(obs + o * T + kp);
@@ -630,8 +649,6 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
         gxs -= slab;
       }
       if (gxpr) gxpr -= (size_t)4 * N;
-#pragma unroll
-      for (int q = 0; q < S; ++q) x[q] = xprev[q];
 #pragma unroll
       for (int o = 0; o < 4; ++o) ob[o] = obp[o];
       t1 = t0;

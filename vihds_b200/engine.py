@@ -286,7 +286,7 @@ class FlatAdam(object):
         self.params = params
         self.betas, self.eps = betas, eps
         self.hyper = torch.tensor([lr, betas[0], betas[1], eps], dtype=torch.float64, device=dev)
-        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.step_dev = torch.zeros(2, dtype=torch.int64, device=dev)  # [updates done, ticket scratch]
         self.vdt = L.VH_F64 if dt == torch.float64 else L.VH_F32
         self.lr = lr
 
@@ -297,6 +297,8 @@ class FlatAdam(object):
     def zero_grad(self):
         self.grad.zero_()
 
-    def step(self):
+    def step(self, zero_grad=False):
+        """zero_grad: clear the gradient vector in the same launch (it is consumed exactly once)."""
         L.check(L.load().vh_adam_step_dev(self.vdt, self.flat.numel(), _ptr(self.flat), _ptr(self.grad), _ptr(self.exp_avg),
-                                          _ptr(self.exp_avg_sq), _ptr(self.hyper), _ptr(self.step_dev), _stream()))
+                                          _ptr(self.exp_avg_sq), _ptr(self.hyper), _ptr(self.step_dev), int(zero_grad),
+                                          _stream()))

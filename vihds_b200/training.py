@@ -179,7 +179,8 @@ class GraphedStep(object):
         S = self.prob.S
         N = self.N
         self.buf = Settings(theta=z(P, N), x_states=z(T, S, N), lpx=z(N, 4), lp=z(N), lq=z(N), cost=z(1), log_w=z(N), w=z(N),
-                            g_lpx=z(N, 4), g_lp=z(N), g_lq=z(N), d_q_mu=z(B, P), d_q_prec=z(B, P))
+                            g_lpx=z(N, 4), g_lp=z(N), g_lq=z(N), d_q=z(2, B, P))
+        self.buf.d_q_mu, self.buf.d_q_prec = self.buf.d_q[0], self.buf.d_q[1]  # adjacent: cleared by one memset
         self.d_weights = z(self.prob.n_weights) if self.prob.n_weights else None
         self.d_extra = z(len(self.extras), N) if (self.extras and hasattr(ode, "offset_layer")) else None
         self.ready = False
@@ -192,6 +193,18 @@ class GraphedStep(object):
         static buffers; otherwise stock PyTorch (captured either way)."""
         enc, ode = self.model.encoder, self.model.decoder.ode_model
         lib, s = self.prob.lib, _stream()
+        # the device conditioner does not depend on the encoder: it runs on a forked branch (a parallel node of the
+        # captured graph) and joins before the ODE kernel
+        fork = bool(self.extras) and getattr(self, "extras_override", None) is None and not hasattr(ode, "offset_layer")
+        if fork:
+            cur = torch.cuda.current_stream()
+            if not hasattr(self, "_side"):
+                self._side = torch.cuda.Stream()
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                L.check(lib.vh_device_conditioner(self.prob.vh_dtype, self.B, self.IW, self.cond_w.shape[1], len(self.extras),
+                                                  _ptr(self.batch.dev_1hot), _ptr(self.rel_mat), _ptr(self.cond_w),
+                                                  _ptr(self.plus_one), _ptr(self.extra_static), _stream()))
         if self.fused_encoder:
             pr = enc.fused_parameters()
             self._enc_io = L.vh_encoder_io(
@@ -210,9 +223,7 @@ class GraphedStep(object):
             self.extra = ode.conditioned_extras(self.B, self.IW, self.batch.dev_1hot)  # trainable: gradient flows back
             self.extra_grad = True
         elif self.extras:
-            L.check(lib.vh_device_conditioner(self.prob.vh_dtype, self.B, self.IW, self.cond_w.shape[1], len(self.extras),
-                                              _ptr(self.batch.dev_1hot), _ptr(self.rel_mat), _ptr(self.cond_w),
-                                              _ptr(self.plus_one), _ptr(self.extra_static), s))
+            cur.wait_stream(self._side)
             self.extra = self.extra_static
         else:
             self.extra = None
@@ -233,17 +244,15 @@ class GraphedStep(object):
                                 g_logq_theta=_ptr(b.g_lq), d_q_mu=_ptr(b.d_q_mu), d_q_prec=_ptr(b.d_q_prec),
                                 d_extra=_ptr(self.d_extra), d_weights=_ptr(self.d_weights))
         vdt = self.prob.vh_dtype
-        self._iwae_fwd_args = (vdt, self.B, self.IW, self.b_total, _ptr(b.lpx), _ptr(b.lp), _ptr(b.lq), _ptr(b.cost),
-                               _ptr(b.log_w), _ptr(b.w))
-        self._iwae_bwd_args = (vdt, self.B, self.IW, self.b_total, _ptr(b.w), None, _ptr(b.g_lpx), _ptr(b.g_lp), _ptr(b.g_lq))
+        self._iwae_args = (vdt, self.B, self.IW, self.b_total, _ptr(b.lpx), _ptr(b.lp), _ptr(b.lq), _ptr(b.cost),
+                           _ptr(b.log_w), _ptr(b.w), _ptr(b.g_lpx), _ptr(b.g_lp), _ptr(b.g_lq))
         self._p_ref, self._fio_ref, self._bio_ref = C.byref(self._p), C.byref(self._fio), C.byref(self._bio)
 
     def _hot(self):
-        """The hot path: four launches of libvihds_b200.so on the current stream (arguments pre-built)."""
+        """The hot path: three launches of libvihds_b200.so on the current stream (arguments pre-built)."""
         lib, s = self.prob.lib, _stream()
         L.check(lib.vh_elbo_terms_fwd(self._p_ref, self._fio_ref, s))
-        L.check(lib.vh_iwae_fwd(*self._iwae_fwd_args, s))
-        L.check(lib.vh_iwae_bwd(*self._iwae_bwd_args, s))
+        L.check(lib.vh_iwae_fwd_bwd(*self._iwae_args, s))
         if self.ev_hot is not None:
             self.ev_hot[0].record()
         L.check(lib.vh_elbo_terms_bwd(self._p_ref, self._bio_ref, s))
@@ -252,8 +261,7 @@ class GraphedStep(object):
 
     def _post(self):
         """encoder backward, ONE gradient all-reduce, fused Adam (captured)."""
-        opt = self.tr.optimizer
-        opt.zero_grad()
+        opt = self.tr.optimizer  # its gradient vector is clean here: prepare() cleared it once, every step clears it again
         outs, grads = [], []
         if self.fused_encoder:
             g = [p.grad for p in self.model.encoder.fused_parameters()]
@@ -273,13 +281,14 @@ class GraphedStep(object):
             torch.autograd.backward(outs, grads)
         if self.pg is not None:
             torch.distributed.all_reduce(opt.grad, group=self.pg)
-        opt.step()
+        opt.step(zero_grad=True)
 
     # -- capture / replay ---------------------------------------------------------------------------------------
     def prepare(self):
         """Warm up eagerly on a side stream, then capture the pre and post segments."""
         if self.ready:
             return
+        self.tr.optimizer.zero_grad()
         if not self.use_graphs:
             self.ready = True
             return
