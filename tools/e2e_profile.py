@@ -28,8 +28,7 @@ for _ in range(n):
     gs.draw_conditioner(); t = tick("draw_conditioner", t)
     gs.load_u(u); t = tick("load_u", t)
     gs.g_pre.replay(); t = tick("g_pre.replay", t)
-    gs._hot(); t = tick("hot (4 ctypes launches)", t)
-    gs.g_post.replay(); t = tick("g_post.replay", t)
+    gs.g_rest.replay(); t = tick("g_rest.replay", t)
     cost_host.copy_(gs.buf.cost, non_blocking=True); t = tick("cost d2h enqueue", t)
     torch.cuda.synchronize(); t = tick("final sync (GPU tail)", t)
     acc["total"] = acc.get("total", 0.0) + (t - t_start)

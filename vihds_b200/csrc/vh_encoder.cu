@@ -25,6 +25,7 @@ struct EncDims {
   int lt, ld, gt, gd;       // conditioning flags (treatments / devices) of the local and global-conditioned groups
   int L1, NCV, NP, NLIN;    // T-1, conv outputs per filter, pooled outputs per filter, F*NP
   int nin_l, nin_g;
+  int stage;                // kernels copy their weights into shared memory up front (cp.async) -- see stage_async
 };
 
 template <typename R>
@@ -41,6 +42,37 @@ __device__ R warp_sum(R v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// Cold-cache latency is what these kernels pay for (the step runs them once, with the weights in HBM): every phase
+// that reads a weight array from global memory costs one or several dependent DRAM round trips (~0.8 us each; the
+// hidden layer alone needed ~11).  So each kernel starts by issuing cp.async copies of EVERYTHING it will read later
+// into shared memory -- one round trip, overlapped with the first phases -- and computes from there.
+__device__ __forceinline__ void cp_async_bytes(void* dst, const void* src, int bytes) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  if (bytes == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  else if (bytes == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+}
+// n contiguous elements; 16-byte copies when both ends are 16-byte aligned (dst always is: carve-up in multiples of 4)
+template <typename R>
+__device__ void stage_async(R* dst, const R* src, int n, int tid, int nt) {
+  if (n <= 0 || !src) return;
+  constexpr int V = 16 / sizeof(R);
+  if ((((size_t)src | (size_t)dst) & 15) == 0) {
+    const int nv = n / V;
+    for (int i = tid; i < nv; i += nt) cp_async_bytes(dst + i * V, src + i * V, 16);
+    for (int i = nv * V + tid; i < n; i += nt) cp_async_bytes(dst + i, src + i, sizeof(R));
+  } else {
+    for (int i = tid; i < n; i += nt) cp_async_bytes(dst + i, src + i, sizeof(R));
+  }
+}
+__host__ __device__ inline int up4(int n) { return (n + 3) & ~3; }
 
 // shared-memory carve-up (elements): delta [NS][L1] | conv scratch [F][NCV] | pooled [NLIN] | xloc [nin_l] | freev | conv w+b
 // Everything here is latency-bound (36 CTAs for the icml batch), so the loops that read weights from global memory
@@ -65,6 +97,22 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, c
   const int ngr = min(G, d.B - b0);
   const int ncw = d.F * d.NS * d.K;
   const int nfree = 2 * (d.nl + d.ng);
+  // staged copies (d.stage): hidden-layer weights + bias, head weights + biases
+  const R *lin_w = p.lin_w, *lin_b = p.lin_b, *local_w = p.local_w, *local_b = p.local_b, *gcond_w = p.gcond_w;
+  if (d.stage) {
+    R* st = delta + up4((int)(cw - delta) + ncw + d.F);  // 16-byte aligned
+    R* s_lin_w = st;
+    R* s_lin_b = s_lin_w + up4(d.H * d.NLIN);
+    R* s_local_w = s_lin_b + up4(d.H);
+    R* s_local_b = s_local_w + up4(2 * d.nl * d.nin_l);
+    R* s_gcond_w = s_local_b + up4(2 * d.nl);
+    stage_async(s_local_w, p.local_w, 2 * d.nl * d.nin_l, tid, nt);
+    stage_async(s_local_b, p.local_b, 2 * d.nl, tid, nt);
+    stage_async(s_gcond_w, p.gcond_w, 2 * d.ng * d.nin_g, tid, nt);
+    stage_async(s_lin_b, p.lin_b, d.H, tid, nt);
+    stage_async(s_lin_w, p.lin_w, d.H * d.NLIN, tid, nt);
+    lin_w = s_lin_w; lin_b = s_lin_b; local_w = s_local_w; local_b = s_local_b; gcond_w = s_gcond_w;
+  }
   for (int i = tid; i < ncw + d.F; i += nt) cw[i] = i < ncw ? p.conv_w[i] : p.conv_b[i - ncw];
   const R inv_pool = R(1) / R(d.PL);
   for (int g = 0; g < ngr; ++g) {
@@ -99,6 +147,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, c
       p.pooled[(size_t)b * d.NLIN + i] = a;
     }
   }
+  if (d.stage) cp_async_commit_wait_all();
   __syncthreads();
   // hidden layer: each warp owns outputs o0, o0 + nw, ... and accumulates ENC_OPW of them for all G individuals per
   // pass over the inputs
@@ -117,7 +166,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, c
       for (int q = 0; q < ENC_OPW; ++q) {
         const int o = o0 + q * nw;
         if (o < d.H) {
-          const R w = p.lin_w[(size_t)o * d.NLIN + i];
+          const R w = lin_w[(size_t)o * d.NLIN + i];
 #pragma unroll
           for (int g = 0; g < G; ++g) acc[q][g] += w * x[g];
         }
@@ -130,7 +179,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, c
       for (int g = 0; g < G; ++g) {
         const R a = warp_sum(acc[q][g]);
         if (lane == 0 && o < d.H && g < ngr) {
-          const R e = vtanh(a + p.lin_b[o]);
+          const R e = vtanh(a + lin_b[o]);
           xloc[g * d.nin_l + o] = e;
           p.enc[(size_t)(b0 + g) * d.H + o] = e;
         }
@@ -143,17 +192,17 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, c
     const int g = e / nfree, r = e % nfree, b = b0 + g;
     R a = R(0);
     if (r < 2 * d.nl) {
-      const R* w = p.local_w + (size_t)r * d.nin_l;
+      const R* w = local_w + (size_t)r * d.nin_l;
       for (int i = lane; i < d.nin_l; i += 32) a += w[i] * xloc[g * d.nin_l + i];
     } else {
-      const R* w = p.gcond_w + (size_t)(r - 2 * d.nl) * d.nin_g;
+      const R* w = gcond_w + (size_t)(r - 2 * d.nl) * d.nin_g;
       for (int i = lane; i < d.nin_g; i += 32) {
         const R x = (d.gt && i < d.C) ? p.inputs[(size_t)b * d.C + i] : p.dev[(size_t)b * d.D + (i - (d.gt ? d.C : 0))];
         a += w[i] * x;
       }
     }
     a = warp_sum(a);
-    if (lane == 0) freev[g * nfree + r] = a + (r < 2 * d.nl ? p.local_b[r] : R(0));
+    if (lane == 0) freev[g * nfree + r] = a + (r < 2 * d.nl ? local_b[r] : R(0));
   }
   __syncthreads();
   for (int e = tid; e < ngr * d.P; e += nt) {
@@ -190,6 +239,27 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const int b0 = blockIdx.x * G;
   const int ngr = min(G, d.B - b0);
+  // this CTA's filters: f = fy, fy + nfy, ...;  local filter index lf = f / nfy
+  const int fy = blockIdx.y, nfy = gridDim.y;
+  const int nfl = (d.F - fy + nfy - 1) / nfy;  // number of filters handled here
+  const int ncol = nfl * d.NP;                 // pooled columns handled here
+  // staged copies (d.stage, G == 1): this CTA's columns of the hidden-layer weights [H][ncol] and the local head weights
+  const R* local_w = p.local_w;
+  R* wl = delta + up4((int)(dpre - delta) + G * d.H);
+  if (d.stage) {
+    R* s_local_w = wl + up4(d.H * ncol);
+    for (int e = tid; e < d.H * ncol; e += nt) {
+      const int o = e / ncol, li = e % ncol;
+      cp_async_bytes(wl + e, p.lin_w + (size_t)o * d.NLIN + (fy + (li / d.NP) * nfy) * d.NP + li % d.NP, sizeof(R));
+    }
+    stage_async(s_local_w, p.local_w, 2 * d.nl * d.nin_l, tid, nt);
+    local_w = s_local_w;
+    const R* obs = p.obs + (size_t)b0 * d.NS * d.T;  // the only individual of this CTA
+    for (int i = tid; i < d.NS * d.L1; i += nt) {
+      const int c = i / d.L1, j = i % d.L1;
+      delta[i] = obs[c * d.T + j + 1] - obs[c * d.T + j];
+    }
+  }
   for (int e = tid; e < ngr * d.nin_l; e += nt) {
     const int g = e / d.nin_l, i = e % d.nin_l, b = b0 + g;
     R v;
@@ -206,6 +276,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
     dfree[g * nfr + 2 * k] = p.d_q_mu[(size_t)b * d.P + k];
     dfree[g * nfr + 2 * k + 1] = p.d_q_prec[(size_t)b * d.P + k] * p.q_prec[(size_t)b * d.P + k];  // d exp(log_prec)
   }
+  if (d.stage) cp_async_commit_wait_all();
   __syncthreads();
   // Small batches: gridDim.y CTAs share one individual, each taking the conv filters f = blockIdx.y (mod gridDim.y) and
   // their pooled columns -- the heavy phases below (dpool, dconv, conv weight gradients) need no exchange between
@@ -242,7 +313,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
     R gp = R(0);
     if (g < ngr) {
       R gg = R(0);
-      for (int r = 0; r < 2 * d.nl; ++r) gg += p.local_w[(size_t)r * d.nin_l + o] * dfree[g * nfr + r];
+      for (int r = 0; r < 2 * d.nl; ++r) gg += local_w[(size_t)r * d.nin_l + o] * dfree[g * nfr + r];
       const R en = xloc[g * d.nin_l + o];
       gp = gg * (R(1) - en * en);  // tanh'
       if (lead) p.d_pre[(size_t)(b0 + g) * d.H + o] = gp;
@@ -255,9 +326,6 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
     for (int g = 0; g < ngr; ++g) a += dpre[g * d.H + o];
     atomicAdd(p.g_lin_b + o, a);
   }
-  // this CTA's filters: f = fy, fy + nfy, ...;  local filter index lf = f / nfy
-  const int fy = blockIdx.y, nfy = gridDim.y;
-  const int nfl = (d.F - fy + nfy - 1) / nfy;  // number of filters handled here
   // cotangent of the pooled features: dpool[g][i] = sum_o W[o][i] dpre[g][o]   (each weight loaded once for G individuals)
   for (int li = tid; li < nfl * d.NP; li += nt) {
     const int i = (fy + (li / d.NP) * nfy) * d.NP + li % d.NP;
@@ -266,7 +334,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
     for (int g = 0; g < G; ++g) acc[g] = R(0);
 #pragma unroll 8
     for (int o = 0; o < d.H; ++o) {
-      const R w = p.lin_w[(size_t)o * d.NLIN + i];
+      const R w = d.stage ? wl[o * ncol + li] : p.lin_w[(size_t)o * d.NLIN + i];
 #pragma unroll
       for (int g = 0; g < G; ++g) acc[g] += w * dpre[g * d.H + o];
     }
@@ -277,7 +345,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
   for (int g = 0; g < ngr; ++g) {
     const R* obs = p.obs + (size_t)(b0 + g) * d.NS * d.T;
     __syncthreads();  // dpool complete / previous individual's delta + dconv consumed
-    for (int i = tid; i < d.NS * d.L1; i += nt) {
+    for (int i = tid; !d.stage && i < d.NS * d.L1; i += nt) {
       const int c = i / d.L1, j = i % d.L1;
       delta[i] = obs[c * d.T + j + 1] - obs[c * d.T + j];
     }
@@ -356,6 +424,7 @@ __global__ void __launch_bounds__(256) enc_lin_wgrad_small_kernel(const EncDims 
   const int o = e / d.NLIN, i = e % d.NLIN;
   R a0 = R(0), a1 = R(0);
   int b = 0;
+#pragma unroll 6  // 12 independent load pairs in flight: the B-deep sum is latency-, not throughput-bound
   for (; b + 1 < d.B; b += 2) {
     a0 += p.d_pre[(size_t)b * d.H + o] * p.pooled[(size_t)b * d.NLIN + i];
     a1 += p.d_pre[(size_t)(b + 1) * d.H + o] * p.pooled[(size_t)(b + 1) * d.NLIN + i];
@@ -392,6 +461,7 @@ static const char* fill_dims(const vh_encoder_desc* e, EncDims& d) {
   d.NLIN = d.F * d.NP;
   d.nin_l = d.H + (d.lt ? d.C : 0) + (d.ld ? d.D : 0);
   d.nin_g = (d.gt ? d.C : 0) + (d.gd ? d.D : 0);
+  d.stage = 0;
   if (d.B <= 0 || d.NP <= 0 || d.H <= 0) return "encoder: B, n_hidden must be positive and T long enough for the conv + pool";
   if (d.ng > 0 && d.nin_g == 0) return "encoder: global-conditioned parameters need a conditioning input";
   return nullptr;
@@ -414,16 +484,21 @@ static void fill_ptrs(const vh_encoder_io* io, const vh_encoder_grads* g, EncPtr
 
 template <typename R, int G>
 static void enc_fwd_g(const EncDims& d, const EncPtrs<R>& p, cudaStream_t s) {
-  const size_t smem = sizeof(R) * ((size_t)d.NS * d.L1 + (size_t)d.F * d.NCV + (size_t)G * d.NLIN + G * d.nin_l +
-                                   G * 2 * (d.nl + d.ng) + (size_t)d.F * d.NS * d.K + d.F + 8);
+  size_t smem = sizeof(R) * ((size_t)d.NS * d.L1 + (size_t)d.F * d.NCV + (size_t)G * d.NLIN + G * d.nin_l +
+                             G * 2 * (d.nl + d.ng) + (size_t)up4(d.F * d.NS * d.K + d.F) + 8);
+  // stage the weights in shared memory when they fit (fp32 at the icml size: 144 KB of hidden-layer weights)
+  const size_t staged = sizeof(R) * ((size_t)up4(d.H * d.NLIN) + up4(d.H) + up4(2 * d.nl * d.nin_l) + up4(2 * d.nl) +
+                                     up4(2 * d.ng * d.nin_g) + 8);
+  EncDims dd = d;
+  dd.stage = (G == 1 && smem + staged <= 220 * 1024) ? 1 : 0;
+  if (dd.stage) smem += staged;
   if (smem > 48 * 1024) cudaFuncSetAttribute(enc_fwd_kernel<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  enc_fwd_kernel<R, G><<<(d.B + G - 1) / G, ENC_THREADS, smem, s>>>(d, p);
+  enc_fwd_kernel<R, G><<<(d.B + G - 1) / G, ENC_THREADS, smem, s>>>(dd, p);
 }
 template <typename R, int G>
 static void enc_bwd_g(const EncDims& d, const EncPtrs<R>& p, cudaStream_t s) {
-  const size_t smem = sizeof(R) * ((size_t)d.NS * d.L1 + (size_t)d.F * d.NCV + (size_t)G * d.NLIN + G * d.nin_l +
-                                   G * 2 * (d.nl + d.ng + d.nglob) + G * d.H + 8);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(enc_bwd_kernel<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t smem = sizeof(R) * ((size_t)d.NS * d.L1 + (size_t)d.F * d.NCV + (size_t)G * d.NLIN + G * d.nin_l +
+                             G * 2 * (d.nl + d.ng + d.nglob) + G * d.H + 8);
   // small batches: split every individual over up to 5 CTAs by conv filter so that the latency-bound phases spread over
   // more SMs (36 individuals -> 180 CTAs)
   int fsplit = 1;
@@ -433,8 +508,15 @@ static void enc_bwd_g(const EncDims& d, const EncPtrs<R>& p, cudaStream_t s) {
     if (fsplit > d.F) fsplit = d.F;
     if (fsplit < 1) fsplit = 1;
   }
+  // stage this CTA's share of the weights in shared memory when it fits
+  const int nfl_max = (d.F + fsplit - 1) / fsplit;
+  const size_t staged = sizeof(R) * ((size_t)up4(d.H * nfl_max * d.NP) + up4(2 * d.nl * d.nin_l) + 8);
+  EncDims dd = d;
+  dd.stage = (G == 1 && smem + staged <= 200 * 1024) ? 1 : 0;
+  if (dd.stage) smem += staged;
+  if (smem > 48 * 1024) cudaFuncSetAttribute(enc_bwd_kernel<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((d.B + G - 1) / G, fsplit);
-  enc_bwd_kernel<R, G><<<grid, ENC_THREADS, smem, s>>>(d, p);
+  enc_bwd_kernel<R, G><<<grid, ENC_THREADS, smem, s>>>(dd, p);
 }
 // individuals per CTA: 1 while the batch does not fill the machine anyway, 4 for large batches (if it fits shared memory)
 template <typename R>

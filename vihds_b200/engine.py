@@ -271,7 +271,8 @@ class FlatAdam(object):
         assert params, "no trainable parameters"
         dev, dt = params[0].device, params[0].dtype
         _need_cuda(*params)
-        n = sum(p.numel() for p in params)
+        pad4 = lambda k: (k + 3) & ~3  # noqa: E731  every view starts 16-byte aligned (vectorised / cp.async copies)
+        n = sum(pad4(p.numel()) for p in params)
         self.flat = torch.zeros(n, dtype=dt, device=dev)
         self.grad = torch.zeros(n, dtype=dt, device=dev)
         self.exp_avg, self.exp_avg_sq = torch.zeros_like(self.flat), torch.zeros_like(self.flat)
@@ -282,7 +283,7 @@ class FlatAdam(object):
                 self.flat[off:off + k].copy_(p.reshape(-1))
                 p.data = self.flat[off:off + k].view_as(p)
                 p.grad = self.grad[off:off + k].view_as(p)
-                off += k
+                off += pad4(k)
         self.params = params
         self.betas, self.eps = betas, eps
         self.hyper = torch.tensor([lr, betas[0], betas[1], eps], dtype=torch.float64, device=dev)

@@ -8,10 +8,10 @@ Two equivalent ways to take a step:
 
 * ``Training._run_batch(batch)``   eager, reference-shaped: ``model(batch, IW)`` -> ``cost`` -> ``backward`` -> Adam.
   Every arithmetic op of the hot path is a launch of libvihds_b200.so through engine.* autograd Functions.
-* ``GraphedStep``                  the production form: static device buffers, the encoder forward and the encoder
-  backward + gradient all-reduce + Adam captured as two CUDA graphs, with the four hot-path launches (fused forward,
-  IWAE forward / backward, fused reverse sweep) issued between them through pre-built C-ABI descriptors on the same
-  stream -- no allocation, no Python tensor work and ~4 ctypes calls per step.
+* ``GraphedStep``                  the production form: static device buffers and pre-built C-ABI descriptors, the
+  whole step captured as two CUDA graphs -- encoder forward + device conditioner | fused forward, IWAE cost + gradient,
+  fused reverse sweep, encoder backward, gradient all-reduce, Adam -- so a step costs the host two graph launches (the
+  end-to-end entry slips the host-to-device copy of ``u`` under the first one).
 """
 import ctypes as C
 import math
@@ -185,7 +185,7 @@ class GraphedStep(object):
         self.d_extra = z(len(self.extras), N) if (self.extras and hasattr(ode, "offset_layer")) else None
         self.ready = False
         self.steps_done = 0
-        self.ev_hot = None  # optional (start, end) CUDA events around the reverse-sweep kernel
+        self.ev_hot = None  # optional (start, end) CUDA events around the reverse-sweep kernel (forces the eager path)
 
     # -- the three segments -------------------------------------------------------------------------------------
     def _pre(self):
@@ -304,13 +304,16 @@ class GraphedStep(object):
                 self._post()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        self.g_pre, self.g_post = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        # two graphs: everything up to the ODE kernels' inputs (the end-to-end entry slips the copy of u underneath it),
+        # and the rest -- ODE forward, IWAE, reverse sweep, encoder backward, all-reduce, Adam.  With the hot launches
+        # issued eagerly between two graphs the host needed ~155 us per step, as long as the device.
+        self.g_pre, self.g_rest = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_pre):
             self._pre()
         self._build_descriptors()
         self.g_pre.replay()
-        self._hot()
-        with torch.cuda.graph(self.g_post, pool=self.g_pre.pool()):
+        with torch.cuda.graph(self.g_rest, pool=self.g_pre.pool()):
+            self._hot()
             self._post()
         torch.cuda.synchronize()
         for t, s in zip((opt.flat, opt.exp_avg, opt.exp_avg_sq, opt.step_dev), snap):
@@ -364,27 +367,25 @@ class GraphedStep(object):
             self._u_ready.record(self._copy_stream)
         if self.use_graphs:
             self.g_pre.replay()
+            cur.wait_event(self._u_ready)
+            self.g_rest.replay()
         else:
             self._pre()
             self._build_descriptors()
-        cur.wait_event(self._u_ready)
-        self._hot()
-        self._u_free.record(cur)
-        if self.use_graphs:
-            self.g_post.replay()
-        else:
+            cur.wait_event(self._u_ready)
+            self._hot()
             self._post()
+        self._u_free.record(cur)
         self.steps_done += 1
         return self.buf.cost
 
     def step(self):
         """One step on whatever the static buffers hold.  Returns the cost (device tensor, no sync)."""
         self.prepare()
-        if self.use_graphs:
+        if self.use_graphs and self.ev_hot is None:
             self.g_pre.replay()
-            self._hot()
-            self.g_post.replay()
-        else:
+            self.g_rest.replay()
+        else:  # no graphs, or instrumented (events around the reverse-sweep launch): the same calls, issued eagerly
             self._pre()
             self._build_descriptors()
             self._hot()
