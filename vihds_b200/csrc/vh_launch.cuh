@@ -255,11 +255,25 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
   const int b = n / a.IW;
   const size_t N = a.N;
   const int T = a.T;
-  enum { FULL0 = 1, EMPTY0 = 3, EPILOGUE = 5 };
-  const SlotScratch<R> sc{ring + 2 * Ring::SLOT + (role & 1) * 32 + lane, 64};  // producer / consumer columns
-  const SlotScratch<R> gloc{ring + 2 * Ring::SLOT + 32 + lane, 64};            // the consumer's, read by every warp
+  enum { FULL0 = 1, EMPTY0 = 3, EPILOGUE = 5, PROLOGUE = 6 };
+  const SlotScratch<R> thv{ring + 2 * Ring::SLOT + lane, 64};        // theta by slot, filled once by the whole team
+  const SlotScratch<R> gloc{ring + 2 * Ring::SLOT + 32 + lane, 64};  // its cotangent, written by the consumer
   const R glq = (a.g_logq_theta && active) ? a.g_logq_theta[n] : R(0);
   const R glp = (a.g_logp_theta && active) ? a.g_logp_theta[n] : R(0);
+  // theta of this trajectory: warp r fetches columns r, r + WS_WARPS, ... (read back from the forward's theta planes,
+  // or re-sampled) and the slots without a column that it owns; the values stay in shared memory for the epilogue
+  for (int s = role; s < M::NSLOT; s += WS_WARPS) {
+    const int src = a.slot_src[s];
+    if (src < 0) thv[s] = src != VH_SLOT_UNUSED ? a.extra[(size_t)(-1 - src) * N + n] : R(0);
+  }
+#pragma unroll 3
+  for (int k = role; k < a.P; k += WS_WARPS) {
+    R lq = R(0), lp = R(0);
+    const R v = a.theta_in ? a.theta_in[(size_t)k * N + n] : sample_column(a, n, b, k, lq, lp, false);
+    const int s = a.col_slot[k];
+    if (s >= 0) thv[s] = v;
+  }
+  named_bar_sync_all(PROLOGUE);
   if (role < 2) {
     // both roles need the RHS constants
     Rhs<M> f;
@@ -267,8 +281,9 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
     R prec[4], iprec[4];
     {
       R th[M::NSLOT];
-      R lq = R(0), lp = R(0), c6, c12;
-      load_theta<M, true>(a, n, b, th, lq, lp, sc, false);
+      R c6, c12;
+#pragma unroll
+      for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? thv[s] : R(0);
       M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
       M::setup(th, c6, c12, f.c);
 #pragma unroll
@@ -397,8 +412,9 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
     for (int s = 0; s < M::NSLOT; ++s) gth[s] = R(0);
     {
       R th[M::NSLOT];
-      R lq = R(0), lp = R(0), c6, c12;
-      load_theta<M, true>(a, n, b, th, lq, lp, sc, false);
+      R c6, c12;
+#pragma unroll
+      for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? thv[s] : R(0);
       M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
       M::init_state_vjp(lam, gth);
       M::setup_vjp(th, c6, c12, f.c, gc, gth);
