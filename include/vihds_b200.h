@@ -199,6 +199,32 @@ int vh_adam_step_dev(int dtype, size_t n, void* param, void* grad, void* exp_avg
                      void* step, int zero_grad, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Multi-GPU exchange step fused with the optimiser (no counterpart in the single-device reference; it takes the place
+ * of ncclAllReduce(flat gradient) + vh_adam_step_dev in the data-parallel step): every rank pushes its gradient vector
+ * into all ranks' inboxes over NVLink peer memory, waits for the others' flags, sums the inbox slots in rank order
+ * (bit-identical on every rank) and applies Adam -- ONE launch.  One process per GPU, all on one node.
+ *
+ *   vh_peer_buffer_bytes    size of a rank's exchange buffer for n parameters and `world` ranks
+ *   vh_peer_buffer_create   cudaMalloc + zero it + CUDA-IPC handle (64 bytes) to send to the peers   [the only
+ *   vh_peer_buffer_open     map a peer's buffer from its handle (peer access enabled lazily)           allocation the
+ *   vh_peer_buffer_close / _destroy                                                                    library makes]
+ *   vh_adam_allreduce_step  param / grad / exp_avg / exp_avg_sq / hyper / step as for vh_adam_step_dev (the gradient
+ *                           is cleared); state = int64[4] {epoch, ticket scratch, timed_out, 0}, zero-initialised,
+ *                           owned by the caller and NEVER rewound (every rank must make the same sequence of calls);
+ *                           peers = DEVICE array of `world` pointers, entry r = this process's mapping of rank r's
+ *                           exchange buffer (entry `rank` = its own).  timed_out != 0: a peer's flag did not arrive
+ *                           within ~10 s (the update of that call is invalid). */
+#define VH_PEER_MAX_WORLD 16
+size_t vh_peer_buffer_bytes(int dtype, size_t n, int world);
+int vh_peer_buffer_create(size_t bytes, void** dev_ptr, void* handle64);
+int vh_peer_buffer_open(const void* handle64, void** dev_ptr);
+int vh_peer_buffer_close(void* dev_ptr);
+int vh_peer_buffer_destroy(void* dev_ptr);
+int vh_adam_allreduce_step(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq,
+                           const void* hyper, void* step, void* state, int rank, int world, const void* peers,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Fused amortised encoder q(theta | x, d) (vihds/encoders.py:16-55 ConditionalEncoder, :126-253 Q_Local / Q_Global_Cond
  * / Q_Global / Q_Constant, :383-404 evaluate_q): delta-observations -> Conv1d -> AvgPool1d(stride 1) -> Linear -> tanh
  * -> packed (mu, log_prec) heads -> q_mu / q_prec [B][P] in the column order local, global-conditioned, global, constant.

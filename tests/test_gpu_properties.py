@@ -288,3 +288,27 @@ def test_adam_dev_counts_steps_and_clears_the_gradient():
             assert step.tolist() == [it, 0]
             assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-7)
             assert torch.equal(ga, torch.zeros_like(ga) if it % 2 else gr)
+
+
+def test_fused_allreduce_adam_single_rank_equals_adam():
+    """vh_adam_allreduce_step with a one-rank exchange (the kernel pushes into its own inbox, publishes and waits on its
+    own flag): same update as vh_adam_step, gradient cleared, epoch / step counters advance, inbox parity alternates."""
+    from vihds_b200.distributed import PeerGradientExchange
+    lib = L.load()
+    for n in (1, 1000, 100003):
+        g = torch.Generator().manual_seed(n)
+        p0 = torch.randn(n, generator=g).cuda()
+        pa, pb = p0.clone(), p0.clone()
+        ma, va, mb, vb = (torch.zeros(n, device="cuda") for _ in range(4))
+        hyper = torch.tensor([0.01, 0.9, 0.999, 1e-8], dtype=torch.float64, device="cuda")
+        step = torch.zeros(2, dtype=torch.int64, device="cuda")
+        ex = PeerGradientExchange(n, torch.float32, torch.device("cuda", 0))
+        for it in range(1, 5):
+            gr = torch.randn(n, generator=g).cuda()
+            ga = gr.clone()
+            L.check(lib.vh_adam_allreduce_step(0, n, _p(pa), _p(ga), _p(ma), _p(va), _p(hyper), _p(step), _p(ex.state),
+                                               0, 1, _p(ex.peers), None))
+            L.check(lib.vh_adam_step(0, n, _p(pb), _p(gr), _p(mb), _p(vb), 0.01, 0.9, 0.999, 1e-8, it, None))
+            assert step.tolist()[0] == it and ex.state.tolist()[:3] == [it, 0, 0]
+            assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-7)
+            assert not ga.any()

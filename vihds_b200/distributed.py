@@ -8,9 +8,13 @@ vh_iwae_fwd/bwd), and the only exchange is a SUM all-reduce of the flat gradient
 dr_constant_icml) followed by an identical Adam step on every rank.  ``u`` is drawn from numpy's global RNG for
 the GLOBAL batch and sliced (vihds/vae.py:22-24 is the RNG contract), so results do not depend on the rank count.
 
-Backend: "nccl" over NVLink on the GPUs (captured inside the post-step CUDA graph, training.GraphedStep._post);
-"gloo" in the CPU tests of this module's logic (tests/test_distributed_cpu.py).
+Backend: "nccl" for the rendezvous and the control plane.  The gradient exchange itself is ``PeerGradientExchange``:
+one kernel of libvihds_b200.so (vh_adam_allreduce_step) that pushes the gradient into every rank's inbox over NVLink
+peer memory, sums in rank order and applies Adam -- captured inside the step's CUDA graph (training.GraphedStep._post).
+``VIHDS_ALLREDUCE=nccl`` selects ncclAllReduce + the plain Adam kernel instead.  "gloo" in the CPU tests of this module's
+host logic (tests/test_distributed_cpu.py).
 """
+import ctypes as C
 import os
 
 import numpy as np
@@ -66,3 +70,45 @@ def allreduce_max(value, group, device):
     if group is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+class PeerGradientExchange(object):
+    """Exchange buffers of the fused all-reduce + Adam kernel (include/vihds_b200.h: vh_peer_*, vh_adam_allreduce_step).
+
+    Every rank allocates one buffer (flags + a double-buffered inbox with one slot per rank), the CUDA-IPC handles go
+    round through ``all_gather_object``, and each rank maps its peers' buffers.  ``group=None`` builds a one-rank
+    exchange (the kernel then only talks to itself: used by the single-GPU test)."""
+
+    def __init__(self, n, dtype, device, group=None):
+        from . import _lib as L
+        self.lib = lib = L.load()
+        self.rank = dist.get_rank(group) if group is not None else 0
+        self.world = dist.get_world_size(group) if group is not None else 1
+        vdt = L.VH_F64 if dtype == torch.float64 else L.VH_F32
+        nbytes = lib.vh_peer_buffer_bytes(vdt, n, self.world)
+        handle = (C.c_ubyte * 64)()
+        own = C.c_void_p()
+        with torch.cuda.device(device):
+            L.check(lib.vh_peer_buffer_create(nbytes, C.byref(own), handle))
+            handles = [bytes(handle)]
+            if group is not None:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, bytes(handle), group=group)
+            ptrs, self._opened = [], []
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(own.value)
+                    continue
+                q = C.c_void_p()
+                buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                L.check(lib.vh_peer_buffer_open(buf, C.byref(q)))
+                ptrs.append(q.value)
+                self._opened.append(q.value)
+        self._own = own.value
+        self.peers = torch.tensor(ptrs, dtype=torch.int64, device=device)
+        self.state = torch.zeros(4, dtype=torch.int64, device=device)  # epoch, ticket, timed_out, -
+        if group is not None:
+            dist.barrier(group=group)  # nobody pushes before everybody has mapped everybody
+
+    def timed_out(self):
+        return bool(self.state[2].item())

@@ -298,6 +298,14 @@ class FlatAdam(object):
     def zero_grad(self):
         self.grad.zero_()
 
+    def step_exchange(self, exchange):
+        """Data-parallel step: sum the ranks' gradients over NVLink peer memory and apply Adam in ONE launch
+        (distributed.PeerGradientExchange); the gradient vector is cleared."""
+        L.check(L.load().vh_adam_allreduce_step(self.vdt, self.flat.numel(), _ptr(self.flat), _ptr(self.grad),
+                                                _ptr(self.exp_avg), _ptr(self.exp_avg_sq), _ptr(self.hyper),
+                                                _ptr(self.step_dev), _ptr(exchange.state), exchange.rank, exchange.world,
+                                                _ptr(exchange.peers), _stream()))
+
     def step(self, zero_grad=False):
         """zero_grad: clear the gradient vector in the same launch (it is consumed exactly once)."""
         L.check(L.load().vh_adam_step_dev(self.vdt, self.flat.numel(), _ptr(self.flat), _ptr(self.grad), _ptr(self.exp_avg),

@@ -15,6 +15,7 @@ Two equivalent ways to take a step:
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -141,10 +142,12 @@ class GraphedStep(object):
     """One ELBO-gradient step over static buffers (see module docstring).
 
     b_total       denominator of the batch mean (global batch when individuals are sharded over ranks)
-    process_group torch.distributed group for the single gradient all-reduce (None: one GPU)
+    process_group torch.distributed group of the data-parallel ranks (None: one GPU)
+    exchange      "peer" (default; env VIHDS_ALLREDUCE): gradient exchange + Adam in one kernel over NVLink peer memory;
+                  "nccl": ncclAllReduce of the flat gradient, then the Adam kernel
     """
 
-    def __init__(self, training, B, IW, T, b_total=None, process_group=None, use_graphs=True):
+    def __init__(self, training, B, IW, T, b_total=None, process_group=None, use_graphs=True, exchange=None):
         self.tr, self.model = training, training.model
         m = self.model
         dev, dt = training.settings.device, training.settings.dtype
@@ -183,6 +186,11 @@ class GraphedStep(object):
         self.buf.d_q_mu, self.buf.d_q_prec = self.buf.d_q[0], self.buf.d_q[1]  # adjacent: cleared by one memset
         self.d_weights = z(self.prob.n_weights) if self.prob.n_weights else None
         self.d_extra = z(len(self.extras), N) if (self.extras and hasattr(ode, "offset_layer")) else None
+        self.exchange = None
+        if self.pg is not None and (exchange or os.environ.get("VIHDS_ALLREDUCE", "peer")) != "nccl":
+            from .distributed import PeerGradientExchange
+            opt = training.optimizer
+            self.exchange = PeerGradientExchange(opt.flat.numel(), opt.flat.dtype, opt.flat.device, self.pg)
         self.ready = False
         self.steps_done = 0
         self.ev_hot = None  # optional (start, end) CUDA events around the reverse-sweep kernel (forces the eager path)
@@ -279,9 +287,12 @@ class GraphedStep(object):
             grads.append(self.d_extra)
         if outs:
             torch.autograd.backward(outs, grads)
-        if self.pg is not None:
-            torch.distributed.all_reduce(opt.grad, group=self.pg)
-        opt.step(zero_grad=True)
+        if self.exchange is not None:
+            opt.step_exchange(self.exchange)  # gradient exchange over NVLink peer memory + Adam, one launch
+        else:
+            if self.pg is not None:
+                torch.distributed.all_reduce(opt.grad, group=self.pg)
+            opt.step(zero_grad=True)
 
     # -- capture / replay ---------------------------------------------------------------------------------------
     def prepare(self):
