@@ -364,6 +364,8 @@ def main():
     ms_per_step = total_ms / a.steps
     value = N * world / (ms_per_step * 1e-3)
     final_cost = float(gs.buf.cost.item())
+    if gs.exchange is not None and gs.exchange.timed_out():
+        raise RuntimeError("gradient exchange: a peer's flag did not arrive (vh_adam_allreduce_step timed out)")
 
     # end-to-end pass: the public step fed from pinned HOST buffers; H2D of the batch + u, D2H of the cost, host sync
     h2d = sum(v.numel() * v.element_size() for v in pinned.values()) + u_host[0].numel() * u_host[0].element_size()
@@ -435,7 +437,9 @@ def main():
             WORKLOADS[a.workload][1], "" if T0 is None else " resampled to a synthetic T=%d grid" % T),
         "config": {"workload": a.workload, "spec": spec_name, "batch_per_gpu": B, "global_batch": B * world, "iw": IW,
                    "trajectories_per_step": N * world, "T": T, "state_width": S, "n_theta": P, "solver": settings.params.solver,
-                   "parallelism": "dp%d (individuals sharded, one gradient all-reduce)" % world,
+                   "parallelism": "dp%d (individuals sharded; gradient sum %s)" % (
+                       world, "n/a" if world == 1 else ("fused with Adam over NVLink peer memory" if gs.exchange is not None
+                                                        else "ncclAllReduce")),
                    "cuda_graphs": not a.no_graphs, "l2": "flushed between timed steps (256 MiB memset)"},
         "roofline": {"kernel": "%s (discrete-adjoint reverse sweep, the dominant launch)" % (
                          "bb_bwd_kernel" if a.workload == "dr_blackbox_icml" else "elbo_bwd_kernel"),
