@@ -370,12 +370,12 @@ class GraphedStep(object):
             self._copy_stream = torch.cuda.Stream()
             self._u_ready, self._u_free = torch.cuda.Event(), torch.cuda.Event()
             self._u_free.record(cur)
-        self.load_batch(batch)
-        self.draw_conditioner()
-        with torch.cuda.stream(self._copy_stream):
+        with torch.cuda.stream(self._copy_stream):  # first: the big copy runs under everything the host does next
             self._copy_stream.wait_event(self._u_free)  # the previous step's reverse sweep still reads the old u
             self.load_u(u)
             self._u_ready.record(self._copy_stream)
+        self.load_batch(batch)
+        self.draw_conditioner()
         if self.use_graphs:
             self.g_pre.replay()
             cur.wait_event(self._u_ready)
