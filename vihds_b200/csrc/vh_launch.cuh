@@ -88,6 +88,9 @@ __device__ __forceinline__ void cp_async_wait() {
 
 // 3 resident CTAs of 128 threads per SM (<= 168 registers) for the fp32 8-species models: measured faster than 2 CTAs
 // at 190 registers and than 4 CTAs with spills; the wider models keep the full register file.
+#ifndef VH_BWD_PF
+#define VH_BWD_PF 3
+#endif
 template <class M>
 struct BwdBounds {
   static constexpr int min_blocks = (sizeof(typename M::real) == 4 && !M::DYN && !M::RELAY) ? 3 : 1;
@@ -172,7 +175,7 @@ __global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel
     NoGW<R> nogw;
     // (a cp.async staging ring as in the warp-specialised kernel was measured here too: 1.340 vs 1.306 ms at
     // N = 131,072 -- with 12 resident warps per SM the one-step register prefetch already hides the latency)
-    DirectCk<R, M::S> ck;
+    DirectCk<R, M::S, VH_BWD_PF> ck;
     traj_backward<M, TB>(a, nn, active, w, nogw, red, sc, ck);
   }
 }

@@ -48,17 +48,6 @@ VH_HD float vdiv(float a, float b) {
 }
 VH_HD double vdiv(double a, double b) { return a / b; }
 
-// Software prefetch of one cache line into L1 (no destination register: the compiler cannot sink it towards the use
-// the way it sinks an early register load under register pressure -- measured: 41 % of the reverse loop's stall samples
-// sat on the first use of the "prefetched" checkpoint).
-VH_HD void prefetch_l1(const void* p) {
-#if defined(__CUDA_ARCH__)
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-  (void)p;
-#endif
-}
-
 // A global load the compiler must issue where it is written.  Used for the one-step-ahead fetch of the small shared
 // inputs (observations, grid time): as plain loads ptxas sank them below the ~400-instruction adjoint body, right in
 // front of their first use, which exposed a full memory latency per time step (41 % of the reverse loop's stall

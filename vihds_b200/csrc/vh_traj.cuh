@@ -535,7 +535,9 @@ VH_HD void traj_forward(const Call<typename M::real>& a, int n, const typename M
 // ---------------------------------------------------------------------------------------------------------------
 // Source of the checkpoints x_k for the reverse sweep, newest first: plain loads, register-prefetched one step ahead.
 // (The warp-specialised kernel has its own source: a cp.async ring in shared memory, vh_launch.cuh.)
-template <typename R, int S>
+// PF > 0 (device, throughput kernels): additionally pull the checkpoint of PF steps further back into L2 (no
+// destination registers) so that the one-step-ahead register load is an L2 hit, not an HBM round trip.
+template <typename R, int S, int PF = 0>
 struct DirectCk {
   const R* xs;
   size_t N;
@@ -555,6 +557,13 @@ struct DirectCk {
       xs -= (size_t)S * N;
 #pragma unroll
       for (int q = 0; q < S; ++q) nx[q] = xs[(size_t)q * N];
+#if defined(__CUDA_ARCH__)
+      if (PF > 0 && k > PF) {
+        const R* pf = xs - (size_t)PF * S * N;
+#pragma unroll
+        for (int q = 0; q < S; ++q) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t)q * N));
+      }
+#endif
     }
     --k;
   }

@@ -160,7 +160,13 @@ class GraphedStep(object):
         self.P = P
         z = lambda *s: torch.zeros(*s, dtype=dt, device=dev)  # noqa: E731
         Cn, Dn = ode.n_treatments, ode.device_depth
-        self.batch = Settings(times=z(T), inputs=z(B, Cn), dev_1hot=z(B, Dn), observations=z(B, 4, T))
+        # the per-individual batch tensors are views of ONE device buffer: a host batch arrives in one copy
+        spans, off = {}, 0
+        for k, shape in (("inputs", (B, Cn)), ("dev_1hot", (B, Dn)), ("observations", (B, 4, T))):
+            spans[k] = (off, off + int(np.prod(shape)), shape)
+            off += int(np.prod(shape))
+        self._batch_dev, self._batch_spans = z(off), spans
+        self.batch = Settings(times=z(T), **{k: self._batch_dev[a:b].view(shape) for k, (a, b, shape) in spans.items()})
         self.u = z(self.N, P)
         self.extras = list(ode.conditioned) if m.decoder.condition_on_device else []
         self.cond_w = z(max(1, len(self.extras)), Dn)
@@ -332,32 +338,65 @@ class GraphedStep(object):
         self.ready = True
 
     def load_batch(self, batch, non_blocking=True):
-        for k in ("times", "inputs", "dev_1hot", "observations"):
-            src = batch[k]
-            if k == "times":  # the time grid belongs to the data set: skip the copy while the same tensor is handed in
-                tag = (id(src), src._version)
-                if getattr(self, "_times_tag", None) == tag:
-                    continue
-                self._times_tag = tag
-            self.batch[k].copy_(src, non_blocking=non_blocking)
+        src = batch["times"]  # the time grid belongs to the data set: skip the copy while the same tensor is handed in
+        tag = (id(src), src._version)
+        if getattr(self, "_times_tag", None) != tag:
+            self._times_tag = tag
+            self.batch.times.copy_(src, non_blocking=non_blocking)
+        keys = ("inputs", "dev_1hot", "observations")
+        if any(batch[k].is_cuda for k in keys):
+            for k in keys:
+                self.batch[k].copy_(batch[k], non_blocking=non_blocking)
+            return
+        # host batch: packed into a pinned staging buffer (two of them, alternating: the previous copy may be in flight)
+        if not hasattr(self, "_bhost"):
+            self._bhost = [torch.empty(self._batch_dev.numel(), dtype=self._batch_dev.dtype).pin_memory() for _ in range(2)]
+            self._bnp = [t.numpy() for t in self._bhost]
+            self._bev, self._bslot = [torch.cuda.Event(), torch.cuda.Event()], 0
+        sl = self._bslot
+        self._bev[sl].synchronize()
+        for k in keys:
+            a, b, _ = self._batch_spans[k]
+            self._bnp[sl][a:b] = batch[k].numpy().reshape(-1)
+        self._batch_dev.copy_(self._bhost[sl], non_blocking=non_blocking)
+        self._bev[sl].record()
+        self._bslot = sl ^ 1
 
     def load_u(self, u, non_blocking=True):
         self.u.copy_(u.reshape(self.N, self.P), non_blocking=non_blocking)
 
-    def draw_conditioner(self):
-        """Fresh conditioner weights per step from the torch CPU RNG (reference quirk, vihds/ode.py:48): per parameter two
-        uniform fills and one normal fill of a [1, D] row -- the draws models._draw_conditioner_weight makes, done in
-        place on a pinned staging buffer -- then one asynchronous copy."""
-        if not self.rel:
-            return
-        if not hasattr(self, "_cond_host"):
-            self._cond_host = torch.empty(len(self.extras), self.cond_w.shape[1]).pin_memory()
-            self._cond_rows = [self._cond_host[k:k + 1] for k in range(len(self.extras))]
-        for row in self._cond_rows:
+    def _cond_fill(self, sl):
+        """Per parameter two uniform fills and one normal fill of a [1, D] row: the draws
+        models._draw_conditioner_weight makes (reference quirk, vihds/ode.py:48), in place on pinned staging buffer sl."""
+        self._cond_ev[sl].synchronize()  # the copy that last read this buffer has finished
+        for row in self._cond_rows[sl]:
             row.uniform_(-1.0, 1.0)
             row.uniform_(-1.0, 1.0)
             row.normal_(mean=2.0, std=1.5)
-        self.cond_w.copy_(self._cond_host, non_blocking=True)
+
+    def draw_conditioner(self):
+        """Fresh conditioner weights per step from the torch CPU RNG stream, then one asynchronous copy.  If
+        ``predraw_conditioner`` has already made this step's draw (same stream, same order) only the copy is left."""
+        if not self.rel:
+            return
+        if not hasattr(self, "_cond_host"):
+            self._cond_host = [torch.empty(len(self.extras), self.cond_w.shape[1]).pin_memory() for _ in range(2)]
+            self._cond_rows = [[h[k:k + 1] for k in range(len(self.extras))] for h in self._cond_host]
+            self._cond_ev, self._cond_slot, self._cond_drawn = [torch.cuda.Event(), torch.cuda.Event()], 0, False
+        sl = self._cond_slot
+        if not self._cond_drawn:
+            self._cond_fill(sl)
+        self.cond_w.copy_(self._cond_host[sl], non_blocking=True)
+        self._cond_ev[sl].record()
+        self._cond_drawn, self._cond_slot = False, sl ^ 1
+
+    def predraw_conditioner(self):
+        """Host only: make the NEXT step's draw now, while the device is busy with this one (~40 us of torch RNG calls
+        that would otherwise sit in front of the next step's first launch).  The RNG stream is consumed in the same
+        order; re-seeding torch between two steps takes effect one step later."""
+        if self.rel and hasattr(self, "_cond_host") and not self._cond_drawn:
+            self._cond_fill(self._cond_slot)
+            self._cond_drawn = True
 
     def step_from_host(self, batch, u):
         """The public end-to-end step: ``batch`` (times, inputs, dev_1hot, observations) and ``u`` [B, IW, P] are HOST
@@ -387,6 +426,7 @@ class GraphedStep(object):
             self._hot()
             self._post()
         self._u_free.record(cur)
+        self.predraw_conditioner()
         self.steps_done += 1
         return self.buf.cost
 
