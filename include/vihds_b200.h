@@ -198,6 +198,11 @@ int vh_adam_step(int dtype, size_t n, void* param, const void* grad, void* exp_a
 int vh_adam_step_dev(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq, const void* hyper,
                      void* step, int zero_grad, void* stream);
 
+/* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream): the step's host <-> device copies (batch, u, conditioner
+ * weights: `.to(device)` in vihds/training.py:326-329, vae.py:22-24) without a tensor library in between.  Host memory
+ * should be pinned. */
+int vh_copy_async(void* dst, const void* src, size_t bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Multi-GPU exchange step fused with the optimiser (no counterpart in the single-device reference; it takes the place
  * of ncclAllReduce(flat gradient) + vh_adam_step_dev in the data-parallel step): every rank pushes its gradient vector

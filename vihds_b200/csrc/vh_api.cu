@@ -507,4 +507,17 @@ int vh_adam_step_dev(int dtype, size_t n, void* param, void* grad, void* exp_avg
   return check_launch("adam_dev_kernel");
 }
 
+int vh_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
+  if (!dst || !src) {
+    set_error("vh_copy_async: null pointer");
+    return VH_ERR_INVALID;
+  }
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_error("vh_copy_async(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    return VH_ERR_CUDA;
+  }
+  return VH_OK;
+}
+
 }  // extern "C"

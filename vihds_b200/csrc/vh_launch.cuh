@@ -99,7 +99,8 @@ struct BwdBounds {
 // sample / clip / log-prob prologue -- warp r takes theta columns r, r + FWD_TEAM, ... and leaves values (by slot) and
 // its partial log q / log p in shared memory -- then warp 0 integrates alone.  Column k of slot s is written only by
 // the warp that owns column k, slots without a column only by the warp that owns slot s (build_call guarantees one
-// column per slot), so the prologue needs a single barrier.  fp32 / fp64, constant-precision models.
+// column per slot), so the prologue needs a single barrier.  fp32 / fp64; the dynamic-precision models keep their
+// NeuralPrecisions weights in shared memory next to it.
 #ifndef VH_FWD_TEAM
 #define VH_FWD_TEAM 4
 #endif
@@ -115,7 +116,11 @@ __global__ void __launch_bounds__(FWD_TEAM * 32) elbo_fwd_team_kernel(const Call
   const int n = active ? n0 : a.N - 1;
   const int b = n / a.IW;
   const SlotScratch<R> loc{sm + lane, 32};
-  R* part = sm + M::NSLOT * 32;  // [2][FWD_TEAM][32]
+  R* part = sm + M::NSLOT * 32;       // [2][FWD_TEAM][32]
+  R* wsm = part + 2 * FWD_TEAM * 32;  // NeuralPrecisions weights (dynamic-precision models)
+  if (M::DYN) {
+    for (int i = threadIdx.x; i < NetInfo<M>::NW; i += blockDim.x) wsm[i] = a.weights[i];
+  }
   for (int s = role; s < M::NSLOT; s += FWD_TEAM) {
     const int src = a.slot_src[s];
     if (src < 0) loc[s] = src != VH_SLOT_UNUSED ? a.extra[(size_t)(-1 - src) * a.N + n] : R(0);
@@ -141,7 +146,7 @@ __global__ void __launch_bounds__(FWD_TEAM * 32) elbo_fwd_team_kernel(const Call
   R th[M::NSLOT];
 #pragma unroll
   for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? loc[s] : R(0);
-  traj_forward_from<M, TB>(a, n, nullptr, th, lq, lp);
+  traj_forward_from<M, TB>(a, n, M::DYN ? wsm : nullptr, th, lq, lp);
 }
 
 template <class M, class TB>
@@ -189,7 +194,8 @@ __global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel
 //                      ring and does the part that is serial in lambda: rk_step_adjoint + the emission adjoint.
 // The two halves of a time step (~200 and ~260 instructions) run on two schedulers instead of one after the other on
 // one.  Hand-off: named barriers (full / empty per slot, bar.arrive on one side, bar.sync on the other), data laid out
-// [item][lane] (conflict-free).  fp32 / fp64, constant-precision models (no weight-gradient accumulators to share).
+// [item][lane] (conflict-free).  fp32 / fp64.  Dynamic-precision models: the NeuralPrecisions weights and the consumer
+// lanes' weight-gradient accumulators [NW][32] sit in shared memory too; the team reduces them after the epilogue.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
@@ -261,6 +267,14 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
   enum { FULL0 = 1, EMPTY0 = 3, EPILOGUE = 5, PROLOGUE = 6 };
   const SlotScratch<R> thv{ring + 2 * Ring::SLOT + lane, 64};        // theta by slot, filled once by the whole team
   const SlotScratch<R> gloc{ring + 2 * Ring::SLOT + 32 + lane, 64};  // its cotangent, written by the consumer
+  // dynamic-precision models: NeuralPrecisions weights and the consumer lanes' weight-gradient accumulators [NW][32]
+  constexpr int NW = NetInfo<M>::NW;
+  R* wsm = ring + 2 * Ring::SLOT + M::NSLOT * 64 + (WS_PF + 1) * S * 32;
+  R* gwsm = wsm + NW;
+  if (M::DYN) {
+    for (int i = threadIdx.x; i < NW; i += blockDim.x) wsm[i] = a.weights[i];
+    for (int i = threadIdx.x; i < NW * 32; i += blockDim.x) gwsm[i] = R(0);
+  }
   const R glq = (a.g_logq_theta && active) ? a.g_logq_theta[n] : R(0);
   const R glp = (a.g_logp_theta && active) ? a.g_logp_theta[n] : R(0);
   // theta of this trajectory: warp r fetches columns r, r + WS_WARPS, ... (read back from the forward's theta planes,
@@ -280,7 +294,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
   if (role < 2) {
     // both roles need the RHS constants
     Rhs<M> f;
-    f.w = nullptr;
+    f.w = M::DYN ? wsm : nullptr;
     R prec[4], iprec[4];
     {
       R th[M::NSLOT];
@@ -291,7 +305,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
       M::setup(th, c6, c12, f.c);
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
-        prec[o] = th[S_prec_x + o];
+        prec[o] = M::DYN ? R(1) : th[S_prec_x + o];
         iprec[o] = R(1) / prec[o];
       }
     }
@@ -353,6 +367,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
 #pragma unroll
     for (int i = 0; i < M::NC; ++i) gc.v[i] = R(0);
     NoGW<R> nogw;
+    StridedGW<R> sgw{gwsm + lane, 32};
     R lam[S], x[S];
     R ob[4] = {R(0), R(0), R(0), R(0)}, obp[4] = {R(0), R(0), R(0), R(0)};
 #pragma unroll
@@ -381,7 +396,10 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
           __threadfence_block();
           named_bar_arrive(EMPTY0 + slot);
         }
-        rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd, lam, gc, nogw);
+        if (M::DYN)
+          rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd, lam, gc, sgw);
+        else
+          rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd, lam, gc, nogw);
       }
       // emission at time k
       R xp[4], gxp[4];
@@ -390,9 +408,15 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
       for (int o = 0; o < 4; ++o) {
         gxp[o] = (gxpr && active) ? gxpr[(size_t)o * N] : R(0);
         if (obs) {
+          const R pr = M::DYN ? x[M::NS + o] : prec[o];
+          const R ipr = M::DYN ? vdiv(R(1), pr) : iprec[o];
           const R d = xp[o] - ob[o];
-          gxp[o] -= gl[o] * prec[o] * d;
-          gprec[o] += gl[o] * R(0.5) * (iprec[o] - d * d);
+          gxp[o] -= gl[o] * pr * d;
+          const R gp = gl[o] * R(0.5) * (ipr - d * d);
+          if (M::DYN)
+            lam[M::NS + o] += gp;
+          else
+            gprec[o] += gp;
         }
       }
       M::observe_vjp(x, gxp, lam);
@@ -421,8 +445,10 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
       M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
       M::init_state_vjp(lam, gth);
       M::setup_vjp(th, c6, c12, f.c, gc, gth);
+if (!M::DYN) {
 #pragma unroll
-      for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gprec[o];
+  for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gprec[o];
+}
     }
 #pragma unroll
     for (int s = 0; s < M::NSLOT; ++s) gloc[s] = M::uses(s) ? gth[s] : R(0);
@@ -441,11 +467,19 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
     for (int s = role; s < M::NSLOT; s += WS_WARPS) {
       const int src = a.slot_src[s];
       if (src < 0 && src != VH_SLOT_UNUSED) a.d_extra[(size_t)(-1 - src) * N + n] = gloc[s];
-    }
-  }
-}
-
-inline int pick_block(int N) {
+      }
+      }
+      if (M::DYN) {  // weight gradients: lanes of the consumer -> one atomic per weight per CTA
+      for (int i = role; i < NW; i += WS_WARPS) {
+      R v = gwsm[i * 32 + lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) atomicAdd(a.d_weights + i, v);
+      }
+      }
+      }
+      
+      inline int pick_block(int N) {
   // small batches are latency-bound: spread warps over as many SMs as possible (148 SMs x 4 schedulers)
   if (N <= 148 * 4 * 32) return 32;
   if (N <= 148 * 8 * 64) return 64;
@@ -463,7 +497,6 @@ struct FwdLauncher {
       const char* m = getenv("VIHDS_FWD_TEAM");
       return !m ? -1 : atoi(m);
     }();
-    if (M::DYN) return false;
     return mode >= 0 ? mode != 0 : block == 32;
   }
   template <class M, class TB>
@@ -472,7 +505,8 @@ struct FwdLauncher {
     const int grid = (a.N + block - 1) / block;
     const size_t smem = sizeof(R) * (((NetInfo<M>::NW + 3) & ~3) + (size_t)M::NSLOT * block);  // weights | slot scratch
     if (use_team<M>(block)) {
-      const size_t tsm = sizeof(R) * ((size_t)M::NSLOT * 32 + 2 * FWD_TEAM * 32);  // slot values | partial log-probs
+      // slot values | partial log-probs | NeuralPrecisions weights
+      const size_t tsm = sizeof(R) * ((size_t)M::NSLOT * 32 + 2 * FWD_TEAM * 32 + NetInfo<M>::NW);
       elbo_fwd_team_kernel<M, TB><<<(a.N + 31) / 32, FWD_TEAM * 32, tsm, stream>>>(a);
     } else {
       if (smem > 48 * 1024)
@@ -500,14 +534,15 @@ struct BwdLauncher {
       const char* m = getenv("VIHDS_BWD_WS");
       return !m ? -1 : atoi(m);
     }();
-    if (M::DYN) return false;
     return mode >= 0 ? mode != 0 : block == 32;
   }
   template <class M, class TB>
   void launch_bwd_variant(bool ws, int grid, int block, size_t smem) {
     if (ws) {
       // hand-off ring | slot scratch | checkpoint staging ring
-      const size_t ring = sizeof(R) * (2 * WsRing<M, TB>::SLOT + (size_t)M::NSLOT * 64 + (size_t)(WS_PF + 1) * M::S * 32);
+      // | NeuralPrecisions weights + weight-gradient accumulators
+      const size_t ring = sizeof(R) * (2 * WsRing<M, TB>::SLOT + (size_t)M::NSLOT * 64 + (size_t)(WS_PF + 1) * M::S * 32 +
+                                       (size_t)NetInfo<M>::NW * 33);
       if (ring > 48 * 1024)
         cudaFuncSetAttribute(elbo_bwd_ws_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
       elbo_bwd_ws_kernel<M, TB><<<(a.N + 31) / 32, WS_WARPS * 32, ring, stream>>>(a);
