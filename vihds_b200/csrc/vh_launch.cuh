@@ -526,7 +526,7 @@ template <typename R>
 struct BwdLauncher {
   Call<R> a;
   cudaStream_t stream;
-  // warp-specialised pair kernel: latency-bound launches (the 32-thread-CTA regime) of constant-precision models.
+  // warp-specialised kernel: latency-bound launches (the 32-thread-CTA regime), every white-box model.
   // VIHDS_BWD_WS=0|1 overrides (tests / measurements).
   template <class M>
   static bool use_ws(int block) {
