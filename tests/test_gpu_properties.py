@@ -302,7 +302,7 @@ def test_fused_allreduce_adam_single_rank_equals_adam():
         ma, va, mb, vb = (torch.zeros(n, device="cuda") for _ in range(4))
         hyper = torch.tensor([0.01, 0.9, 0.999, 1e-8], dtype=torch.float64, device="cuda")
         step = torch.zeros(2, dtype=torch.int64, device="cuda")
-        ex = PeerGradientExchange(n, torch.float32, torch.device("cuda", 0))
+        ex = PeerGradientExchange(n, torch.float32, torch.device("cuda", 0))  # closed at the end of the loop body
         for it in range(1, 5):
             gr = torch.randn(n, generator=g).cuda()
             ga = gr.clone()
@@ -312,3 +312,5 @@ def test_fused_allreduce_adam_single_rank_equals_adam():
             assert step.tolist()[0] == it and ex.state.tolist()[:3] == [it, 0, 0]
             assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-7)
             assert not ga.any()
+        torch.cuda.synchronize()
+        ex.close()

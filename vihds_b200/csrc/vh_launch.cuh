@@ -353,105 +353,105 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
         t0 = tp;
       }
     } else {
-    // ---------------- consumer: everything that is serial in lambda ----------------
-    R gl[4], gprec[4];
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      gprec[o] = R(0);
-      gl[o] = (a.g_logp_species && active) ? a.g_logp_species[(size_t)n * 4 + o] : R(0);
-    }
-    const R* obs = a.obs ? a.obs + (size_t)b * 4 * T : nullptr;
-    const R* gxs = a.g_x_states ? a.g_x_states + (size_t)(T - 1) * slab + n : nullptr;
-    const R* gxpr = a.g_x_predict ? a.g_x_predict + (size_t)(T - 1) * 4 * N + n : nullptr;
-    typename M::Consts gc;
-#pragma unroll
-    for (int i = 0; i < M::NC; ++i) gc.v[i] = R(0);
-    NoGW<R> nogw;
-    StridedGW<R> sgw{gwsm + lane, 32};
-    R lam[S], x[S];
-    R ob[4] = {R(0), R(0), R(0), R(0)}, obp[4] = {R(0), R(0), R(0), R(0)};
-#pragma unroll
-    for (int q = 0; q < S; ++q) {
-      lam[q] = R(0);
-      x[q] = a.x_states[(size_t)(T - 1) * slab + (size_t)q * N + n];
-    }
-    if (obs) {
-#pragma unroll
-      for (int o = 0; o < 4; ++o) ob[o] = obs[o * T + T - 1];
-    }
-    R t1 = a.times[T - 1], t0 = t1;
-    for (int k = T - 1; k >= 0; --k) {
-      const int kp = k > 0 ? k - 1 : 0;
-      if (obs) {
-#pragma unroll
-        for (int o = 0; o < 4; ++o) obp[o] = ld_early(obs + o * T + kp);
-      }
-      const R tp = ld_early(a.times + kp);
-      if (k + 1 < T) {
-        const int it = T - 2 - k, slot = it & 1;
-        typename Ring::SD sd;
-        named_bar_sync(FULL0 + slot);
-        Ring::get(ring + slot * Ring::SLOT, lane, x, sd);
-        if (k >= 2) {  // slot will be refilled with step k-2; the last two fills are never waited for
-          __threadfence_block();
-          named_bar_arrive(EMPTY0 + slot);
-        }
-        if (M::DYN)
-          rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd, lam, gc, sgw);
-        else
-          rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd, lam, gc, nogw);
-      }
-      // emission at time k
-      R xp[4], gxp[4];
-      M::observe(x, xp);
+      // ---------------- consumer: everything that is serial in lambda ----------------
+      R gl[4], gprec[4];
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
-        gxp[o] = (gxpr && active) ? gxpr[(size_t)o * N] : R(0);
+        gprec[o] = R(0);
+        gl[o] = (a.g_logp_species && active) ? a.g_logp_species[(size_t)n * 4 + o] : R(0);
+      }
+      const R* obs = a.obs ? a.obs + (size_t)b * 4 * T : nullptr;
+      const R* gxs = a.g_x_states ? a.g_x_states + (size_t)(T - 1) * slab + n : nullptr;
+      const R* gxpr = a.g_x_predict ? a.g_x_predict + (size_t)(T - 1) * 4 * N + n : nullptr;
+      typename M::Consts gc;
+#pragma unroll
+      for (int i = 0; i < M::NC; ++i) gc.v[i] = R(0);
+      NoGW<R> nogw;
+      StridedGW<R> sgw{gwsm + lane, 32};
+      R lam[S], x[S];
+      R ob[4] = {R(0), R(0), R(0), R(0)}, obp[4] = {R(0), R(0), R(0), R(0)};
+#pragma unroll
+      for (int q = 0; q < S; ++q) {
+        lam[q] = R(0);
+        x[q] = a.x_states[(size_t)(T - 1) * slab + (size_t)q * N + n];
+      }
+      if (obs) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) ob[o] = obs[o * T + T - 1];
+      }
+      R t1 = a.times[T - 1], t0 = t1;
+      for (int k = T - 1; k >= 0; --k) {
+        const int kp = k > 0 ? k - 1 : 0;
         if (obs) {
-          const R pr = M::DYN ? x[M::NS + o] : prec[o];
-          const R ipr = M::DYN ? vdiv(R(1), pr) : iprec[o];
-          const R d = xp[o] - ob[o];
-          gxp[o] -= gl[o] * pr * d;
-          const R gp = gl[o] * R(0.5) * (ipr - d * d);
+#pragma unroll
+          for (int o = 0; o < 4; ++o) obp[o] = ld_early(obs + o * T + kp);
+        }
+        const R tp = ld_early(a.times + kp);
+        if (k + 1 < T) {
+          const int it = T - 2 - k, slot = it & 1;
+          typename Ring::SD sd;
+          named_bar_sync(FULL0 + slot);
+          Ring::get(ring + slot * Ring::SLOT, lane, x, sd);
+          if (k >= 2) {  // slot will be refilled with step k-2; the last two fills are never waited for
+            __threadfence_block();
+            named_bar_arrive(EMPTY0 + slot);
+          }
           if (M::DYN)
-            lam[M::NS + o] += gp;
+            rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd, lam, gc, sgw);
           else
-            gprec[o] += gp;
+            rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd, lam, gc, nogw);
+        }
+        // emission at time k
+        R xp[4], gxp[4];
+        M::observe(x, xp);
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          gxp[o] = (gxpr && active) ? gxpr[(size_t)o * N] : R(0);
+          if (obs) {
+            const R pr = M::DYN ? x[M::NS + o] : prec[o];
+            const R ipr = M::DYN ? vdiv(R(1), pr) : iprec[o];
+            const R d = xp[o] - ob[o];
+            gxp[o] -= gl[o] * pr * d;
+            const R gp = gl[o] * R(0.5) * (ipr - d * d);
+            if (M::DYN)
+              lam[M::NS + o] += gp;
+            else
+              gprec[o] += gp;
+          }
+        }
+        M::observe_vjp(x, gxp, lam);
+        if (gxs) {
+          if (active) {
+#pragma unroll
+            for (int q = 0; q < S; ++q) lam[q] += gxs[(size_t)q * N];
+          }
+          gxs -= slab;
+        }
+        if (gxpr) gxpr -= (size_t)4 * N;
+#pragma unroll
+        for (int o = 0; o < 4; ++o) ob[o] = obp[o];
+        t1 = t0;
+        t0 = tp;
+      }
+      // chain rule back to theta + scatter (as traj_backward)
+      R gth[M::NSLOT];
+#pragma unroll
+      for (int s = 0; s < M::NSLOT; ++s) gth[s] = R(0);
+      {
+        R th[M::NSLOT];
+        R c6, c12;
+#pragma unroll
+        for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? thv[s] : R(0);
+        M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
+        M::init_state_vjp(lam, gth);
+        M::setup_vjp(th, c6, c12, f.c, gc, gth);
+        if (!M::DYN) {
+#pragma unroll
+          for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gprec[o];
         }
       }
-      M::observe_vjp(x, gxp, lam);
-      if (gxs) {
-        if (active) {
 #pragma unroll
-          for (int q = 0; q < S; ++q) lam[q] += gxs[(size_t)q * N];
-        }
-        gxs -= slab;
-      }
-      if (gxpr) gxpr -= (size_t)4 * N;
-#pragma unroll
-      for (int o = 0; o < 4; ++o) ob[o] = obp[o];
-      t1 = t0;
-      t0 = tp;
-    }
-    // chain rule back to theta + scatter (as traj_backward)
-    R gth[M::NSLOT];
-#pragma unroll
-    for (int s = 0; s < M::NSLOT; ++s) gth[s] = R(0);
-    {
-      R th[M::NSLOT];
-      R c6, c12;
-#pragma unroll
-      for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? thv[s] : R(0);
-      M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
-      M::init_state_vjp(lam, gth);
-      M::setup_vjp(th, c6, c12, f.c, gc, gth);
-if (!M::DYN) {
-#pragma unroll
-  for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gprec[o];
-}
-    }
-#pragma unroll
-    for (int s = 0; s < M::NSLOT; ++s) gloc[s] = M::uses(s) ? gth[s] : R(0);
+      for (int s = 0; s < M::NSLOT; ++s) gloc[s] = M::uses(s) ? gth[s] : R(0);
     }  // consumer
   }    // producer / consumer
   named_bar_sync_all(EPILOGUE);  // gloc is complete (bar.sync orders the shared-memory writes)

@@ -112,3 +112,12 @@ class PeerGradientExchange(object):
 
     def timed_out(self):
         return bool(self.state[2].item())
+
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (call on every rank, after a barrier: peers may still push)."""
+        for q in self._opened:
+            self.lib.vh_peer_buffer_close(C.c_void_p(q))
+        self._opened = []
+        if self._own is not None:
+            self.lib.vh_peer_buffer_destroy(C.c_void_p(self._own))
+            self._own = None
