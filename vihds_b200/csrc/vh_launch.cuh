@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel
 //                      ring and does the part that is serial in lambda: rk_step_adjoint + the emission adjoint.
 // The two halves of a time step (~200 and ~260 instructions) run on two schedulers instead of one after the other on
 // one.  Hand-off: named barriers (full / empty per slot, bar.arrive on one side, bar.sync on the other), data laid out
-// [item][lane] (conflict-free).  fp32 / fp64.  Dynamic-precision models: the NeuralPrecisions weights and the consumer
-// lanes' weight-gradient accumulators [NW][32] sit in shared memory too; the team reduces them after the epilogue.
+// [item][lane] (conflict-free).  fp32 / fp64.  Dynamic-precision models: the NeuralPrecisions weights sit in shared
+// memory too, and a third warp accumulates their gradient (WgradRing).
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
@@ -250,6 +250,35 @@ __device__ __forceinline__ void named_bar_sync_all(int id) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(WS_WARPS * 32) : "memory");
 }
 
+// Dynamic-precision models: the consumer warp does not accumulate the NeuralPrecisions weight gradient itself (112
+// shared-memory read-modify-writes per VJP at 13 inputs -- 40 % of its instructions); it hands the two factors of the
+// outer product (a[NIN], gzp[4], gzd[4]) to a third warp through a two-slot ring, and that warp -- otherwise asleep
+// until the epilogue -- keeps all NW accumulators in registers.
+enum { WG_FULL0 = 7, WG_EMPTY0 = 9 };
+template <typename R, int NIN>
+struct WgradRing {
+  static constexpr int NITEM = NIN + 8;
+  R* buf;  // [2][NITEM][32] + lane
+  int it;
+  __device__ void add(int, R) const {}
+  template <int N2>
+  __device__ void outer(const R* a, const R* gzp, const R* gzd) {
+    const int slot = it & 1;
+    if (it >= 2) named_bar_sync(WG_EMPTY0 + slot);
+    R* s = buf + slot * NITEM * 32;
+#pragma unroll
+    for (int j = 0; j < NIN; ++j) s[j * 32] = a[j];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      s[(NIN + o) * 32] = gzp[o];
+      s[(NIN + 4 + o) * 32] = gzd[o];
+    }
+    __threadfence_block();
+    named_bar_arrive(WG_FULL0 + slot);
+    ++it;
+  }
+};
+
 template <class M, class TB>
 __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<typename M::real> a) {
   typedef typename M::real R;
@@ -267,13 +296,13 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
   enum { FULL0 = 1, EMPTY0 = 3, EPILOGUE = 5, PROLOGUE = 6 };
   const SlotScratch<R> thv{ring + 2 * Ring::SLOT + lane, 64};        // theta by slot, filled once by the whole team
   const SlotScratch<R> gloc{ring + 2 * Ring::SLOT + 32 + lane, 64};  // its cotangent, written by the consumer
-  // dynamic-precision models: NeuralPrecisions weights and the consumer lanes' weight-gradient accumulators [NW][32]
+  // dynamic-precision models: NeuralPrecisions weights and the hand-off ring of the weight-gradient warp
   constexpr int NW = NetInfo<M>::NW;
+  typedef WgradRing<R, M::NIN> WG;
   R* wsm = ring + 2 * Ring::SLOT + M::NSLOT * 64 + (WS_PF + 1) * S * 32;
-  R* gwsm = wsm + NW;
+  R* wgbuf = wsm + ((NW + 3) & ~3);
   if (M::DYN) {
     for (int i = threadIdx.x; i < NW; i += blockDim.x) wsm[i] = a.weights[i];
-    for (int i = threadIdx.x; i < NW * 32; i += blockDim.x) gwsm[i] = R(0);
   }
   const R glq = (a.g_logq_theta && active) ? a.g_logq_theta[n] : R(0);
   const R glp = (a.g_logp_theta && active) ? a.g_logp_theta[n] : R(0);
@@ -367,7 +396,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
 #pragma unroll
       for (int i = 0; i < M::NC; ++i) gc.v[i] = R(0);
       NoGW<R> nogw;
-      StridedGW<R> sgw{gwsm + lane, 32};
+      WG sgw{wgbuf + lane, 0};
       R lam[S], x[S];
       R ob[4] = {R(0), R(0), R(0), R(0)}, obp[4] = {R(0), R(0), R(0), R(0)};
 #pragma unroll
@@ -454,6 +483,48 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
       for (int s = 0; s < M::NSLOT; ++s) gloc[s] = M::uses(s) ? gth[s] : R(0);
     }  // consumer
   }    // producer / consumer
+  if (M::DYN && role == 2) {
+    // ---------------- weight-gradient warp: acc[k] += outer product of every NeuralPrecisions VJP ----------------
+    constexpr int NIN = M::NIN, H = 4 * NIN + 4;
+    R acc[NW > 0 ? NW : 1];
+#pragma unroll
+    for (int i = 0; i < NW; ++i) acc[i] = R(0);
+    const int nev = TB::s * (T - 1);
+    for (int e = 0; e < nev; ++e) {
+      const int slot = e & 1;
+      const R* sb = wgbuf + lane + slot * WG::NITEM * 32;
+      R av[NIN], gp[4], gd[4];
+      named_bar_sync(WG_FULL0 + slot);
+#pragma unroll
+      for (int j = 0; j < NIN; ++j) av[j] = sb[j * 32];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        gp[o] = sb[(NIN + o) * 32];
+        gd[o] = sb[(NIN + 4 + o) * 32];
+      }
+      if (e + 2 < nev) {
+        __threadfence_block();
+        named_bar_arrive(WG_EMPTY0 + slot);
+      }
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        acc[4 * NIN + o] += gp[o];
+        acc[H + 4 * NIN + o] += gd[o];
+#pragma unroll
+        for (int j = 0; j < NIN; ++j) {
+          acc[o * NIN + j] += gp[o] * av[j];
+          acc[H + o * NIN + j] += gd[o] * av[j];
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NW; ++i) {
+      R v = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) atomicAdd(a.d_weights + i, v);
+    }
+  }
   named_bar_sync_all(EPILOGUE);  // gloc is complete (bar.sync orders the shared-memory writes)
   WarpSegRed<R> red(a.d_q_mu, a.d_q_prec, a.P, b, active);
 #pragma unroll 3
@@ -469,17 +540,9 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
       if (src < 0 && src != VH_SLOT_UNUSED) a.d_extra[(size_t)(-1 - src) * N + n] = gloc[s];
       }
       }
-      if (M::DYN) {  // weight gradients: lanes of the consumer -> one atomic per weight per CTA
-      for (int i = role; i < NW; i += WS_WARPS) {
-      R v = gwsm[i * 32 + lane];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) atomicAdd(a.d_weights + i, v);
-      }
-      }
-      }
-      
-      inline int pick_block(int N) {
+    }
+
+inline int pick_block(int N) {
   // small batches are latency-bound: spread warps over as many SMs as possible (148 SMs x 4 schedulers)
   if (N <= 148 * 4 * 32) return 32;
   if (N <= 148 * 8 * 64) return 64;
@@ -540,9 +603,9 @@ struct BwdLauncher {
   void launch_bwd_variant(bool ws, int grid, int block, size_t smem) {
     if (ws) {
       // hand-off ring | slot scratch | checkpoint staging ring
-      // | NeuralPrecisions weights + weight-gradient accumulators
+      // | NeuralPrecisions weights + hand-off ring of the weight-gradient warp
       const size_t ring = sizeof(R) * (2 * WsRing<M, TB>::SLOT + (size_t)M::NSLOT * 64 + (size_t)(WS_PF + 1) * M::S * 32 +
-                                       (size_t)NetInfo<M>::NW * 33);
+                                       (size_t)((NetInfo<M>::NW + 3) & ~3) + 2 * (M::NIN + 8) * 32);
       if (ring > 48 * 1024)
         cudaFuncSetAttribute(elbo_bwd_ws_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
       elbo_bwd_ws_kernel<M, TB><<<(a.N + 31) / 32, WS_WARPS * 32, ring, stream>>>(a);

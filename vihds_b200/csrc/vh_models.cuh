@@ -609,6 +609,7 @@ struct LinPrecNet {
     for (int j = 1; j < NIN; ++j) a[j] = vtanh(species[j - 1]);
 #pragma unroll
     for (int j = 0; j < NIN; ++j) ga[j] = R(0);
+    R gzp[4], gzd[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       R zp = w[4 * NIN + o], zd = w[(4 * NIN + 4) + 4 * NIN + o];
@@ -619,17 +620,12 @@ struct LinPrecNet {
       }
       const R sp = sigmoid(zp), sd = sigmoid(zd);
       gv[o] -= g[o] * sd;
-      const R gzp = g[o] * sp * (R(1) - sp);
-      const R gzd = -g[o] * v[o] * sd * (R(1) - sd);
-      gw.add(4 * NIN + o, gzp);
-      gw.add((4 * NIN + 4) + 4 * NIN + o, gzd);
+      gzp[o] = g[o] * sp * (R(1) - sp);
+      gzd[o] = -g[o] * v[o] * sd * (R(1) - sd);
 #pragma unroll
-      for (int j = 0; j < NIN; ++j) {
-        gw.add(o * NIN + j, gzp * a[j]);
-        gw.add((4 * NIN + 4) + o * NIN + j, gzd * a[j]);
-        ga[j] += gzp * w[o * NIN + j] + gzd * w[(4 * NIN + 4) + o * NIN + j];
-      }
+      for (int j = 0; j < NIN; ++j) ga[j] += gzp[o] * w[o * NIN + j] + gzd[o] * w[(4 * NIN + 4) + o * NIN + j];
     }
+    gw.template outer<NIN>(a, gzp, gzd);  // weight gradients (in place, or handed to another warp)
 #pragma unroll
     for (int j = 1; j < NIN; ++j) gspecies[j - 1] += ga[j] * (R(1) - a[j] * a[j]);
   }

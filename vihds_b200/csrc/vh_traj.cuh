@@ -78,15 +78,36 @@ struct Call {
 };
 
 // weight-gradient accumulator handles -------------------------------------------------------------------------
+// outer<NIN>(a, gzp, gzd): one NeuralPrecisions evaluation's contribution to the flat weight gradient
+//   Wp[o][j] += gzp[o] a[j], bp[o] += gzp[o], Wd[o][j] += gzd[o] a[j], bd[o] += gzd[o]      (layout: LinPrecNet)
+template <int NIN, typename GW, typename R>
+VH_HD void prec_outer_adds(GW& gw, const R* a, const R* gzp, const R* gzd) {
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    gw.add(4 * NIN + o, gzp[o]);
+    gw.add((4 * NIN + 4) + 4 * NIN + o, gzd[o]);
+#pragma unroll
+    for (int j = 0; j < NIN; ++j) {
+      gw.add(o * NIN + j, gzp[o] * a[j]);
+      gw.add((4 * NIN + 4) + o * NIN + j, gzd[o] * a[j]);
+    }
+  }
+}
 template <typename R>
 struct NoGW {
   VH_HD void add(int, R) const {}
+  template <int NIN>
+  VH_HD void outer(const R*, const R*, const R*) const {}
 };
 template <typename R>
 struct StridedGW {  // element k of this thread's accumulators lives at base[k * stride]
   R* base;
   int stride;
   VH_HD void add(int k, R v) const { base[k * stride] += v; }
+  template <int NIN>
+  VH_HD void outer(const R* a, const R* gzp, const R* gzd) const {
+    prec_outer_adds<NIN>(*this, a, gzp, gzd);
+  }
 };
 
 // full right-hand side over the ODE state (species + dynamic-precision states) ---------------------------------
