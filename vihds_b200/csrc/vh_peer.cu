@@ -57,10 +57,11 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(size_t n, size_t n_
       inbox[((size_t)par * world + rank) * n_pad + i] = val;
     }
   }
-  __threadfence_system();
   __syncthreads();  // every thread of this CTA has pushed and has read epoch / step
-  // B. last block publishes
+  // B. last block publishes.  One system-scope fence per CTA, by the thread that takes the ticket: the CTA barrier
+  // orders the other threads' stores before it and fences are cumulative (the cooperative-groups grid-sync pattern).
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned long long ticket = atomicAdd((unsigned long long*)(state + 1), 1ULL);
     if (ticket == (unsigned long long)gridDim.x - 1) {
       __threadfence_system();
