@@ -426,12 +426,14 @@ class GraphedStep(object):
             self._copy_stream = torch.cuda.Stream()
             self._u_ready, self._u_free = torch.cuda.Event(), torch.cuda.Event()
             self._u_free.record(cur)
-        with torch.cuda.stream(self._copy_stream):  # first: the big copy runs under everything the host does next
+        # the small copies first: host-to-device copies of all streams queue on one copy engine, and the encoder graph
+        # must not wait behind the big one (18 MB of u at the synthetic size)
+        self.load_batch(batch)
+        self.draw_conditioner()
+        with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(self._u_free)  # the previous step's reverse sweep still reads the old u
             self.load_u(u)
             self._u_ready.record(self._copy_stream)
-        self.load_batch(batch)
-        self.draw_conditioner()
         if self.use_graphs:
             self.g_pre.replay()
             cur.wait_event(self._u_ready)
