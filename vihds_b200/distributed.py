@@ -72,6 +72,10 @@ def allreduce_max(value, group, device):
     return float(t.item())
 
 
+class ExchangeUnavailable(RuntimeError):
+    """Raised on EVERY rank when any rank could not set the peer exchange up (the caller then takes the NCCL path)."""
+
+
 class PeerGradientExchange(object):
     """Exchange buffers of the fused all-reduce + Adam kernel (include/vihds_b200.h: vh_peer_*, vh_adam_allreduce_step).
 
@@ -88,27 +92,44 @@ class PeerGradientExchange(object):
         nbytes = lib.vh_peer_buffer_bytes(vdt, n, self.world)
         handle = (C.c_ubyte * 64)()
         own = C.c_void_p()
+        self._own, self._opened, err = None, [], None
+        # Every rank runs every collective below whatever happens locally, and all ranks reach the same verdict:
+        # a rank that cannot create or map a buffer (no peer access, IPC unavailable) must not leave the others waiting.
         with torch.cuda.device(device):
-            L.check(lib.vh_peer_buffer_create(nbytes, C.byref(own), handle))
-            handles = [bytes(handle)]
+            try:
+                L.check(lib.vh_peer_buffer_create(nbytes, C.byref(own), handle))
+                self._own = own.value
+            except RuntimeError as e:
+                err = str(e)
+            mine = bytes(handle) if err is None else None
+            handles = [mine]
             if group is not None:
                 handles = [None] * self.world
-                dist.all_gather_object(handles, bytes(handle), group=group)
-            ptrs, self._opened = [], []
-            for r in range(self.world):
-                if r == self.rank:
-                    ptrs.append(own.value)
-                    continue
-                q = C.c_void_p()
-                buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
-                L.check(lib.vh_peer_buffer_open(buf, C.byref(q)))
-                ptrs.append(q.value)
-                self._opened.append(q.value)
-        self._own = own.value
+                dist.all_gather_object(handles, mine, group=group)
+            ptrs = []
+            if err is None and all(h is not None for h in handles):
+                try:
+                    for r in range(self.world):
+                        if r == self.rank:
+                            ptrs.append(own.value)
+                            continue
+                        q = C.c_void_p()
+                        buf = (C.c_ubyte * 64).from_buffer_copy(handles[r])
+                        L.check(lib.vh_peer_buffer_open(buf, C.byref(q)))
+                        ptrs.append(q.value)
+                        self._opened.append(q.value)
+                except RuntimeError as e:
+                    err = str(e)
+            elif err is None:
+                err = "a peer could not create its exchange buffer"
+            ok = torch.tensor([0 if err else 1], dtype=torch.int32, device=device)
+            if group is not None:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)  # also: nobody pushes before everybody has mapped
+            if int(ok.item()) == 0:
+                self.close()
+                raise ExchangeUnavailable(err or "a peer could not map the exchange buffers")
         self.peers = torch.tensor(ptrs, dtype=torch.int64, device=device)
         self.state = torch.zeros(4, dtype=torch.int64, device=device)  # epoch, ticket, timed_out, -
-        if group is not None:
-            dist.barrier(group=group)  # nobody pushes before everybody has mapped everybody
 
     def timed_out(self):
         return bool(self.state[2].item())

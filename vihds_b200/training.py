@@ -194,9 +194,13 @@ class GraphedStep(object):
         self.d_extra = z(len(self.extras), N) if (self.extras and hasattr(ode, "offset_layer")) else None
         self.exchange = None
         if self.pg is not None and (exchange or os.environ.get("VIHDS_ALLREDUCE", "peer")) != "nccl":
-            from .distributed import PeerGradientExchange
+            from .distributed import ExchangeUnavailable, PeerGradientExchange
             opt = training.optimizer
-            self.exchange = PeerGradientExchange(opt.flat.numel(), opt.flat.dtype, opt.flat.device, self.pg)
+            try:
+                self.exchange = PeerGradientExchange(opt.flat.numel(), opt.flat.dtype, opt.flat.device, self.pg)
+            except ExchangeUnavailable as e:  # same verdict on every rank: ncclAllReduce + Adam instead
+                import warnings
+                warnings.warn("peer gradient exchange unavailable (%s): using ncclAllReduce" % e)
         self.ready = False
         self.steps_done = 0
         self.ev_hot = None  # optional (start, end) CUDA events around the reverse-sweep kernel (forces the eager path)
