@@ -201,12 +201,17 @@ template <typename R>
 __global__ void adam_dev_kernel(size_t n, R* __restrict__ p, R* __restrict__ g, R* __restrict__ m, R* __restrict__ v,
                                 const double* __restrict__ hyper, long long* step, int zero_grad) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const double t = (double)(*(volatile long long*)step + 1);
+  __shared__ R s_bc[2];
+  if (threadIdx.x == 0) {  // the bias corrections: two double-precision pow per CTA, not per thread
+    const double t = (double)(*(volatile long long*)step + 1);
+    s_bc[0] = (R)(1.0 - pow(hyper[1], t));
+    s_bc[1] = (R)sqrt(1.0 - pow(hyper[2], t));
+  }
+  __syncthreads();
   if (i < n) {
     const double lr = hyper[0], b1d = hyper[1], b2d = hyper[2];
     const R b1 = (R)b1d, b2 = (R)b2d, eps = (R)hyper[3];
-    const R bc1 = (R)(1.0 - pow(b1d, t));
-    const R bc2_sqrt = (R)sqrt(1.0 - pow(b2d, t));
+    const R bc1 = s_bc[0], bc2_sqrt = s_bc[1];
     const R gi = g[i];
     const R mi = m[i] + (gi - m[i]) * (R(1) - b1);
     const R vi = b2 * v[i] + (R(1) - b2) * gi * gi;
@@ -216,7 +221,7 @@ __global__ void adam_dev_kernel(size_t n, R* __restrict__ p, R* __restrict__ g, 
     p[i] -= ((R)lr / bc1) * (mi / denom);
     if (zero_grad) g[i] = R(0);
   }
-  __syncthreads();  // every thread of this CTA has read step[0]
+  __syncthreads();  // this CTA has read step[0] (thread 0, above) and is done
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned long long ticket = atomicAdd((unsigned long long*)(step + 1), 1ULL);

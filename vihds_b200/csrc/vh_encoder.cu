@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
 #define ENC_WG_BCHUNK 32
 template <typename R>
 __global__ void __launch_bounds__(128) enc_lin_wgrad_kernel(const EncDims d, const EncPtrs<R> p, int b_per_block) {
-  __shared__ R sh[ENC_WG_BCHUNK * ENC_WG_HMAX];
+  __shared__ __align__(16) R sh[ENC_WG_BCHUNK * ENC_WG_HMAX];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int b0 = blockIdx.y * b_per_block, b1 = min(d.B, b0 + b_per_block);
   for (int o0 = 0; o0 < d.H; o0 += ENC_WG_HMAX) {
@@ -401,10 +401,19 @@ __global__ void __launch_bounds__(128) enc_lin_wgrad_kernel(const EncDims d, con
       }
       __syncthreads();
       if (i < d.NLIN) {
+        // the d_pre row is a broadcast operand: read it 16 bytes at a time (one shared-memory load per 4 (2) FMAs
+        // instead of one per FMA -- the loop was bound by the load/store unit, not by the FMA pipe)
+        constexpr int V = 16 / sizeof(R);
+        struct alignas(16) Vec { R v[V]; };
         for (int r = 0; r < nb; ++r) {
           const R x = p.pooled[(size_t)(bb + r) * d.NLIN + i];
+          const Vec* row = reinterpret_cast<const Vec*>(sh + r * ENC_WG_HMAX);
 #pragma unroll
-          for (int o = 0; o < ENC_WG_HMAX; ++o) acc[o] += sh[r * ENC_WG_HMAX + o] * x;
+          for (int o = 0; o < ENC_WG_HMAX / V; ++o) {
+            const Vec q = row[o];
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[o * V + e] += q.v[e] * x;
+          }
         }
       }
     }
