@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include "vh_bb.cuh"
+#include "vh_bb_mma.cuh"
 #include "vh_launch.cuh"
 
 namespace vh {
@@ -347,7 +348,57 @@ struct BbLauncher {
   Call<R> a;
   cudaStream_t stream;
   template <class F, class TB>
+  int run_mma_dispatch(const Call<float>& af) {
+    return run_mma<F, TB>(af);
+  }
+  template <class F, class TB>
+  int run_mma_dispatch(const Call<double>&) {
+    return VH_ERR_UNSUPPORTED;
+  }
+  // fp32: the warp-level tensor-core kernels (vh_bb_mma.cuh) unless VIHDS_BB_IMPL=scalar (read per call: tests
+  // compare the two implementations in one process); fp64: always the scalar kernels
+  static bool use_mma() {
+    if (sizeof(R) != 4) return false;
+    const char* m = getenv("VIHDS_BB_IMPL");
+    return !m || strcmp(m, "scalar") != 0;
+  }
+  template <class F, class TB>
+  int run_mma(const Call<float>& af) {
+    cudaError_t e = cudaSuccess;
+    if (BWD) {
+#if VH_BB_DIR != 0
+      const size_t smem = bbm::Smem<F>::bwd_bytes(TB::s);
+      if (smem > 48 * 1024) e = cudaFuncSetAttribute(bbm::bbm_bwd_kernel<F, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(smem=%zu) failed: %s", smem, cudaGetErrorString(e));
+        return VH_ERR_CUDA;
+      }
+      if (af.d_q_mu && af.P > 0) {
+        cudaMemsetAsync(af.d_q_mu, 0, sizeof(float) * (size_t)af.B * af.P, stream);
+        cudaMemsetAsync(af.d_q_prec, 0, sizeof(float) * (size_t)af.B * af.P, stream);
+      }
+      cudaMemsetAsync(af.d_weights, 0, sizeof(float) * F::L::total, stream);
+      bbm::bbm_bwd_kernel<F, TB><<<(af.N + bbm::ROWS - 1) / bbm::ROWS, 64, smem, stream>>>(af);
+#endif
+    } else {
+#if VH_BB_DIR != 1
+      const size_t smem = bbm::Smem<F>::fwd_bytes;
+      // latency regime: one warp per CTA spreads the 16-trajectory groups over every SM; otherwise 4 warps share the tiles
+      const int warps = af.N <= 148 * 4 * bbm::ROWS ? 1 : 4;
+      const int groups = (af.N + bbm::ROWS - 1) / bbm::ROWS;
+      bbm::bbm_fwd_kernel<F, TB><<<(groups + warps - 1) / warps, warps * 32, smem, stream>>>(af);
+#endif
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("%s launch failed: %s", BWD ? "bbm_bwd_kernel" : "bbm_fwd_kernel", cudaGetErrorString(e));
+      return VH_ERR_CUDA;
+    }
+    return VH_OK;
+  }
+  template <class F, class TB>
   int run() {
+    if (use_mma()) return run_mma_dispatch<F, TB>(a);
     const int block = a.N <= 148 * 4 * 32 ? 32 : 64;
     const int grid = (a.N + block - 1) / block;
     const size_t smem = sizeof(R) * (((F::L::total + 3) & ~3) + (size_t)block * F::ROWL::ROW);
