@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define VH_ABI_VERSION 1
+#define VH_ABI_VERSION 2
 
 enum vh_status {
   VH_OK = 0,
@@ -191,12 +191,15 @@ int vh_iw_moments(const vh_problem* p, const void* w, const void* x_states, cons
 int vh_adam_step(int dtype, size_t n, void* param, const void* grad, void* exp_avg, void* exp_avg_sq, double lr,
                  double beta1, double beta2, double eps, int step, void* stream);
 /* Same update with the hyper-parameters and the step counter ON THE DEVICE, so that the launch can be captured in a
- * CUDA graph and replayed: hyper = double[4] {lr, beta1, beta2, eps}; step = int64[2]: step[0] = the number of updates
+ * CUDA graph and replayed: hyper = double[4] {lr, beta1, beta2, eps}; step = int64[4]: step[0] = the number of updates
  * done so far (the call uses step[0]+1 for the bias correction and increments it when its last thread block retires),
- * step[1] = scratch ticket counter, zero on entry and on exit.  zero_grad != 0: grad is cleared once it has been
- * consumed (optimizer.zero_grad() of the next step, training.py:333, without a launch of its own). */
+ * step[1] = scratch ticket counter, zero on entry and on exit, step[2] = number of calls skipped by the guard.
+ * zero_grad != 0: grad is cleared once it has been consumed (optimizer.zero_grad() of the next step, training.py:333,
+ * without a launch of its own).  guard: device pointer to the step's cost (or NULL): if it is NaN the parameters and
+ * moments are left untouched -- the reference tests torch.isnan(elbo) BEFORE optimizer.step() (training.py:331-336) --
+ * the gradient is still cleared and step[2] is incremented instead of step[0]. */
 int vh_adam_step_dev(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq, const void* hyper,
-                     void* step, int zero_grad, void* stream);
+                     void* step, int zero_grad, const void* guard, void* stream);
 
 /* cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream): the step's host <-> device copies (batch, u, conditioner
  * weights: `.to(device)` in vihds/training.py:326-329, vae.py:22-24) without a tensor library in between.  Host memory
@@ -213,12 +216,16 @@ int vh_copy_async(void* dst, const void* src, size_t bytes, void* stream);
  *   vh_peer_buffer_create   cudaMalloc + zero it + CUDA-IPC handle (64 bytes) to send to the peers   [the only
  *   vh_peer_buffer_open     map a peer's buffer from its handle (peer access enabled lazily)           allocation the
  *   vh_peer_buffer_close / _destroy                                                                    library makes]
- *   vh_adam_allreduce_step  param / grad / exp_avg / exp_avg_sq / hyper / step as for vh_adam_step_dev (the gradient
- *                           is cleared); state = int64[4] {epoch, ticket scratch, timed_out, 0}, zero-initialised,
- *                           owned by the caller and NEVER rewound (every rank must make the same sequence of calls);
- *                           peers = DEVICE array of `world` pointers, entry r = this process's mapping of rank r's
- *                           exchange buffer (entry `rank` = its own).  timed_out != 0: a peer's flag did not arrive
- *                           within ~10 s (the update of that call is invalid). */
+ *   vh_adam_allreduce_step  param / grad / exp_avg / exp_avg_sq / hyper / step / guard as for vh_adam_step_dev (the
+ *                           gradient is cleared); state = int64[4] {epoch, ticket scratch, timed_out, skipped steps},
+ *                           zero-initialised, owned by the caller and NEVER rewound (every rank must make the same
+ *                           sequence of calls); peers = DEVICE array of `world` pointers, entry r = this process's
+ *                           mapping of rank r's exchange buffer (entry `rank` = its own).  A NaN guard on ANY rank makes
+ *                           EVERY rank skip the update of that call (state[3], step[2] count them).  timed_out != 0
+ *                           (sticky): a peer's flag did not arrive within timeout_s seconds (<= 0: 10 s, measured with
+ *                           %globaltimer); the thread blocks that saw the timeout skip their part of the update and
+ *                           every later call returns without touching anything -- the host must check state[2] whenever
+ *                           it synchronises and stop. */
 #define VH_PEER_MAX_WORLD 16
 size_t vh_peer_buffer_bytes(int dtype, size_t n, int world);
 int vh_peer_buffer_create(size_t bytes, void** dev_ptr, void* handle64);
@@ -227,7 +234,7 @@ int vh_peer_buffer_close(void* dev_ptr);
 int vh_peer_buffer_destroy(void* dev_ptr);
 int vh_adam_allreduce_step(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq,
                            const void* hyper, void* step, void* state, int rank, int world, const void* peers,
-                           void* stream);
+                           const void* guard, double timeout_s, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Fused amortised encoder q(theta | x, d) (vihds/encoders.py:16-55 ConditionalEncoder, :126-253 Q_Local / Q_Global_Cond
@@ -261,11 +268,13 @@ int vh_encoder_fwd(const vh_encoder_desc* e, const vh_encoder_io* io, void* stre
 int vh_encoder_bwd(const vh_encoder_desc* e, const vh_encoder_io* io, const vh_encoder_grads* g, void* stream);
 
 /* Device conditioner (vihds/ode.py:43-58 OdeModel.device_conditioner with param = ones, :99-116 DeviceConditioner):
- * out[k][n] = (plus_one[k] ? 1 : 0) + relu(dot(w[k], dev_1hot[n % B] * rel[k])),  n = b*IW + i.  `n % B` reproduces the
- * reference's repeat([n_iwae, 1]) + reshape, which hands sample (b, i) the conditioner row (b*IW + i) % B.
- * rel, w: [n_cond][D];  plus_one[k] = the parameter is listed in data.default_devices. */
-int vh_device_conditioner(int dtype, int B, int IW, int D, int n_cond, const void* dev_1hot, const void* rel, const void* w,
-                          const int* plus_one, void* out, void* stream);
+ * out[k][n] = (plus_one[k] ? 1 : 0) + relu(dot(w[k], dev_1hot[m % B_global] * rel[k])),  m = (b_offset + b)*IW + i,
+ * n = b*IW + i.  `m % B_global` reproduces the reference's repeat([n_iwae, 1]) + reshape, which hands sample (b, i) of
+ * the batch the conditioner row (b*IW + i) % B.  dev_1hot is the one-hot table of the GLOBAL batch [B_global][D]; a rank
+ * holding the slab of individuals [b_offset, b_offset + B) gets exactly the rows a single process would compute
+ * (one GPU: B_global = B, b_offset = 0).  rel, w: [n_cond][D];  plus_one[k] = the parameter is in data.default_devices. */
+int vh_device_conditioner(int dtype, int B, int IW, int D, int n_cond, int B_global, int b_offset, const void* dev_1hot,
+                          const void* rel, const void* w, const int* plus_one, void* out, void* stream);
 
 #ifdef __cplusplus
 }

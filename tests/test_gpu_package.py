@@ -179,7 +179,7 @@ def test_graphed_step_equals_eager_steps(use_graphs):
         costs_b.append(float(gs.step().item()))
     assert np.allclose(costs_a, costs_b, rtol=1e-5), (costs_a, costs_b)
     assert _rel(tr_b.optimizer.flat.cpu().numpy(), tr_a.optimizer.flat.cpu().numpy()) < 1e-4
-    assert tr_b.optimizer.step_dev.tolist() == [3, 0]
+    assert tr_b.optimizer.step_dev.tolist() == [3, 0, 0, 0]
 
 
 def test_evaluation_moments_match_numpy_reduction():
@@ -273,9 +273,19 @@ def test_device_conditioner_kernel_matches_reference_quirk():
     plus = torch.tensor([1, 1], dtype=torch.int32, device="cuda")
     out = torch.zeros(2, B * IW, device="cuda")
     p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
-    L.check(L.load().vh_device_conditioner(0, B, IW, D, 2, p(dev_1hot), p(rel), p(w), p(plus), p(out), None))
+    L.check(L.load().vh_device_conditioner(0, B, IW, D, 2, B, 0, p(dev_1hot), p(rel), p(w), p(plus), p(out), None))
     torch.cuda.synchronize()
     assert torch.allclose(out, ref, rtol=1e-6, atol=1e-6)
+    # sharded over individuals: every slab, computed from the GLOBAL one-hot table and its offset, must reproduce the
+    # rows of the single-process result (sample (b, i) of the global batch gets individual (b*IW + i) % B_global)
+    from vihds_b200.distributed import shard_bounds
+    for world in (2, 5):
+        for rank in range(world):
+            lo, hi = shard_bounds(B, world, rank)
+            part = torch.zeros(2, (hi - lo) * IW, device="cuda")
+            L.check(L.load().vh_device_conditioner(0, hi - lo, IW, D, 2, B, lo, p(dev_1hot), p(rel), p(w), p(plus), p(part), None))
+            torch.cuda.synchronize()
+            assert torch.equal(part, out[:, lo * IW:hi * IW])
 
 
 @pytest.mark.parametrize("spec", ["dr_constant_icml", "dr_blackbox_icml", "relay_constant_precisions"])

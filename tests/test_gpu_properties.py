@@ -279,15 +279,55 @@ def test_adam_dev_counts_steps_and_clears_the_gradient():
         pa, pb = p0.clone(), p0.clone()
         ma, va, mb, vb = (torch.zeros(n, device="cuda") for _ in range(4))
         hyper = torch.tensor([0.01, 0.9, 0.999, 1e-8], dtype=torch.float64, device="cuda")
-        step = torch.zeros(2, dtype=torch.int64, device="cuda")
+        step = torch.zeros(4, dtype=torch.int64, device="cuda")
+        good = torch.tensor([1.5], device="cuda")
         for it in range(1, 4):
             gr = torch.randn(n, generator=g).cuda()
             ga = gr.clone()
-            L.check(lib.vh_adam_step_dev(0, n, _p(pa), _p(ga), _p(ma), _p(va), _p(hyper), _p(step), it % 2, None))
+            L.check(lib.vh_adam_step_dev(0, n, _p(pa), _p(ga), _p(ma), _p(va), _p(hyper), _p(step), it % 2,
+                                         _p(good) if it == 2 else None, None))
             L.check(lib.vh_adam_step(0, n, _p(pb), _p(gr), _p(mb), _p(vb), 0.01, 0.9, 0.999, 1e-8, it, None))
-            assert step.tolist() == [it, 0]
+            assert step.tolist() == [it, 0, 0, 0]
             assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-7)
             assert torch.equal(ga, torch.zeros_like(ga) if it % 2 else gr)
+
+
+def test_adam_dev_nan_cost_leaves_parameters_and_moments_untouched():
+    """The device-side guard of the graphed step (vihds/training.py:331-336 checks isnan BEFORE optimizer.step()): with a
+    NaN cost -- and therefore NaN gradients -- the call must not touch parameters or moments, must not count as a step,
+    must still clear the gradient and must count the refusal; the next good step continues with the old step count."""
+    lib = L.load()
+    n = 70001
+    g = torch.Generator().manual_seed(5)
+    pa = torch.randn(n, generator=g).cuda()
+    ma, va = torch.rand(n, generator=g).cuda(), torch.rand(n, generator=g).cuda()
+    p0, m0, v0 = pa.clone(), ma.clone(), va.clone()
+    hyper = torch.tensor([0.01, 0.9, 0.999, 1e-8], dtype=torch.float64, device="cuda")
+    step = torch.tensor([7, 0, 0, 0], dtype=torch.int64, device="cuda")
+    bad = torch.tensor([float("nan")], device="cuda")
+    ga = torch.full((n,), float("nan"), device="cuda")
+    L.check(lib.vh_adam_step_dev(0, n, _p(pa), _p(ga), _p(ma), _p(va), _p(hyper), _p(step), 1, _p(bad), None))
+    torch.cuda.synchronize()
+    assert torch.equal(pa, p0) and torch.equal(ma, m0) and torch.equal(va, v0)
+    assert step.tolist() == [7, 0, 1, 0] and not ga.any()
+    # one-rank exchange kernel: same contract
+    from vihds_b200.distributed import PeerGradientExchange
+    ex = PeerGradientExchange(n, torch.float32, torch.device("cuda", 0))
+    ga = torch.full((n,), float("nan"), device="cuda")
+    L.check(lib.vh_adam_allreduce_step(0, n, _p(pa), _p(ga), _p(ma), _p(va), _p(hyper), _p(step), _p(ex.state), 0, 1,
+                                       _p(ex.peers), _p(bad), 0.0, None))
+    torch.cuda.synchronize()
+    assert torch.equal(pa, p0) and torch.equal(ma, m0) and torch.equal(va, v0)
+    assert step.tolist() == [7, 0, 2, 0] and ex.state.tolist() == [1, 0, 0, 1] and not ga.any()
+    gr = torch.randn(n, generator=g).cuda()
+    ga, pb, mb, vb = gr.clone(), p0.clone(), m0.clone(), v0.clone()
+    good = torch.tensor([3.0], device="cuda")
+    L.check(lib.vh_adam_allreduce_step(0, n, _p(pa), _p(ga), _p(ma), _p(va), _p(hyper), _p(step), _p(ex.state), 0, 1,
+                                       _p(ex.peers), _p(good), 0.0, None))
+    L.check(lib.vh_adam_step(0, n, _p(pb), _p(gr), _p(mb), _p(vb), 0.01, 0.9, 0.999, 1e-8, 8, None))
+    torch.cuda.synchronize()
+    assert step.tolist() == [8, 0, 2, 0] and torch.allclose(pa, pb, rtol=1e-6, atol=1e-7)
+    ex.close()
 
 
 def test_fused_allreduce_adam_single_rank_equals_adam():
@@ -301,15 +341,15 @@ def test_fused_allreduce_adam_single_rank_equals_adam():
         pa, pb = p0.clone(), p0.clone()
         ma, va, mb, vb = (torch.zeros(n, device="cuda") for _ in range(4))
         hyper = torch.tensor([0.01, 0.9, 0.999, 1e-8], dtype=torch.float64, device="cuda")
-        step = torch.zeros(2, dtype=torch.int64, device="cuda")
+        step = torch.zeros(4, dtype=torch.int64, device="cuda")
         ex = PeerGradientExchange(n, torch.float32, torch.device("cuda", 0))  # closed at the end of the loop body
         for it in range(1, 5):
             gr = torch.randn(n, generator=g).cuda()
             ga = gr.clone()
             L.check(lib.vh_adam_allreduce_step(0, n, _p(pa), _p(ga), _p(ma), _p(va), _p(hyper), _p(step), _p(ex.state),
-                                               0, 1, _p(ex.peers), None))
+                                               0, 1, _p(ex.peers), None, 0.0, None))
             L.check(lib.vh_adam_step(0, n, _p(pb), _p(gr), _p(mb), _p(vb), 0.01, 0.9, 0.999, 1e-8, it, None))
-            assert step.tolist()[0] == it and ex.state.tolist()[:3] == [it, 0, 0]
+            assert step.tolist()[0] == it and ex.state.tolist() == [it, 0, 0, 0]
             assert torch.allclose(pa, pb, rtol=1e-6, atol=1e-7)
             assert not ga.any()
         torch.cuda.synchronize()

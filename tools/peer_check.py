@@ -22,14 +22,14 @@ for n in (1000, 44411, 1 << 20):
     pa, pb = p0.clone(), p0.clone()
     ma, va, mb, vb = (torch.zeros(n, device=dev) for _ in range(4))
     hyper = torch.tensor([0.01, 0.9, 0.999, 1e-8], dtype=torch.float64, device=dev)
-    step = torch.zeros(2, dtype=torch.int64, device=dev)
+    step = torch.zeros(4, dtype=torch.int64, device=dev)
     ex = PeerGradientExchange(n, torch.float32, dev, pg)
     gr_gen = torch.Generator().manual_seed(100 + rank)
     for it in range(1, 8):
         gr = torch.randn(n, generator=gr_gen).to(dev)
         ga = gr.clone()
         L.check(lib.vh_adam_allreduce_step(0, n, _p(pa), _p(ga), _p(ma), _p(va), _p(hyper), _p(step), _p(ex.state),
-                                           rank, world, _p(ex.peers), None))
+                                           rank, world, _p(ex.peers), None, 0.0, None))
         dist.all_reduce(gr, group=pg)
         L.check(lib.vh_adam_step(0, n, _p(pb), _p(gr), _p(mb), _p(vb), 0.01, 0.9, 0.999, 1e-8, it, None))
     torch.cuda.synchronize()

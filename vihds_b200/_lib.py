@@ -93,7 +93,7 @@ def load():
     lib.vh_iw_moments.argtypes = [C.POINTER(vh_problem)] + [C.c_void_p] * 9
     lib.vh_adam_step.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                  C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
-    lib.vh_adam_step_dev.argtypes = [C.c_int, C.c_size_t] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p]
+    lib.vh_adam_step_dev.argtypes = [C.c_int, C.c_size_t] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p]
     lib.vh_copy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.vh_peer_buffer_bytes.restype = C.c_size_t
     lib.vh_peer_buffer_bytes.argtypes = [C.c_int, C.c_size_t, C.c_int]
@@ -101,12 +101,13 @@ def load():
     lib.vh_peer_buffer_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     lib.vh_peer_buffer_close.argtypes = [C.c_void_p]
     lib.vh_peer_buffer_destroy.argtypes = [C.c_void_p]
-    lib.vh_adam_allreduce_step.argtypes = [C.c_int, C.c_size_t] + [C.c_void_p] * 7 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.vh_adam_allreduce_step.argtypes = ([C.c_int, C.c_size_t] + [C.c_void_p] * 7 +
+                                           [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p])
     lib.vh_iwae_fwd_bwd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 10
-    lib.vh_device_conditioner.argtypes = [C.c_int] * 5 + [C.c_void_p] * 6
+    lib.vh_device_conditioner.argtypes = [C.c_int] * 7 + [C.c_void_p] * 6
     lib.vh_encoder_fwd.argtypes = [C.POINTER(vh_encoder_desc), C.POINTER(vh_encoder_io), C.c_void_p]
     lib.vh_encoder_bwd.argtypes = [C.POINTER(vh_encoder_desc), C.POINTER(vh_encoder_io), C.POINTER(vh_encoder_grads), C.c_void_p]
-    if lib.vh_abi_version() != 1:
+    if lib.vh_abi_version() != 2:
         raise RuntimeError("vihds_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -197,28 +197,37 @@ __global__ void adam_kernel(size_t n, R* __restrict__ p, const R* __restrict__ g
 // graph-capturable variant: hyper-parameters and step counter are read from device memory.  step[0] = updates done so
 // far, step[1] = ticket counter: every CTA reads step[0] before it takes a ticket, the last one bumps the counter
 // (no separate increment launch).  zero_grad: the gradient is cleared once consumed (no separate fill launch).
+// guard: the step's cost on the device (or NULL).  A NaN cost means NaN gradients (training.py:331-333 stops BEFORE
+// optimizer.step()): the update of parameters and moments is skipped, the gradient is still cleared, step[0] stays and
+// step[2] counts the skipped call -- the host reads it when it next looks at the cost.
 template <typename R>
 __global__ void adam_dev_kernel(size_t n, R* __restrict__ p, R* __restrict__ g, R* __restrict__ m, R* __restrict__ v,
-                                const double* __restrict__ hyper, long long* step, int zero_grad) {
+                                const double* __restrict__ hyper, long long* step, int zero_grad, const R* __restrict__ guard) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   __shared__ R s_bc[2];
+  __shared__ int s_skip;
   if (threadIdx.x == 0) {  // the bias corrections: two double-precision pow per CTA, not per thread
     const double t = (double)(*(volatile long long*)step + 1);
     s_bc[0] = (R)(1.0 - pow(hyper[1], t));
     s_bc[1] = (R)sqrt(1.0 - pow(hyper[2], t));
+    const R c = guard ? *guard : R(0);
+    s_skip = c != c;
   }
   __syncthreads();
+  const bool skip = s_skip != 0;
   if (i < n) {
-    const double lr = hyper[0], b1d = hyper[1], b2d = hyper[2];
-    const R b1 = (R)b1d, b2 = (R)b2d, eps = (R)hyper[3];
-    const R bc1 = s_bc[0], bc2_sqrt = s_bc[1];
-    const R gi = g[i];
-    const R mi = m[i] + (gi - m[i]) * (R(1) - b1);
-    const R vi = b2 * v[i] + (R(1) - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const R denom = vsqrt(vi) / bc2_sqrt + eps;
-    p[i] -= ((R)lr / bc1) * (mi / denom);
+    if (!skip) {
+      const double lr = hyper[0], b1d = hyper[1], b2d = hyper[2];
+      const R b1 = (R)b1d, b2 = (R)b2d, eps = (R)hyper[3];
+      const R bc1 = s_bc[0], bc2_sqrt = s_bc[1];
+      const R gi = g[i];
+      const R mi = m[i] + (gi - m[i]) * (R(1) - b1);
+      const R vi = b2 * v[i] + (R(1) - b2) * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      const R denom = vsqrt(vi) / bc2_sqrt + eps;
+      p[i] -= ((R)lr / bc1) * (mi / denom);
+    }
     if (zero_grad) g[i] = R(0);
   }
   __syncthreads();  // this CTA has read step[0] (thread 0, above) and is done
@@ -227,7 +236,7 @@ __global__ void adam_dev_kernel(size_t n, R* __restrict__ p, R* __restrict__ g, 
     const unsigned long long ticket = atomicAdd((unsigned long long*)(step + 1), 1ULL);
     if (ticket == (unsigned long long)gridDim.x - 1) {
       step[1] = 0;
-      step[0] += 1;
+      step[skip ? 2 : 0] += 1;
     }
   }
 }
@@ -487,7 +496,7 @@ int vh_adam_step(int dtype, size_t n, void* param, const void* grad, void* exp_a
 }
 
 int vh_adam_step_dev(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq, const void* hyper,
-                     void* step, int zero_grad, void* stream) {
+                     void* step, int zero_grad, const void* guard, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper || !step) {
     set_error("vh_adam_step_dev: bad arguments");
     return VH_ERR_INVALID;
@@ -501,10 +510,10 @@ int vh_adam_step_dev(int dtype, size_t n, void* param, void* grad, void* exp_avg
   const unsigned grid = (unsigned)((n + block - 1) / block);
   if (dtype == VH_F32)
     adam_dev_kernel<float><<<grid, block, 0, s>>>(n, (float*)param, (float*)grad, (float*)exp_avg, (float*)exp_avg_sq,
-                                                   (const double*)hyper, (long long*)step, zero_grad);
+                                                   (const double*)hyper, (long long*)step, zero_grad, (const float*)guard);
   else if (dtype == VH_F64)
     adam_dev_kernel<double><<<grid, block, 0, s>>>(n, (double*)param, (double*)grad, (double*)exp_avg, (double*)exp_avg_sq,
-                                                    (const double*)hyper, (long long*)step, zero_grad);
+                                                    (const double*)hyper, (long long*)step, zero_grad, (const double*)guard);
   else {
     set_error("unknown dtype %d", dtype);
     return VH_ERR_INVALID;

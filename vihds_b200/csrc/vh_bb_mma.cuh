@@ -106,18 +106,37 @@ __device__ __forceinline__ void split(float v, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
   lo = v - hi;
 }
-// c += A B, one m16n8k8 TF32 tile (operands are fp32 bit patterns; the tensor core reads their upper 19 bits)
-__device__ __forceinline__ void mma8(float* c, const float* a, float b0, float b1) {
-  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+// d = c + A B, one m16n8k8 TF32 tile (operands are fp32 bit patterns; the tensor core reads their upper 19 bits).
+// d and c are separate register quadruples so that a persistent accumulator initialiser (the folded constants) or a
+// literal zero can be the C operand without a copy.
+__device__ __forceinline__ void mma8(float* d, const float* a, float b0, float b1, const float* c) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
       : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
-        "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+        "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
 }
-// 3xTF32 with a pre-split B tile b = (b0 hi, b0 lo, b1 hi, b1 lo): main += hi*hi, corr += lo*hi + hi*lo
-__device__ __forceinline__ void mma3(float* main, float* corr, const float* ah, const float* al, const float4 b) {
-  mma8(corr, al, b.x, b.z);
-  mma8(corr, ah, b.y, b.w);
-  mma8(main, ah, b.x, b.z);
+__device__ __forceinline__ void mma8(float* c, const float* a, float b0, float b1) { mma8(c, a, b0, b1, c); }
+// 3xTF32 with a pre-split B tile b = (b0 hi, b1 hi, b0 lo, b1 lo) -- the register pairs the instruction wants.
+// One accumulator chain, small terms first:  d = ((c + lo*hi) + hi*lo) + hi*hi
+__device__ __forceinline__ void mma3c(float* d, const float* ah, const float* al, const float4 b, const float* c) {
+  mma8(d, al, b.x, b.y, c);
+  mma8(d, ah, b.z, b.w);
+  mma8(d, ah, b.x, b.y);
+}
+// three independent accumulators (hi*hi, lo*hi, hi*lo): dependent chains a third as long, summed by the caller
+__device__ __forceinline__ void mma3x(float (*acc)[4], const float* ah, const float* al, const float4 b) {
+  mma8(acc[0], ah, b.x, b.y);
+  mma8(acc[1], al, b.x, b.y);
+  mma8(acc[2], ah, b.z, b.w);
+}
+// sigmoid on the SFU: ex2.approx + rcp.approx, 4 instructions instead of the ~14 of 1 / (1 + expf(-z)).  The argument
+// product carries |z| * 2^-24 of error, i.e. an absolute error in sigma of at most sigma (1 - sigma) |z| 1e-7 < 2e-7:
+// fp32 round-off class, three orders of magnitude inside the 1e-4 parity bar.  NaN propagates; +-inf saturate.
+__device__ __forceinline__ float sigmoid_fast(float z) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
 }
 // a C tile as the A fragment of the next GEMM: (c0, c2, c1, c3), split
 __device__ __forceinline__ void frag_of(const float* c, float* ah, float* al) {
@@ -140,14 +159,14 @@ __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 enum { BAR_FULL0 = 1, BAR_EMPTY0 = 3, BAR_TAIL1 = 5, BAR_TAIL2 = 6 };
 
-// fragment-ordered, pre-split weight tiles: tiles[tile * 32 + lane] = (b0 hi, b0 lo, b1 hi, b1 lo)
+// fragment-ordered, pre-split weight tiles: tiles[tile * 32 + lane] = (b0 hi, b1 hi, b0 lo, b1 lo)
 template <class F>
 __device__ void build_tiles(const float* w_smem, float4* tiles, int ntile) {
   for (int i = threadIdx.x; i < ntile * 32; i += blockDim.x) {
     const int tile = i >> 5, ln = i & 31, g = ln >> 2, tg = ln & 3;
     float4 v;
-    split(btile<F>(w_smem, tile, tg, g), v.x, v.y);
-    split(btile<F>(w_smem, tile, tg + 4, g), v.z, v.w);
+    split(btile<F>(w_smem, tile, tg, g), v.x, v.z);
+    split(btile<F>(w_smem, tile, tg + 4, g), v.y, v.w);
     tiles[i] = v;
   }
 }
@@ -239,35 +258,48 @@ struct WarpMlp {
     for (int i = 0; i < 4; ++i) split(in[i], ah[i], al[i]);
 #pragma unroll
     for (int nt = 0; nt < 7; ++nt) {
-      float c[4] = {hc[nt][0], hc[nt][1], hc[nt][2], hc[nt][3]};
-      float cc[4] = {0.f, 0.f, 0.f, 0.f};
-      mma3(c, cc, ah, al, bt[nt * 32]);
+      float c[4];
+      mma3c(c, ah, al, bt[nt * 32], hc[nt]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float v = c[i] + cc[i];
-        k.hid[nt][i] = v > 0.f ? v : 0.f;
-      }
+      for (int i = 0; i < 4; ++i) k.hid[nt][i] = fmaxf(c[i], 0.f);
     }
-    float mP[4] = {0.f, 0.f, 0.f, 0.f}, cP[4] = {0.f, 0.f, 0.f, 0.f}, mD[4] = {0.f, 0.f, 0.f, 0.f}, cD[4] = {0.f, 0.f, 0.f, 0.f};
-    float mQ[4] = {0.f, 0.f, 0.f, 0.f}, cQ[4] = {0.f, 0.f, 0.f, 0.f};
+    const float zero[4] = {0.f, 0.f, 0.f, 0.f};
+    float aP[3][4], aD[3][4], aQ[3][4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float hh[4], hl[4];
       frag_of(k.hid[j], hh, hl);
-      mma3(mP, cP, hh, hl, bt[(7 + 2 * j) * 32]);
-      mma3(mD, cD, hh, hl, bt[(8 + 2 * j) * 32]);
+      const float4 bp = bt[(7 + 2 * j) * 32], bd = bt[(8 + 2 * j) * 32];
+      if (j == 0) {
+        mma8(aP[0], hh, bp.x, bp.y, zero);
+        mma8(aP[1], hl, bp.x, bp.y, zero);
+        mma8(aP[2], hh, bp.z, bp.w, zero);
+        mma8(aD[0], hh, bd.x, bd.y, zero);
+        mma8(aD[1], hl, bd.x, bd.y, zero);
+        mma8(aD[2], hh, bd.z, bd.w, zero);
+      } else {
+        mma3x(aP, hh, hl, bp);
+        mma3x(aD, hh, hl, bd);
+      }
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       float hh[4], hl[4];
       frag_of(k.hid[4 + j], hh, hl);
-      mma3(mQ, cQ, hh, hl, bt[(15 + j) * 32]);
+      const float4 bq = bt[(15 + j) * 32];
+      if (j == 0) {
+        mma8(aQ[0], hh, bq.x, bq.y, zero);
+        mma8(aQ[1], hl, bq.x, bq.y, zero);
+        mma8(aQ[2], hh, bq.z, bq.w, zero);
+      } else {
+        mma3x(aQ, hh, hl, bq);
+      }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      k.sP[i] = sigmoid(mP[i] + cP[i]);
-      k.sD[i] = sigmoid(mD[i] + cD[i]);
-      k.sQ[i] = sigmoid(mQ[i] + cQ[i]);
+      k.sP[i] = sigmoid_fast((aP[1][i] + aP[2][i]) + aP[0][i]);
+      k.sD[i] = sigmoid_fast((aD[1][i] + aD[2][i]) + aD[0][i]);
+      k.sQ[i] = sigmoid_fast((aQ[1][i] + aQ[2][i]) + aQ[0][i]);
     }
   }
   __device__ void derivative(const float* Y, const Kept& k, float* dY) const {
@@ -318,44 +350,65 @@ struct WarpMlp {
       frag_of(gzP, ph, pl);
       frag_of(gzD, dh, dl);
       frag_of(gq, qh, ql);
+      const float zero[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        float m[4] = {0.f, 0.f, 0.f, 0.f}, c[4] = {0.f, 0.f, 0.f, 0.f};
-        mma3(m, c, ph, pl, bt[(18 + nt) * 32]);
-        mma3(m, c, dh, dl, bt[(22 + nt) * 32]);
+        float m[4];
+        mma3c(m, ph, pl, bt[(18 + nt) * 32], zero);
+        mma3c(m, dh, dl, bt[(22 + nt) * 32], m);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) gpre[nt][i] = k.hid[nt][i] > 0.f ? m[i] + c[i] : 0.f;
+        for (int i = 0; i < 4; ++i) gpre[nt][i] = k.hid[nt][i] > 0.f ? m[i] : 0.f;
       }
 #pragma unroll
       for (int nt = 0; nt < 3; ++nt) {
-        float m[4] = {0.f, 0.f, 0.f, 0.f}, c[4] = {0.f, 0.f, 0.f, 0.f};
-        mma3(m, c, qh, ql, bt[(26 + nt) * 32]);
+        float m[4];
+        mma3c(m, qh, ql, bt[(26 + nt) * 32], zero);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) gpre[4 + nt][i] = k.hid[4 + nt][i] > 0.f ? m[i] + c[i] : 0.f;
+        for (int i = 0; i < 4; ++i) gpre[4 + nt][i] = k.hid[4 + nt][i] > 0.f ? m[i] : 0.f;
       }
     }
 #pragma unroll
     for (int nt = 0; nt < 7; ++nt)
 #pragma unroll
       for (int i = 0; i < 4; ++i) gc.ghc[nt][i] += gpre[nt][i];
-    // input cotangents: gx = W1x^T gpre + Q1x^T gqpre
-    float mS[4] = {0.f, 0.f, 0.f, 0.f}, cS[4] = {0.f, 0.f, 0.f, 0.f}, mQ[4] = {0.f, 0.f, 0.f, 0.f}, cQ[4] = {0.f, 0.f, 0.f, 0.f};
+    // input cotangents: gx = W1x^T gpre + Q1x^T gqpre  (six independent accumulator chains)
+    float aS[3][4], aQ[3][4];
+    {
+      const float zero[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float ah[4], al[4];
-      frag_of(gpre[j], ah, al);
-      mma3(mS, cS, ah, al, bt[(29 + j) * 32]);
-    }
+      for (int j = 0; j < 4; ++j) {
+        float ah[4], al[4];
+        frag_of(gpre[j], ah, al);
+        const float4 b = bt[(29 + j) * 32];
+        if (j == 0) {
+          mma8(aS[0], ah, b.x, b.y, zero);
+          mma8(aS[1], al, b.x, b.y, zero);
+          mma8(aS[2], ah, b.z, b.w, zero);
+        } else {
+          mma3x(aS, ah, al, b);
+        }
+      }
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      float ah[4], al[4];
-      frag_of(gpre[4 + j], ah, al);
-      mma3(mQ, cQ, ah, al, bt[(33 + j) * 32]);
+      for (int j = 0; j < 3; ++j) {
+        float ah[4], al[4];
+        frag_of(gpre[4 + j], ah, al);
+        const float4 b = bt[(33 + j) * 32];
+        if (j == 0) {
+          mma8(aQ[0], ah, b.x, b.y, zero);
+          mma8(aQ[1], al, b.x, b.y, zero);
+          mma8(aQ[2], ah, b.z, b.w, zero);
+        } else {
+          mma3x(aQ, ah, al, b);
+        }
+      }
     }
-    gX[0] += (mS[0] + mQ[0]) + (cS[0] + cQ[0]);
-    if (hasB) gX[1] += (mS[1] + mQ[1]) + (cS[1] + cQ[1]);
-    gX[3] += (mS[2] + mQ[2]) + (cS[2] + cQ[2]);
-    if (hasB) gX[4] += (mS[3] + mQ[3]) + (cS[3] + cQ[3]);
+    float r[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = ((aS[1][i] + aS[2][i]) + (aQ[1][i] + aQ[2][i])) + (aS[0][i] + aQ[0][i]);
+    gX[0] += r[0];
+    if (hasB) gX[1] += r[1];
+    gX[3] += r[2];
+    if (hasB) gX[4] += r[3];
     float in[4];
     inputs(t, Y, in);
     gw.put(in, k.hid, gpre, gzP, gzD, gq);

@@ -443,13 +443,15 @@ __global__ void __launch_bounds__(256) enc_lin_wgrad_small_kernel(const EncDims 
 }
 
 // device conditioner (vihds/ode.py:43-58, :99-116) including the reference's repeat/reshape quirk: sample n = b*IW + i
-// receives the conditioner output of individual n % B
+// of the GLOBAL batch receives the conditioner output of individual n % B_global.  A rank that holds the slab of
+// individuals [b_offset, b_offset + B) passes the global one-hot table, so the result does not depend on the rank count.
 template <typename R>
-__global__ void conditioner_kernel(int B, int N, int D, int n_cond, const R* __restrict__ dev, const R* __restrict__ rel,
-                                   const R* __restrict__ w, const int* __restrict__ plus_one, R* __restrict__ out) {
+__global__ void conditioner_kernel(int B_global, long long n_offset, int N, int D, int n_cond, const R* __restrict__ dev,
+                                   const R* __restrict__ rel, const R* __restrict__ w, const int* __restrict__ plus_one,
+                                   R* __restrict__ out) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
-  const R* d = dev + (size_t)(n % B) * D;
+  const R* d = dev + (size_t)((n_offset + n) % B_global) * D;
   for (int k = 0; k < n_cond; ++k) {
     R a = R(0);
     for (int j = 0; j < D; ++j) a += w[k * D + j] * (d[j] * rel[k * D + j]);
@@ -602,18 +604,20 @@ int vh_encoder_fwd(const vh_encoder_desc* e, const vh_encoder_io* io, void* stre
   return VH_OK;
 }
 
-int vh_device_conditioner(int dtype, int B, int IW, int D, int n_cond, const void* dev_1hot, const void* rel, const void* w,
-                          const int* plus_one, void* out, void* stream) {
-  if (B <= 0 || IW <= 0 || D <= 0 || n_cond <= 0 || !dev_1hot || !rel || !w || !plus_one || !out) {
+int vh_device_conditioner(int dtype, int B, int IW, int D, int n_cond, int B_global, int b_offset, const void* dev_1hot,
+                          const void* rel, const void* w, const int* plus_one, void* out, void* stream) {
+  if (B <= 0 || IW <= 0 || D <= 0 || n_cond <= 0 || !dev_1hot || !rel || !w || !plus_one || !out || B_global < B ||
+      b_offset < 0 || b_offset + B > B_global) {
     set_error("vh_device_conditioner: bad arguments");
     return VH_ERR_INVALID;
   }
+  const long long n_off = (long long)b_offset * IW;
   const int N = B * IW, block = 128, grid = (N + block - 1) / block;
   cudaStream_t s = (cudaStream_t)stream;
   if (dtype == VH_F32)
-    conditioner_kernel<float><<<grid, block, 0, s>>>(B, N, D, n_cond, (const float*)dev_1hot, (const float*)rel, (const float*)w, plus_one, (float*)out);
+    conditioner_kernel<float><<<grid, block, 0, s>>>(B_global, n_off, N, D, n_cond, (const float*)dev_1hot, (const float*)rel, (const float*)w, plus_one, (float*)out);
   else if (dtype == VH_F64)
-    conditioner_kernel<double><<<grid, block, 0, s>>>(B, N, D, n_cond, (const double*)dev_1hot, (const double*)rel, (const double*)w, plus_one, (double*)out);
+    conditioner_kernel<double><<<grid, block, 0, s>>>(B_global, n_off, N, D, n_cond, (const double*)dev_1hot, (const double*)rel, (const double*)w, plus_one, (double*)out);
   else {
     set_error("unknown dtype %d", dtype);
     return VH_ERR_INVALID;

@@ -24,7 +24,8 @@
 namespace vh {
 void set_error(const char* fmt, ...);
 
-// buffer layout (bytes): [0, 4096): flags, uint64 [2][VH_PEER_MAX_WORLD]  |  [4096, ...): inbox R [2][world][n_pad]
+// buffer layout (bytes): [0, 4096): uint64 [4][VH_PEER_MAX_WORLD] = flags of parity 0, 1, "bad" words of parity 0, 1
+// |  [4096, ...): inbox R [2][world][n_pad]
 constexpr int PEER_FLAG_BYTES = 4096;
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -36,18 +37,33 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   return v;
 }
 
-// state: int64[4] = {epoch, ticket, timed_out, unused}; step: int64[2] as for vh_adam_step_dev (step[1] unused here)
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// state: int64[4] = {epoch, ticket, timed_out (sticky), skipped steps}; step: int64[4] as for vh_adam_step_dev.
+// guard: this rank's cost of the step (or NULL).  A NaN cost anywhere means a NaN gradient sum everywhere: every rank
+// publishes a "bad" word next to its flag, every rank ORs all of them and skips the update together (the reference
+// stops before optimizer.step(), vihds/training.py:331-333); state[3] / step[2] count the skipped calls.
+// A wait that exceeds timeout_ns marks the exchange as timed out (sticky) and the CTA skips its part of the update; once
+// the flag is set every later call returns at once, so the peers time out as well and every host finds the flag.
 template <typename R>
 __global__ void __launch_bounds__(256) adam_allreduce_kernel(size_t n, size_t n_pad, R* __restrict__ p, R* __restrict__ g,
                                                              R* __restrict__ m, R* __restrict__ v,
                                                              const double* __restrict__ hyper, long long* step,
                                                              long long* state, int rank, int world,
-                                                             unsigned char* const* __restrict__ peers) {
+                                                             unsigned char* const* __restrict__ peers,
+                                                             const R* __restrict__ guard, unsigned long long timeout_ns) {
+  if (*(volatile long long*)(state + 2) != 0) return;  // the exchange has failed before: nothing may be applied
   const unsigned long long epoch = (unsigned long long)*(volatile long long*)state;
   const double t = (double)(*(volatile long long*)step + 1);
   const int par = (int)(epoch & 1);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int s_skip, s_last;
+  if (threadIdx.x == 0) s_skip = s_last = 0;
   // A. push
   for (size_t i = i0; i < n; i += stride) {
     const R val = g[i];
@@ -64,6 +80,13 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(size_t n, size_t n_
     __threadfence_system();
     const unsigned long long ticket = atomicAdd((unsigned long long*)(state + 1), 1ULL);
     if (ticket == (unsigned long long)gridDim.x - 1) {
+      s_last = 1;
+      const R c = guard ? *guard : R(0);
+      const unsigned long long bad = (c != c) ? 1ULL : 0ULL;
+      for (int r = 0; r < world; ++r) {
+        unsigned long long* flags = reinterpret_cast<unsigned long long*>(peers[r]);
+        flags[(2 + par) * VH_PEER_MAX_WORLD + rank] = bad;  // ordered before the flag by the release below
+      }
       __threadfence_system();
       for (int r = 0; r < world; ++r) {
         unsigned long long* flags = reinterpret_cast<unsigned long long*>(peers[r]);
@@ -71,22 +94,38 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(size_t n, size_t n_
       }
       state[1] = 0;
       state[0] = (long long)(epoch + 1);
-      step[0] += 1;
     }
   }
   // C. wait for every rank's push of this epoch (bounded: a lost peer must not wedge the GPU)
   if (threadIdx.x < world) {
     const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(peers[rank]);
-    const long long t0 = clock64();
+    const unsigned long long t0 = global_ns();
+    bool ok = true;
     while (ld_acquire_sys(flags + par * VH_PEER_MAX_WORLD + threadIdx.x) < epoch + 1) {
-      if (clock64() - t0 > 20000000000LL) {  // ~10 s
-        state[2] = 1;
+      if (global_ns() - t0 > timeout_ns) {
+        ok = false;
         break;
       }
       __nanosleep(64);
     }
+    if (!ok) {
+      state[2] = 1;
+      atomicOr(&s_skip, 2);
+    } else if (ld_acquire_sys(flags + (2 + par) * VH_PEER_MAX_WORLD + threadIdx.x) != 0) {
+      atomicOr(&s_skip, 1);
+    }
   }
   __syncthreads();
+  const int skip = s_skip;
+  if (threadIdx.x == 0 && s_last) {  // the step / skip counters advance once per call, after the verdict
+    if (skip == 0)
+      step[0] += 1;
+    else if (skip == 1) {
+      step[2] += 1;
+      state[3] += 1;
+    }
+  }
+  if (skip) return;
   const double lr = hyper[0], b1d = hyper[1], b2d = hyper[2];
   const R b1 = (R)b1d, b2 = (R)b2d, eps = (R)hyper[3];
   const R bc1 = (R)(1.0 - pow(b1d, t));
@@ -154,7 +193,8 @@ int vh_peer_buffer_close(void* dev_ptr) { return cudaIpcCloseMemHandle(dev_ptr) 
 int vh_peer_buffer_destroy(void* dev_ptr) { return cudaFree(dev_ptr) == cudaSuccess ? VH_OK : VH_ERR_CUDA; }
 
 int vh_adam_allreduce_step(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq, const void* hyper,
-                           void* step, void* state, int rank, int world, const void* peers, void* stream) {
+                           void* step, void* state, int rank, int world, const void* peers, const void* guard,
+                           double timeout_s, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper || !step || !state || !peers || n == 0 || world < 1 ||
       world > VH_PEER_MAX_WORLD || rank < 0 || rank >= world) {
     set_error("vh_adam_allreduce_step: bad arguments");
@@ -171,14 +211,15 @@ int vh_adam_allreduce_step(int dtype, size_t n, void* param, void* grad, void* e
   const size_t cap = (size_t)(sms > 0 ? sms : 1) * 2;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   unsigned char* const* pp = (unsigned char* const*)peers;
+  const unsigned long long tns = (unsigned long long)((timeout_s > 0 ? timeout_s : 10.0) * 1e9);
   if (dtype == VH_F32)
     adam_allreduce_kernel<float><<<grid, block, 0, s>>>(n, n_pad, (float*)param, (float*)grad, (float*)exp_avg,
                                                          (float*)exp_avg_sq, (const double*)hyper, (long long*)step,
-                                                         (long long*)state, rank, world, pp);
+                                                         (long long*)state, rank, world, pp, (const float*)guard, tns);
   else if (dtype == VH_F64)
     adam_allreduce_kernel<double><<<grid, block, 0, s>>>(n, n_pad, (double*)param, (double*)grad, (double*)exp_avg,
                                                           (double*)exp_avg_sq, (const double*)hyper, (long long*)step,
-                                                          (long long*)state, rank, world, pp);
+                                                          (long long*)state, rank, world, pp, (const double*)guard, tns);
   else {
     set_error("unknown dtype %d", dtype);
     return VH_ERR_INVALID;

@@ -83,8 +83,10 @@ class PeerGradientExchange(object):
     round through ``all_gather_object``, and each rank maps its peers' buffers.  ``group=None`` builds a one-rank
     exchange (the kernel then only talks to itself: used by the single-GPU test)."""
 
-    def __init__(self, n, dtype, device, group=None):
+    def __init__(self, n, dtype, device, group=None, timeout_s=None):
         from . import _lib as L
+        # bound of the in-kernel wait for the peers' flags (seconds of %globaltimer); env VIHDS_EXCHANGE_TIMEOUT_S
+        self.timeout_s = float(timeout_s if timeout_s is not None else os.environ.get("VIHDS_EXCHANGE_TIMEOUT_S", "10"))
         self.lib = lib = L.load()
         self.rank = dist.get_rank(group) if group is not None else 0
         self.world = dist.get_world_size(group) if group is not None else 1
@@ -129,10 +131,17 @@ class PeerGradientExchange(object):
                 self.close()
                 raise ExchangeUnavailable(err or "a peer could not map the exchange buffers")
         self.peers = torch.tensor(ptrs, dtype=torch.int64, device=device)
-        self.state = torch.zeros(4, dtype=torch.int64, device=device)  # epoch, ticket, timed_out, -
+        self.state = torch.zeros(4, dtype=torch.int64, device=device)  # epoch, ticket, timed_out (sticky), skipped
 
     def timed_out(self):
         return bool(self.state[2].item())
+
+    def check(self):
+        """Raise if the exchange has ever timed out (synchronises).  A timed-out call applies no complete update and
+        every later call is a no-op on this rank, so the replicas must not be used any further."""
+        if self.timed_out():
+            raise RuntimeError("gradient exchange: a peer's flag did not arrive within %.1f s (vh_adam_allreduce_step "
+                               "timed out); the parameter replicas are no longer in step" % self.timeout_s)
 
     def close(self):
         """Unmap the peers' buffers and free this rank's (call on every rank, after a barrier: peers may still push)."""

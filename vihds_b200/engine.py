@@ -287,7 +287,7 @@ class FlatAdam(object):
         self.params = params
         self.betas, self.eps = betas, eps
         self.hyper = torch.tensor([lr, betas[0], betas[1], eps], dtype=torch.float64, device=dev)
-        self.step_dev = torch.zeros(2, dtype=torch.int64, device=dev)  # [updates done, ticket scratch]
+        self.step_dev = torch.zeros(4, dtype=torch.int64, device=dev)  # [updates done, ticket scratch, skipped (NaN cost), -]
         self.vdt = L.VH_F64 if dt == torch.float64 else L.VH_F32
         self.lr = lr
 
@@ -298,16 +298,23 @@ class FlatAdam(object):
     def zero_grad(self):
         self.grad.zero_()
 
-    def step_exchange(self, exchange):
+    def step_exchange(self, exchange, guard=None):
         """Data-parallel step: sum the ranks' gradients over NVLink peer memory and apply Adam in ONE launch
-        (distributed.PeerGradientExchange); the gradient vector is cleared."""
+        (distributed.PeerGradientExchange); the gradient vector is cleared.  guard: this rank's cost (device tensor):
+        a NaN cost on ANY rank makes every rank skip the update (vihds/training.py:331-336)."""
         L.check(L.load().vh_adam_allreduce_step(self.vdt, self.flat.numel(), _ptr(self.flat), _ptr(self.grad),
                                                 _ptr(self.exp_avg), _ptr(self.exp_avg_sq), _ptr(self.hyper),
                                                 _ptr(self.step_dev), _ptr(exchange.state), exchange.rank, exchange.world,
-                                                _ptr(exchange.peers), _stream()))
+                                                _ptr(exchange.peers), _ptr(guard), float(exchange.timeout_s), _stream()))
 
-    def step(self, zero_grad=False):
-        """zero_grad: clear the gradient vector in the same launch (it is consumed exactly once)."""
+    def step(self, zero_grad=False, guard=None):
+        """zero_grad: clear the gradient vector in the same launch (it is consumed exactly once).  guard: the step's cost
+        (device tensor) -- if it is NaN the update is skipped on the device, as the reference does on the host before
+        optimizer.step() (vihds/training.py:331-336), and ``skipped_steps`` counts it."""
         L.check(L.load().vh_adam_step_dev(self.vdt, self.flat.numel(), _ptr(self.flat), _ptr(self.grad), _ptr(self.exp_avg),
                                           _ptr(self.exp_avg_sq), _ptr(self.hyper), _ptr(self.step_dev), int(zero_grad),
-                                          _stream()))
+                                          _ptr(guard), _stream()))
+
+    def skipped_steps(self):
+        """Number of updates the device-side NaN guard has refused so far (synchronises)."""
+        return int(self.step_dev[2].item())

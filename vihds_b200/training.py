@@ -142,17 +142,21 @@ class GraphedStep(object):
     """One ELBO-gradient step over static buffers (see module docstring).
 
     b_total       denominator of the batch mean (global batch when individuals are sharded over ranks)
+    b_offset      index of this rank's first individual in the global batch.  The device conditioner reproduces the
+                  reference's repeat / reshape quirk on GLOBAL sample indices (vihds/ode.py:46-58), so a sharded run
+                  needs the global one-hot table (``load_global_devices``) to give rank-count-independent results
     process_group torch.distributed group of the data-parallel ranks (None: one GPU)
     exchange      "peer" (default; env VIHDS_ALLREDUCE): gradient exchange + Adam in one kernel over NVLink peer memory;
                   "nccl": ncclAllReduce of the flat gradient, then the Adam kernel
     """
 
-    def __init__(self, training, B, IW, T, b_total=None, process_group=None, use_graphs=True, exchange=None):
+    def __init__(self, training, B, IW, T, b_total=None, process_group=None, use_graphs=True, exchange=None, b_offset=0):
         self.tr, self.model = training, training.model
         m = self.model
         dev, dt = training.settings.device, training.settings.dtype
         self.B, self.IW, self.T, self.N = B, IW, T, B * IW
         self.b_total = b_total or B
+        self.b_offset = int(b_offset)
         self.pg = process_group
         self.use_graphs = use_graphs
         enc, ode = m.encoder, m.decoder.ode_model
@@ -176,6 +180,9 @@ class GraphedStep(object):
             self.rel_mat = torch.stack(self.rel).contiguous()
             self.plus_one = torch.tensor([int(n in ode.default_devices) for n in self.extras], dtype=torch.int32, device=dev)
             self.extra_static = z(len(self.extras), self.N)
+            # sharded: one-hot table of the global batch (rows of all ranks); one GPU: the batch's own table
+            self.dev_1hot_global = z(self.b_total, Dn) if self.b_total != B else None
+            self._global_devices_loaded = self.dev_1hot_global is None
         # fused encoder: static activations + direct gradient pointers (no autograd on the encoder side)
         self.fused_encoder = bool(getattr(enc, "fused", False))
         if self.fused_encoder:
@@ -190,6 +197,7 @@ class GraphedStep(object):
         self.buf = Settings(theta=z(P, N), x_states=z(T, S, N), lpx=z(N, 4), lp=z(N), lq=z(N), cost=z(1), log_w=z(N), w=z(N),
                             g_lpx=z(N, 4), g_lp=z(N), g_lq=z(N), d_q=z(2, B, P))
         self.buf.d_q_mu, self.buf.d_q_prec = self.buf.d_q[0], self.buf.d_q[1]  # adjacent: cleared by one memset
+        self.buf.cost_sum = z(1)  # NCCL path: sum of the ranks' costs (guard of the Adam update)
         self.d_weights = z(self.prob.n_weights) if self.prob.n_weights else None
         self.d_extra = z(len(self.extras), N) if (self.extras and hasattr(ode, "offset_layer")) else None
         self.exchange = None
@@ -220,8 +228,14 @@ class GraphedStep(object):
                 self._side = torch.cuda.Stream()
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
+                if not self._global_devices_loaded:
+                    raise RuntimeError("sharded step with a device conditioner: call load_global_devices(dev_1hot of the "
+                                       "GLOBAL batch) first -- the conditioner row of sample (b, i) is individual "
+                                       "(b*IW + i) % B_global (vihds/ode.py:46-58)")
+                table = self.dev_1hot_global if self.dev_1hot_global is not None else self.batch.dev_1hot
                 L.check(lib.vh_device_conditioner(self.prob.vh_dtype, self.B, self.IW, self.cond_w.shape[1], len(self.extras),
-                                                  _ptr(self.batch.dev_1hot), _ptr(self.rel_mat), _ptr(self.cond_w),
+                                                  table.shape[0], self.b_offset if self.dev_1hot_global is not None else 0,
+                                                  _ptr(table), _ptr(self.rel_mat), _ptr(self.cond_w),
                                                   _ptr(self.plus_one), _ptr(self.extra_static), _stream()))
         if self.fused_encoder:
             pr = enc.fused_parameters()
@@ -297,12 +311,16 @@ class GraphedStep(object):
             grads.append(self.d_extra)
         if outs:
             torch.autograd.backward(outs, grads)
+        # the cost guards the update ON THE DEVICE: a NaN cost (NaN gradients) must not reach the parameters or the Adam
+        # moments before the host has looked at it (vihds/training.py:331-336 checks before optimizer.step())
         if self.exchange is not None:
-            opt.step_exchange(self.exchange)  # gradient exchange over NVLink peer memory + Adam, one launch
+            opt.step_exchange(self.exchange, guard=self.buf.cost)  # exchange over NVLink peer memory + Adam, one launch
         else:
             if self.pg is not None:
                 torch.distributed.all_reduce(opt.grad, group=self.pg)
-            opt.step(zero_grad=True)
+                self.buf.cost_sum.copy_(self.buf.cost)
+                torch.distributed.all_reduce(self.buf.cost_sum, group=self.pg)  # a NaN on any rank reaches every rank
+            opt.step(zero_grad=True, guard=self.buf.cost_sum if self.pg is not None else self.buf.cost)
 
     # -- capture / replay ---------------------------------------------------------------------------------------
     def prepare(self):
@@ -340,10 +358,27 @@ class GraphedStep(object):
         for t, s in zip((opt.flat, opt.exp_avg, opt.exp_avg_sq, opt.step_dev), snap):
             t.copy_(s)  # warm-up and capture passes must not count as training steps
         self.ready = True
+        self.check_health()  # rank skew during lazy module loading / capture is where an exchange time-out would show first
+
+    def check_health(self):
+        """Synchronises.  Raises if the gradient exchange has timed out (the replicas are then no longer in step)."""
+        if self.exchange is not None:
+            self.exchange.check()
+
+    def skipped_steps(self):
+        """Updates refused by the device-side NaN guard so far (synchronises)."""
+        return self.tr.optimizer.skipped_steps()
+
+    def load_global_devices(self, dev_1hot_global):
+        """Sharded runs: the device one-hot rows of the GLOBAL batch [b_total, D] (same on every rank)."""
+        if getattr(self, "dev_1hot_global", None) is None:
+            return
+        self.dev_1hot_global.copy_(dev_1hot_global.to(self.dev_1hot_global.dtype), non_blocking=True)
+        self._global_devices_loaded = True
 
     def load_batch(self, batch, non_blocking=True):
-        src = batch["times"]  # the time grid belongs to the data set: skip the copy while the same tensor is handed in
-        tag = (id(src), src._version)
+        src = batch["times"]  # the time grid belongs to the data set: skip the copy while the same storage is handed in
+        tag = (src.data_ptr(), src._version, src.numel(), tuple(src.stride()))
         if getattr(self, "_times_tag", None) != tag:
             self._times_tag = tag
             self.batch.times.copy_(src, non_blocking=non_blocking)
@@ -372,16 +407,20 @@ class GraphedStep(object):
         L.check(self.prob.lib.vh_copy_async(dst.data_ptr(), src.data_ptr(), dst.numel() * dst.element_size(), _stream()))
 
     def load_u(self, u, non_blocking=True):
-        key = (u.data_ptr(), u.numel(), u.dtype)
-        fast = getattr(self, "_u_fast", None)
-        if fast is None:
-            fast = self._u_fast = {}
-        if key not in fast:  # is_pinned() asks the driver: once per host buffer
-            if len(fast) > 64:
-                fast.clear()
-            fast[key] = (not u.is_cuda and u.is_pinned() and u.is_contiguous() and u.dtype == self.u.dtype and
-                         u.numel() == self.u.numel())
-        if fast[key]:
+        # raw asynchronous copy for contiguous pinned host buffers of the right dtype / size; only the answer of
+        # is_pinned() (a driver query) is cached per host allocation, everything else is re-checked on every call
+        fast = False
+        if not u.is_cuda and u.dtype == self.u.dtype and u.numel() == self.u.numel() and u.is_contiguous():
+            pins = getattr(self, "_u_pinned", None)
+            if pins is None:
+                pins = self._u_pinned = {}
+            key = (u.untyped_storage().data_ptr(), u.untyped_storage().nbytes())
+            if key not in pins:
+                if len(pins) > 64:
+                    pins.clear()
+                pins[key] = u.is_pinned()
+            fast = pins[key]
+        if fast:
             self._h2d(self.u, u)
         else:
             self.u.copy_(u.reshape(self.N, self.P), non_blocking=non_blocking)
