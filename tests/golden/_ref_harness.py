@@ -1,184 +1,8 @@
-"""Harness that imports the UNMODIFIED reference (microsoft/vi-hds at /root/reference) in the build container.
-
-Test/fixture infrastructure only: it is used by ``make_golden.py`` to mint the golden vectors committed next to
-this file, and it is never imported by the product package, by ``bench.py`` or by any ``-m gpu`` test
-(``/root/reference`` does not exist on the GPU box).
-
-The reference needs four harness-side shims on this image; none of them edits the reference:
-
-* ``munch``            -- not installed; a small attribute dict is enough (config.py:9, training.py:6).
-* ``seaborn``/``matplotlib`` -- imported by vihds/plotting.py:5-10 but never called with plot_epoch=0.
-* ``vihds.datasets.merge_observations`` -- datasets.py:137-138 builds a ragged ``np.asarray`` that numpy>=1.24
-  rejects for every multi-file spec; replaced by a ragged-safe equivalent with the same nearest-time selection.
-* ``torchdiffeq``      -- pinned ==0.1 (requirements.txt:3), not vendored and not installable offline.  The
-  fixed-grid schemes are restated from the published algorithm of torchdiffeq 0.1 (fixed_grid.py / rk_common.py):
-  the integration grid is the requested ``times`` (no ``step_size``), outputs are the grid values themselves.
-  PARITY UNPINNED for this third-party arithmetic: the only reference-side pin is tests/test_ode_solvers.py:62-89
-  (CV < 5 % across solvers).  The in-repo ``modeuler``/``modeulerwhile`` solvers (vihds/solvers.py) need no shim.
-
-Two-line monkeypatch for relay_constant_precisions (broken as shipped: relay_constant.py:201 calls a non-existent
-``init_with_params`` and relay_constant.py:17 passes 6 args to ``OdeFunc.__init__``): this patched behaviour is the
-de-facto oracle for BASELINE config 5 and is declared as such in DESIGN.md.
-"""
+"""Kept for ``make_golden.py``: the harness that imports the unmodified reference lives in oracle/ref_harness.py (the
+reference arm of bench.py uses it too, through the vendored copy built by oracle/build_ref.py)."""
 import os
 import sys
-import types
 
-REFERENCE_ROOT = os.environ.get("VIHDS_REFERENCE_ROOT", "/root/reference")
-
-
-class Munch(dict):
-    """Minimal stand-in for munch.Munch: a dict with attribute access."""
-
-    def __getattr__(self, k):
-        try:
-            return self[k]
-        except KeyError:
-            raise AttributeError(k)
-
-    def __setattr__(self, k, v):
-        self[k] = v
-
-    def __delattr__(self, k):
-        del self[k]
-
-
-def munchify(x):
-    if isinstance(x, dict):
-        return Munch((k, munchify(v)) for k, v in x.items())
-    if isinstance(x, list):
-        return [munchify(v) for v in x]
-    if isinstance(x, tuple):
-        return tuple(munchify(v) for v in x)
-    return x
-
-
-def _fixed_grid_odeint(func, y0, t, method="midpoint", **_unused):
-    """Fixed-grid solvers of torchdiffeq 0.1 restated (grid == t, no sub-stepping)."""
-    import torch
-
-    ys = [y0]
-    y = y0
-    for t0, t1 in zip(t[:-1], t[1:]):
-        dt = t1 - t0
-        if method == "euler":
-            dy = dt * func(t0, y)
-        elif method == "midpoint":
-            y_mid = y + func(t0, y) * dt / 2
-            dy = dt * func(t0 + dt / 2, y_mid)
-        elif method == "rk4":
-            # torchdiffeq 0.1 uses rk4_alt_step_func, the 3/8 rule
-            k1 = func(t0, y)
-            k2 = func(t0 + dt / 3, y + dt * k1 / 3)
-            k3 = func(t0 + dt * 2 / 3, y + dt * (k1 / -3 + k2))
-            k4 = func(t0 + dt, y + dt * (k1 - k2 + k3))
-            dy = (k1 + 3 * k2 + 3 * k3 + k4) * (dt / 8)
-        else:
-            raise NotImplementedError("harness odeint: method %s not restated (adaptive solvers are out of scope)" % method)
-        y = y + dy
-        ys.append(y)
-    return torch.stack(ys)
-
-
-def install_shims():
-    if "munch" not in sys.modules:
-        m = types.ModuleType("munch")
-        m.Munch = Munch
-        m.munchify = munchify
-        sys.modules["munch"] = m
-    for name in ("seaborn", "matplotlib", "matplotlib.pyplot", "matplotlib.cm", "matplotlib.colors"):
-        if name not in sys.modules:
-            sys.modules[name] = types.ModuleType(name)
-    sys.modules["matplotlib"].use = lambda *a, **k: None
-    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
-    sys.modules["matplotlib"].cm = sys.modules["matplotlib.cm"]
-    sys.modules["matplotlib"].colors = sys.modules["matplotlib.colors"]
-    if "torchdiffeq" not in sys.modules:
-        td = types.ModuleType("torchdiffeq")
-        td.odeint = _fixed_grid_odeint
-        td.odeint_adjoint = _fixed_grid_odeint  # same forward values; gradients are compared against odeint only
-        sys.modules["torchdiffeq"] = td
-
-
-def import_reference():
-    """Put /root/reference on sys.path, install shims + monkeypatches, return the handful of modules used."""
-    import numpy as np
-
-    if not os.path.isdir(REFERENCE_ROOT):
-        raise RuntimeError("reference tree %s not present (golden vectors can only be minted in the build container)" % REFERENCE_ROOT)
-    install_shims()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
-    import vihds.datasets as ds
-    import vihds.ode as ode
-
-    def merge_observations(times_list, observations_list):
-        n_list = np.array([len(t) for t in times_list])
-        loc = int(np.argmin(n_list))
-        chosen = times_list[loc]
-        out = []
-        for t, obs in zip(times_list, observations_list):
-            locs = [ds.find_nearest(t, ti) for ti in chosen]
-            out.append(obs[:, :, locs])
-        return chosen, np.concatenate(out)
-
-    ds.merge_observations = merge_observations
-
-    # relay monkeypatch
-    if not hasattr(ode.OdeModel, "init_with_params"):
-        ode.OdeModel.init_with_params = ode.OdeModel.__init__
-    if not getattr(ode.OdeFunc, "_harness_patched", False):
-        _orig = ode.OdeFunc.__init__
-
-        def _init(self, config, _theta, _conditions, _dev1_hot, *extra):
-            _orig(self, config, _theta, _conditions, _dev1_hot)
-
-        ode.OdeFunc.__init__ = _init
-        ode.OdeFunc._harness_patched = True
-    return ds, ode
-
-
-def build_reference(spec, samples, seed=0, dtype="float32", solver=None, extra_args=()):
-    """Build (args, settings, data, parameters, model, training) of the reference for specs/<spec>.yaml."""
-    import torch
-
-    import_reference()
-    from vihds.config import Config
-    from vihds.datasets import build_datasets
-    from vihds.parameters import Parameters
-    from vihds.run_xval import create_parser
-    from vihds.training import Training
-    from vihds.vae import build_model
-
-    os.environ["INFERENCE_DATA_DIR"] = os.path.join(REFERENCE_ROOT, "data")
-    parser = create_parser(True)
-    args = parser.parse_args(
-        ["--train_samples=%d" % samples, "--test_samples=%d" % samples, "--seed=%d" % seed, "--plot_epoch=0", *extra_args,
-         os.path.join(REFERENCE_ROOT, "specs", spec + ".yaml")]
-    )
-    args.heldout = None
-    # dtype has to be patched into the parsed yaml, Config reads data.dtype (config.py:134, :164-178)
-    import yaml as _yaml
-
-    if dtype != "float32":
-        _orig_load = _yaml.safe_load
-
-        def _load(stream):
-            d = _orig_load(stream)
-            d["data"]["dtype"] = dtype
-            return d
-
-        _yaml.safe_load = _load
-    try:
-        settings = Config(args)
-    finally:
-        if dtype != "float32":
-            _yaml.safe_load = _orig_load
-    if solver is not None:
-        settings.params.solver = solver
-    data = build_datasets(args, settings)
-    parameters = Parameters(settings.params)
-    model = build_model(args, settings, data, parameters)
-    training = Training(args, settings, data, parameters, model)
-    torch.set_default_dtype(torch.float64 if dtype == "float64" else torch.float32)
-    return args, settings, data, parameters, model, training
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "oracle"))
+from ref_harness import *  # noqa: E402,F401,F403
+from ref_harness import REFERENCE_ROOT, build_reference, import_reference, install_shims  # noqa: E402,F401

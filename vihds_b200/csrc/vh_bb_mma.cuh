@@ -174,11 +174,11 @@ __device__ void build_tiles(const float* w_smem, float4* tiles, int ntile) {
 // hand-off of one evaluation's weight-gradient operands from the adjoint warp to the weight-gradient warp
 struct PanelSink {
   float* ring;  // [2][ROWS][RS]
-  int it, g, tg;
+  int it, g, tg, bar0;  // bar0: first named-barrier id of this warp pair
   __device__ void put(const float* in, const float (*hid)[4], const float (*gpre)[4], const float* gzP, const float* gzD,
                       const float* gq) {
     const int slot = it & 1;
-    if (it >= 2) bar_sync(BAR_EMPTY0 + slot, 64);
+    if (it >= 2) bar_sync(bar0 + BAR_EMPTY0 + slot, 64);
     float* p0 = ring + (slot * ROWS + g) * RS;
     float* p1 = p0 + 8 * RS;
     p0[PX + tg] = in[0];
@@ -206,7 +206,7 @@ struct PanelSink {
     *reinterpret_cast<float2*>(p0 + PQ + 2 * tg) = make_float2(gq[0], gq[1]);
     *reinterpret_cast<float2*>(p1 + PQ + 2 * tg) = make_float2(gq[2], gq[3]);
     __threadfence_block();
-    bar_arrive(BAR_FULL0 + slot, 64);
+    bar_arrive(bar0 + BAR_FULL0 + slot, 64);
     ++it;
   }
 };
@@ -753,7 +753,7 @@ __device__ void warp_forward(const Call<float>& a, int n_base, const float* w, c
 // ---------------------------------------------------------------------------------------------------------------
 template <class F, class TB>
 __device__ void warp_backward(const Call<float>& a, int n_base, const float* w, const float4* tiles, float* ring,
-                              float* kept_sm) {
+                              float* kept_sm, int bar0) {
   typedef typename F::L L;
   constexpr int NST = F::NST;
   const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
@@ -774,7 +774,7 @@ __device__ void warp_backward(const Call<float>& a, int n_base, const float* w, 
   for (int nt = 0; nt < 7; ++nt)
 #pragma unroll
     for (int i = 0; i < 4; ++i) gc.ghc[nt][i] = 0.f;
-  PanelSink sink{ring, 0, g, tg};
+  PanelSink sink{ring, 0, g, tg, bar0};
   float gl[2], glq[2], glp[2];
   const float* obs[2];
   const float* xs[2];
@@ -863,7 +863,7 @@ __device__ void warp_backward(const Call<float>& a, int n_base, const float* w, 
   // ---- tail: constants' weight gradients (through the weight-gradient warp) and the chain rule back to theta ----
   float cv[2][3][2], x0[2], lq[2], lp[2];
   load_consts<F>(a, ri, tg, false, cv, x0, lq, lp);
-  bar_sync(BAR_TAIL1, 64);  // the weight-gradient warp has consumed every evaluation panel
+  bar_sync(bar0 + BAR_TAIL1, 64);  // the weight-gradient warp has consumed every evaluation panel
   {
     float* p0 = ring + g * RS;
     float* p1 = p0 + 8 * RS;
@@ -888,7 +888,7 @@ __device__ void warp_backward(const Call<float>& a, int n_base, const float* w, 
       }
   }
   __threadfence_block();
-  bar_sync(BAR_TAIL2, 64);
+  bar_sync(bar0 + BAR_TAIL2, 64);
   // cotangent of c: gc = W1c^T ghc + Q1c^T ghpc, landing on the lane that sampled c
   float gcv[2][3][2];
   {
@@ -987,7 +987,7 @@ __device__ __forceinline__ void mma3_ab(float* c, const float* ah, const float* 
 }
 
 template <class F>
-__device__ void warp_wgrad(const Call<float>& a, float* ring, int nev) {
+__device__ void warp_wgrad(const Call<float>& a, float* ring, int nev, int bar0) {
   typedef typename F::L L;
   constexpr int NST = F::NST, H = F::H, HP = F::HP, NC = F::NC;
   const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
@@ -999,7 +999,7 @@ __device__ void warp_wgrad(const Call<float>& a, float* ring, int nev) {
   for (int e = 0; e < nev; ++e) {
     const int slot = e & 1;
     const float* panel = ring + slot * ROWS * RS;
-    bar_sync(BAR_FULL0 + slot, 64);
+    bar_sync(bar0 + BAR_FULL0 + slot, 64);
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks) {
       float bxh[2], bxl[2], bph[2], bpl[2], bdh[2], bdl[2], bqh[2], bql[2];
@@ -1023,7 +1023,7 @@ __device__ void warp_wgrad(const Call<float>& a, float* ring, int nev) {
     }
     if (e + 2 < nev) {
       __threadfence_block();
-      bar_arrive(BAR_EMPTY0 + slot, 64);
+      bar_arrive(bar0 + BAR_EMPTY0 + slot, 64);
     }
   }
   float* d = a.d_weights;
@@ -1045,8 +1045,8 @@ __device__ void warp_wgrad(const Call<float>& a, float* ring, int nev) {
         atomicAdd(h < H ? d + L::Wd + o * H + h : d + L::bd + o, cWpd[m][1][i]);
       }
     }
-  bar_sync(BAR_TAIL1, 64);
-  bar_sync(BAR_TAIL2, 64);  // the adjoint warp has left ghc | ghpc and the constants panel in ring slot 0
+  bar_sync(bar0 + BAR_TAIL1, 64);
+  bar_sync(bar0 + BAR_TAIL2, 64);  // the adjoint warp has left ghc | ghpc and the constants panel in ring slot 0
   // constants' columns of the hidden layers and their biases: dW[h][NST + j] += sum_r ghc[r][h] c[r][j]; column NC = 1
   const float* panel = ring;
 #pragma unroll
@@ -1090,13 +1090,19 @@ __device__ void warp_wgrad(const Call<float>& a, float* ring, int nev) {
   }
 }
 
+// A reverse CTA holds BWD_PAIRS (adjoint, weight-gradient) warp pairs = 4 warps with the two HMMA-heavy adjoint warps at
+// warp 0 and 2: measured (tools/micro/warp_placement.cu), 225 such CTAs put every adjoint warp on a sub-partition of
+// its own, whereas 450 two-warp CTAs leave two adjoint warps on one tensor pipe in a third of the sub-partitions.
+constexpr int BWD_PAIRS = 2;
 template <class F>
 struct Smem {
   static constexpr int WRAW = (F::L::total + 3) & ~3;
   static constexpr size_t fwd_bytes = sizeof(float) * WRAW + sizeof(float4) * NT_FWD * 32;
-  static constexpr size_t bwd_base = sizeof(float) * WRAW + sizeof(float4) * NT_ALL * 32 + sizeof(float) * 2 * ROWS * RS;
-  // + the parked activations of the re-evaluated stages (KeptStore): [stages - 1][40][32]
-  static constexpr size_t bwd_bytes(int stages) { return bwd_base + sizeof(float) * (stages > 1 ? stages - 1 : 0) * 40 * 32; }
+  // per pair: the two-slot panel ring + the parked activations of the re-evaluated stages (KeptStore): [stages - 1][40][32]
+  static constexpr int pair_floats(int stages) { return 2 * ROWS * RS + (stages > 1 ? stages - 1 : 0) * 40 * 32; }
+  static constexpr size_t bwd_bytes(int stages) {
+    return sizeof(float) * WRAW + sizeof(float4) * NT_ALL * 32 + sizeof(float) * BWD_PAIRS * pair_floats(stages);
+  }
 };
 
 template <class F, class TB>
@@ -1113,20 +1119,23 @@ __global__ void __launch_bounds__(128) bbm_fwd_kernel(const Call<float> a) {
 }
 
 template <class F, class TB>
-__global__ void __launch_bounds__(64) bbm_bwd_kernel(const Call<float> a) {
+__global__ void __launch_bounds__(BWD_PAIRS * 64) bbm_bwd_kernel(const Call<float> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* w = reinterpret_cast<float*>(smem_raw);
   float4* tiles = reinterpret_cast<float4*>(w + Smem<F>::WRAW);
-  float* ring = reinterpret_cast<float*>(tiles + NT_ALL * 32);
   for (int i = threadIdx.x; i < F::L::total; i += blockDim.x) w[i] = a.weights[i];
   __syncthreads();
   build_tiles<F>(w, tiles, NT_ALL);
   __syncthreads();
-  const int n_base = blockIdx.x * ROWS;
-  if ((threadIdx.x >> 5) == 0)
-    warp_backward<F, TB>(a, n_base, w, tiles, ring, ring + 2 * ROWS * RS);
+  const int warp = threadIdx.x >> 5, pair = warp >> 1;
+  const int n_base = (blockIdx.x * BWD_PAIRS + pair) * ROWS;
+  if (n_base >= a.N) return;  // a whole pair leaves together: its named barriers are its own
+  float* ring = reinterpret_cast<float*>(tiles + NT_ALL * 32) + pair * Smem<F>::pair_floats(TB::s);
+  const int bar0 = pair * 6;
+  if ((warp & 1) == 0)
+    warp_backward<F, TB>(a, n_base, w, tiles, ring, ring + 2 * ROWS * RS, bar0);
   else
-    warp_wgrad<F>(a, ring, TB::s * (a.T - 1));
+    warp_wgrad<F>(a, ring, TB::s * (a.T - 1), bar0);
 }
 #endif  // __CUDACC__
 

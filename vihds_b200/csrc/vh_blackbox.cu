@@ -378,7 +378,8 @@ struct BbLauncher {
         cudaMemsetAsync(af.d_q_prec, 0, sizeof(float) * (size_t)af.B * af.P, stream);
       }
       cudaMemsetAsync(af.d_weights, 0, sizeof(float) * F::L::total, stream);
-      bbm::bbm_bwd_kernel<F, TB><<<(af.N + bbm::ROWS - 1) / bbm::ROWS, 64, smem, stream>>>(af);
+      const int groups = (af.N + bbm::ROWS - 1) / bbm::ROWS;
+      bbm::bbm_bwd_kernel<F, TB><<<(groups + bbm::BWD_PAIRS - 1) / bbm::BWD_PAIRS, bbm::BWD_PAIRS * 64, smem, stream>>>(af);
 #endif
     } else {
 #if VH_BB_DIR != 1
