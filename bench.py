@@ -197,8 +197,9 @@ def cpu_case(parameters, model, host, B, IW, rng, solver):
     enc = model.encoder
     dev = enc.global_free.device  # (Encoder.parameters is the spec table, as in the reference, not nn.Module.parameters)
     with torch.no_grad():
-        mu, prec = enc.q_table(Settings(observations=host["observations"].to(dev), inputs=host["inputs"].to(dev),
-                                        dev_1hot=host["dev_1hot"].to(dev)))
+        q_table = enc.q_table if dev.type == "cuda" else enc.q_table_reference  # CPU arm: the stock-PyTorch restatement
+        mu, prec = q_table(Settings(observations=host["observations"].to(dev), inputs=host["inputs"].to(dev),
+                                    dev_1hot=host["dev_1hot"].to(dev)))
     p_mu, p_prec, _, _ = parameters.prior_arrays(np.float32)
     ode = model.decoder.ode_model
     case = {

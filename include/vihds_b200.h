@@ -197,7 +197,9 @@ int vh_adam_step(int dtype, size_t n, void* param, const void* grad, void* exp_a
  * zero_grad != 0: grad is cleared once it has been consumed (optimizer.zero_grad() of the next step, training.py:333,
  * without a launch of its own).  guard: device pointer to the step's cost (or NULL): if it is NaN the parameters and
  * moments are left untouched -- the reference tests torch.isnan(elbo) BEFORE optimizer.step() (training.py:331-336) --
- * the gradient is still cleared and step[2] is incremented instead of step[0]. */
+ * the gradient is still cleared and step[2] is incremented instead of step[0].  The refusal is sticky: while step[2] != 0
+ * every later guarded call is refused as well (the reference stops training at the first NaN); the host clears step[2]
+ * to resume. */
 int vh_adam_step_dev(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq, const void* hyper,
                      void* step, int zero_grad, const void* guard, void* stream);
 

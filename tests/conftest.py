@@ -26,7 +26,7 @@ def load_case(name):
 
 
 def golden_cases():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("dataset_"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("dataset_") and "_train" not in f)
 
 
 @pytest.fixture(scope="session")

@@ -175,6 +175,69 @@ def dump_dataset(spec, tag):
     print("==> %s: %d individuals, T=%d" % (tag, len(ds), ds.n_times))
 
 
+def run_training_steps(spec="dr_constant_icml", iw=20, k=5, tag=None):
+    """k consecutive training steps of the reference's own ``Training._run_batch`` (vihds/training.py:324-340) on ONE
+    mini-batch: records what is random per step (u from numpy's RNG, the device-conditioner output) and what the
+    reference made of it (the cost of every step, every trainable parameter before the first and after the last step)."""
+    import time
+
+    args, settings, data, parameters, model, training = H.build_reference(spec, samples=iw)
+    batch = next(iter(training.train_loader))
+    us, conds, losses = [], [], []
+    orig_sample_u = model.sample_u
+
+    def sample_u(n_batch_, n_samples, device=None):
+        u = orig_sample_u(n_batch_, n_samples)
+        us.append(_np(u).copy())
+        return u
+
+    model.sample_u = sample_u
+    ode = model.decoder.ode_model
+    orig_dc = ode.device_conditioner
+
+    def device_conditioner(param, name, dev_1hot, *a, **kw):
+        out = orig_dc(param, name, dev_1hot, *a, **kw)
+        conds.append((name, _np(out).copy()))
+        return out
+
+    ode.device_conditioner = device_conditioner
+    orig_cost = training.cost
+
+    def cost(*a, **kw):
+        r = orig_cost(*a, **kw)
+        losses.append(float(r.elbo))
+        return r
+
+    training.cost = cost
+
+    class Log(object):
+        batch_feed_time = batch_train_time = 0.0
+
+    model.train()
+    init = {n: _np(w).copy() for n, w in model.named_parameters()}
+    for _ in range(k):
+        assert training._run_batch(time.time(), batch, Log())
+    final = {n: _np(w).copy() for n, w in model.named_parameters()}
+    names = sorted({n for n, _ in conds}, key=[n for n, _ in conds].index)
+    out = {
+        "spec": spec, "solver": settings.params.solver, "dtype": "float32", "model": settings.model, "steps": np.array(k),
+        "learning_rate": np.array(float(settings.params.learning_rate)),
+        "times": _np(batch.times).astype(np.float32), "inputs": _np(batch.inputs).astype(np.float32),
+        "dev_1hot": _np(batch.dev_1hot).astype(np.float32), "observations": _np(batch.observations).astype(np.float32),
+        "u": np.stack(us).astype(np.float32), "cond_names": np.array(names),
+        "cond": np.stack([np.stack([c for n, c in conds[i * len(names):(i + 1) * len(names)]]) for i in range(k)]).astype(np.float32)
+        if names else np.zeros((k, 0), np.float32),
+        "losses": np.array(losses[:k], np.float64),
+    }
+    for n, w in init.items():
+        out["init:" + n] = w
+    for n, w in final.items():
+        out["final:" + n] = w
+    name = tag or "%s_train%d_iw%d" % (spec, k, iw)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("==> %s: losses %s" % (name, " ".join("%.4f" % v for v in losses[:k])))
+
+
 SPECS = ("dr_constant_one", "dr_constant_icml", "dr_blackbox_icml", "relay_constant_precisions", "dr_constant_v2",
          "dr_constant_precisions", "dr_constant_precisions_v2", "auto_constant", "auto_constant_precisions",
          "prpr_constant", "prpr_constant_precisions")
@@ -193,6 +256,12 @@ def main(group="all"):
         dump_spec(spec)
     if group == "small":
         return small_models()
+    if group == "full":  # BASELINE sizes (B = 36 x IW = 200) of configs 3 and 5, last-timepoint states only
+        run_case("dr_blackbox_icml", "midpoint", "float32", 200, traces=False)
+        run_case("relay_constant_precisions", "midpoint", "float32", 200, traces=False)
+        return
+    if group == "train":
+        return run_training_steps("dr_constant_icml", 20, 5)
     # config 1: every fixed-step solver, fp32; fp64 for the default and the in-repo solver
     for solver in ("midpoint", "rk4", "euler", "modeuler", "modeulerwhile"):
         run_case("dr_constant_one", solver, "float32", 5, n_batch=8)
@@ -212,6 +281,9 @@ def main(group="all"):
     run_case("dr_constant_precisions", "midpoint", "float32", 8, n_batch=12)
     run_case("dr_constant_precisions_v2", "midpoint", "float32", 8, n_batch=12)
     small_models()
+    run_case("dr_blackbox_icml", "midpoint", "float32", 200, traces=False)
+    run_case("relay_constant_precisions", "midpoint", "float32", 200, traces=False)
+    run_training_steps("dr_constant_icml", 20, 5)
     dump_dataset("dr_constant_icml", "dataset_dr_icml")
     dump_dataset("relay_constant_precisions", "dataset_relay")
 

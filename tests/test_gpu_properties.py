@@ -319,14 +319,23 @@ def test_adam_dev_nan_cost_leaves_parameters_and_moments_untouched():
     torch.cuda.synchronize()
     assert torch.equal(pa, p0) and torch.equal(ma, m0) and torch.equal(va, v0)
     assert step.tolist() == [7, 0, 2, 0] and ex.state.tolist() == [1, 0, 0, 1] and not ga.any()
+    # the refusal is sticky (the reference stops training at the first NaN): a good cost does not re-open the update ...
     gr = torch.randn(n, generator=g).cuda()
     ga, pb, mb, vb = gr.clone(), p0.clone(), m0.clone(), v0.clone()
     good = torch.tensor([3.0], device="cuda")
     L.check(lib.vh_adam_allreduce_step(0, n, _p(pa), _p(ga), _p(ma), _p(va), _p(hyper), _p(step), _p(ex.state), 0, 1,
                                        _p(ex.peers), _p(good), 0.0, None))
+    torch.cuda.synchronize()
+    assert torch.equal(pa, p0) and step.tolist() == [7, 0, 3, 0] and ex.state.tolist() == [2, 0, 0, 2]
+    # ... until the host clears the counters
+    step[2] = 0
+    ex.state[3] = 0
+    ga = gr.clone()
+    L.check(lib.vh_adam_allreduce_step(0, n, _p(pa), _p(ga), _p(ma), _p(va), _p(hyper), _p(step), _p(ex.state), 0, 1,
+                                       _p(ex.peers), _p(good), 0.0, None))
     L.check(lib.vh_adam_step(0, n, _p(pb), _p(gr), _p(mb), _p(vb), 0.01, 0.9, 0.999, 1e-8, 8, None))
     torch.cuda.synchronize()
-    assert step.tolist() == [8, 0, 2, 0] and torch.allclose(pa, pb, rtol=1e-6, atol=1e-7)
+    assert step.tolist() == [8, 0, 0, 0] and torch.allclose(pa, pb, rtol=1e-6, atol=1e-7)
     ex.close()
 
 

@@ -58,10 +58,31 @@ def test_parameter_table_and_encoder_match_reference(case_name, spec, dims):
     enc = Encoder(par, dims)
     data = Settings(observations=torch.as_tensor(case["observations"]), inputs=torch.as_tensor(case["inputs"]),
                     dev_1hot=torch.as_tensor(case["dev_1hot"]))
-    q = enc(data)
-    assert np.abs(q.mu.detach().numpy() - case["q_mu"]).max() < 1e-6
-    assert (np.abs(q.prec.detach().numpy() - case["q_prec"]) / case["q_prec"]).max() < 1e-6
+    q_mu, q_prec = enc.q_table_reference(data)  # the stock-PyTorch restatement; the product path needs CUDA tensors
+    assert np.abs(q_mu.detach().numpy() - case["q_mu"]).max() < 1e-6
+    assert (np.abs(q_prec.detach().numpy() - case["q_prec"]) / case["q_prec"]).max() < 1e-6
     assert enc.p.mu.shape == (len(par.names),)
+    with pytest.raises(RuntimeError):  # no silent CPU path on the product surface
+        enc(data)
+
+
+def test_encoder_loads_and_exports_reference_state_dict():
+    """The packed heads <-> the reference's per-parameter layers (names of vihds/encoders.py): a reference checkpoint
+    loads into the packed encoder and comes back out unchanged, and the trained reference parameters of the 5-step
+    training golden give the q table the reference itself would compute from them."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "dr_constant_icml_train5_iw20.npz"))
+    cfg = _config("dr_constant_icml")
+    par = Parameters(cfg.params)
+    enc = Encoder(par, (4, 86, 2, 7))
+    sd = {k[len("final:"):]: torch.as_tensor(z[k]) for k in z.files if k.startswith("final:")}
+    enc.load_reference_state_dict(sd)
+    out = enc.reference_state_dict()
+    assert set(out) == {k for k in sd if k.startswith("encoder.")}
+    for k, v in out.items():
+        assert torch.equal(v.reshape(-1), sd[k].reshape(-1).to(v.dtype)), k
+    # a row of the packed local heads is the reference's nn.Linear(., 1) of that parameter
+    k = [s.name for s in enc.local].index("tlag")
+    assert torch.equal(enc.local_heads.weight[2 * k + 1], sd["encoder.q_local_defs.tlag.layers.log_prec.weight"][0])
 
 
 def test_dense_distribution_table_matches_oracle():

@@ -199,7 +199,8 @@ __global__ void adam_kernel(size_t n, R* __restrict__ p, const R* __restrict__ g
 // (no separate increment launch).  zero_grad: the gradient is cleared once consumed (no separate fill launch).
 // guard: the step's cost on the device (or NULL).  A NaN cost means NaN gradients (training.py:331-333 stops BEFORE
 // optimizer.step()): the update of parameters and moments is skipped, the gradient is still cleared, step[0] stays and
-// step[2] counts the skipped call -- the host reads it when it next looks at the cost.
+// step[2] counts the skipped call -- the host reads it when it next looks at the cost.  The refusal is sticky (every
+// later guarded call is skipped too until the host clears step[2]): the reference stops training at the first NaN.
 template <typename R>
 __global__ void adam_dev_kernel(size_t n, R* __restrict__ p, R* __restrict__ g, R* __restrict__ m, R* __restrict__ v,
                                 const double* __restrict__ hyper, long long* step, int zero_grad, const R* __restrict__ guard) {
@@ -211,7 +212,7 @@ __global__ void adam_dev_kernel(size_t n, R* __restrict__ p, R* __restrict__ g, 
     s_bc[0] = (R)(1.0 - pow(hyper[1], t));
     s_bc[1] = (R)sqrt(1.0 - pow(hyper[2], t));
     const R c = guard ? *guard : R(0);
-    s_skip = c != c;
+    s_skip = (c != c) || (guard && *(volatile long long*)(step + 2) != 0);  // sticky: training stops at the first NaN
   }
   __syncthreads();
   const bool skip = s_skip != 0;

@@ -538,9 +538,9 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
     for (int s = role; s < M::NSLOT; s += WS_WARPS) {
       const int src = a.slot_src[s];
       if (src < 0 && src != VH_SLOT_UNUSED) a.d_extra[(size_t)(-1 - src) * N + n] = gloc[s];
-      }
-      }
     }
+  }
+}
 
 inline int pick_block(int N) {
   // small batches are latency-bound: spread warps over as many SMs as possible (148 SMs x 4 schedulers)
@@ -553,13 +553,11 @@ template <typename R>
 struct FwdLauncher {
   Call<R> a;
   cudaStream_t stream;
-  // VIHDS_FWD_TEAM=0|1 overrides (tests / measurements)
+  // VIHDS_FWD_TEAM=0|1 overrides (tests / measurements; read per call so that one process can compare the forms)
   template <class M>
   static bool use_team(int block) {
-    static const int mode = [] {
-      const char* m = getenv("VIHDS_FWD_TEAM");
-      return !m ? -1 : atoi(m);
-    }();
+    const char* m = getenv("VIHDS_FWD_TEAM");
+    const int mode = (!m || !*m) ? -1 : atoi(m);
     return mode >= 0 ? mode != 0 : block == 32;
   }
   template <class M, class TB>
@@ -590,13 +588,11 @@ struct BwdLauncher {
   Call<R> a;
   cudaStream_t stream;
   // warp-specialised kernel: latency-bound launches (the 32-thread-CTA regime), every white-box model.
-  // VIHDS_BWD_WS=0|1 overrides (tests / measurements).
+  // VIHDS_BWD_WS=0|1 overrides (tests / measurements; read per call).
   template <class M>
   static bool use_ws(int block) {
-    static const int mode = [] {
-      const char* m = getenv("VIHDS_BWD_WS");
-      return !m ? -1 : atoi(m);
-    }();
+    const char* m = getenv("VIHDS_BWD_WS");
+    const int mode = (!m || !*m) ? -1 : atoi(m);
     return mode >= 0 ? mode != 0 : block == 32;
   }
   template <class M, class TB>

@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(size_t n, size_t n_
     if (ticket == (unsigned long long)gridDim.x - 1) {
       s_last = 1;
       const R c = guard ? *guard : R(0);
-      const unsigned long long bad = (c != c) ? 1ULL : 0ULL;
+      // sticky, like vh_adam_step_dev: state[3] advances on every rank together, so the verdict stays collective
+      const unsigned long long bad = ((c != c) || (guard && *(volatile long long*)(state + 3) != 0)) ? 1ULL : 0ULL;
       for (int r = 0; r < world; ++r) {
         unsigned long long* flags = reinterpret_cast<unsigned long long*>(peers[r]);
         flags[(2 + par) * VH_PEER_MAX_WORLD + rank] = bad;  // ordered before the flag by the release below

@@ -1,10 +1,12 @@
 """Amortised encoder q(theta | x, d) producing the dense q table the fused kernel consumes.
 
-Takes over vihds/encoders.py (reference): the Conv1d -> AvgPool1d -> Linear -> tanh feature extractor
-(encoders.py:16-55) is kept as stock PyTorch (cuDNN / cuBLAS; SURVEY.md section 2 row 9: out of scope for hand-written
-kernels), but the 2 x n_param ``Linear(., 1)`` heads that the reference evaluates one by one (encoders.py:126-253,
-:383-404) are packed into ONE weight matrix per group so that all local heads are a single GEMM, all
-global-conditioned heads another, and the result is written straight into ``q_mu`` / ``q_prec`` of shape [B, P].
+Takes over vihds/encoders.py (reference).  On the product path the whole encoder -- Conv1d -> AvgPool1d -> Linear ->
+tanh feature extractor (encoders.py:16-55) and the 2 x n_param ``Linear(., 1)`` heads that the reference evaluates one
+by one (encoders.py:126-253, :383-404) -- is ONE launch of libvihds_b200.so forward (vh_encoder_fwd) and two backward
+(vh_encoder_bwd), bound here as ``FusedEncoder``; the heads are packed into one weight matrix per group and the result
+is written straight into ``q_mu`` / ``q_prec`` of shape [B, P].  ``q_table_reference`` is the same computation in stock
+PyTorch ops: the fp32 reference the kernels are tested against (and what the CPU-only tests use); it is never taken
+silently -- ``q_table`` raises on CPU tensors.
 
 Initialisation draws from the torch RNG in exactly the reference's order (conv, hidden layer, then per local
 parameter the ``mu`` head and the ``log_prec`` head, then the global-conditioned heads), so that with the same seed
@@ -135,9 +137,15 @@ class Encoder(nn.Module):
         self.const = parameters.group("constant")
 
         def cond_of(group, default):
-            c = group[0].conditioning if group else None
-            c = c or default
-            return bool(c.get("treatments", False)), bool(c.get("devices", False))
+            """One conditioning per group: the packed heads share their inputs.  The reference builds every Q_Local /
+            Q_Global_Cond from its own description.conditioning (encoders.py:125-175); a spec that mixes conditionings
+            inside a group has no packed equivalent here and is refused rather than computed wrongly."""
+            conds = [(bool((sp.conditioning or default).get("treatments", False)), bool((sp.conditioning or default).get("devices", False)))
+                     for sp in group]
+            if len(set(conds)) > 1:
+                raise NotImplementedError("parameters of one group with different `conditioning` entries (%s) are not supported "
+                                          "by the packed encoder heads" % ", ".join(sp.name for sp in group))
+            return conds[0] if conds else (bool(default.get("treatments", False)), bool(default.get("devices", False)))
 
         self.local_cond = cond_of(self.local, {"treatments": False, "devices": False})
         self.gcond_cond = cond_of(self.gcond, {"treatments": False, "devices": False})
@@ -189,11 +197,46 @@ class Encoder(nn.Module):
         return (cv.conv.weight, cv.conv.bias, cv.lin.weight, cv.lin.bias, self.local_heads.weight, self.local_heads.bias,
                 self.gcond_heads.weight, self.global_free)
 
+    # reference checkpoints -------------------------------------------------------------------------------------
+    def reference_parameter_map(self):
+        """[(reference parameter name (vihds/encoders.py module tree), tensor view of this module)]: the reference keeps
+        one nn.Linear pair per local / global-conditioned parameter (``q_local_defs.<name>.layers.{mu,log_prec}``,
+        encoders.py:126-175) and one free (mu, log_prec) pair per global one (``q_global_defs.<name>.free_params``,
+        :201-206); here they are rows of the packed heads / entries of ``global_free``."""
+        cv = self.conditional
+        out = [("conditional.conv.weight", cv.conv.weight), ("conditional.conv.bias", cv.conv.bias),
+               ("conditional.lin.weight", cv.lin.weight), ("conditional.lin.bias", cv.lin.bias)]
+        for k, sp in enumerate(self.local):
+            for j, part in enumerate(("mu", "log_prec")):
+                out.append(("q_local_defs.%s.layers.%s.weight" % (sp.name, part), self.local_heads.weight[2 * k + j:2 * k + j + 1]))
+                out.append(("q_local_defs.%s.layers.%s.bias" % (sp.name, part), self.local_heads.bias[2 * k + j:2 * k + j + 1]))
+        for k, sp in enumerate(self.gcond):
+            for j, part in enumerate(("mu", "log_prec")):
+                out.append(("q_global_cond_defs.%s.layers.%s.weight" % (sp.name, part), self.gcond_heads.weight[2 * k + j:2 * k + j + 1]))
+        for k, sp in enumerate(self.glob):
+            for j, part in enumerate(("mu", "log_prec")):
+                out.append(("q_global_defs.%s.free_params.%s" % (sp.name, part), self.global_free[2 * k + j:2 * k + j + 1]))
+        return out
+
+    def load_reference_state_dict(self, sd, prefix="encoder."):
+        """Copy a state_dict of the reference's Encoder (names as in vihds/encoders.py) into the packed parameters."""
+        with torch.no_grad():
+            for name, view in self.reference_parameter_map():
+                src = torch.as_tensor(sd[prefix + name]).to(device=view.device, dtype=view.dtype)
+                view.copy_(src.reshape(view.shape))
+
+    def reference_state_dict(self, prefix="encoder."):
+        """The trainable parameters under the reference's names (a checkpoint the reference's Encoder can load)."""
+        return {prefix + name: view.detach().clone() for name, view in self.reference_parameter_map()}
+
     def q_table(self, data):
         """(q_mu [B,P], q_prec [B,P]).  On a CUDA device: the fused encoder kernels (one launch forward, two backward);
         ``q_table_reference`` is the same computation in stock PyTorch ops (any device) -- the fp32 reference the fused
         kernels are tested against."""
-        if self.fused and data.observations.is_cuda:
+        if not data.observations.is_cuda:
+            raise RuntimeError("vihds_b200: Encoder.q_table runs the fused CUDA encoder kernels and needs CUDA tensors (got %s); "
+                               "q_table_reference is the stock-PyTorch restatement the kernels are tested against" % data.observations.device)
+        if self.fused:
             return FusedEncoder.apply(self, data.observations, data.inputs, data.dev_1hot, *self.fused_parameters())
         return self.q_table_reference(data)
 

@@ -316,5 +316,9 @@ class FlatAdam(object):
                                           _ptr(guard), _stream()))
 
     def skipped_steps(self):
-        """Number of updates the device-side NaN guard has refused so far (synchronises)."""
+        """Number of updates the device-side NaN guard has refused so far (synchronises).  Non-zero means training has
+        stopped: the guard is sticky, like the reference's early exit at the first NaN cost."""
         return int(self.step_dev[2].item())
+
+    def clear_skipped(self):
+        self.step_dev[2] = 0

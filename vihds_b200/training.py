@@ -8,7 +8,8 @@ Two equivalent ways to take a step:
 
 * ``Training._run_batch(batch)``   eager, reference-shaped: ``model(batch, IW)`` -> ``cost`` -> ``backward`` -> Adam.
   Every arithmetic op of the hot path is a launch of libvihds_b200.so through engine.* autograd Functions.
-* ``GraphedStep``                  the production form: static device buffers and pre-built C-ABI descriptors, the
+* ``GraphedStep``                  the production form, and what ``Training.run`` uses on a CUDA device (one instance per
+  batch shape, ``Training.graphed_step``): static device buffers and pre-built C-ABI descriptors, the
   whole step captured as two CUDA graphs -- encoder forward + device conditioner | fused forward, IWAE cost + gradient,
   fused reverse sweep, encoder backward, gradient all-reduce, Adam -- so a step costs the host two graph launches (the
   end-to-end entry slips the host-to-device copy of ``u`` under the first one).
@@ -119,16 +120,60 @@ class Training(object):
             result, theta, q, p = self.model(data, samples)
             return self.cost(data, result, theta, q, p, full_output=True)
 
-    def run(self, epochs=None, loader=None, verbose=True):
-        """Epoch loop (training.py:342-383) over shuffled mini-batches drawn with numpy's global RNG."""
+    def graphed_step(self, B, IW, T):
+        """The CUDA-graph form of the step for one batch shape, built on first use and reused (the ragged last
+        mini-batch of an epoch gets its own capture)."""
+        cache = self.__dict__.setdefault("_graphed", {})
+        key = (int(B), int(IW), int(T))
+        if key not in cache:
+            want = self.model.want_predict
+            self.model.want_predict = False  # nothing reads the x_predict trace in a training step
+            cache[key] = GraphedStep(self, *key)
+            self.model.want_predict = want
+        return cache[key]
+
+    def _run_batch_graphed(self, batch, u=None):
+        """Same step as ``_run_batch`` through ``GraphedStep``: two graph launches, no host synchronisation.  The NaN
+        check of training.py:331-333 happens ON THE DEVICE (the Adam kernel refuses the update and every later one, see
+        vh_adam_step_dev); ``run`` looks at the refusal counter when it next synchronises."""
+        IW = self.args.train_samples
+        gs = self.graphed_step(len(batch.inputs), IW, batch.times.numel())
+        gs.load_batch(batch)
+        if u is None:
+            u = self.model.sample_u(len(batch.inputs), IW)  # numpy's global RNG, as vae.py:22-24
+        gs.load_u(u.to(device=gs.u.device, dtype=gs.u.dtype, non_blocking=True) if not u.is_cuda else u)
+        gs.draw_conditioner()  # torch CPU RNG, draw for draw what condition_theta consumes in the reference
+        self.last_cost = gs.step()
+        return gs
+
+    def run(self, epochs=None, loader=None, verbose=True, graphed=None):
+        """Epoch loop (training.py:342-383) over shuffled mini-batches drawn with numpy's global RNG.  On a CUDA device
+        the steps go through the CUDA-graph form (``graphed=False`` forces the eager, reference-shaped ``_run_batch``);
+        ``self.path_taken`` records which one ran and ``self.costs`` the cost of every step of the last epoch."""
         epochs = epochs or self.args.epochs
         ds, ids = self.dataset_pair.train.dataset, np.asarray(self.dataset_pair.train.indices)
+        if graphed is None:
+            graphed = torch.device(self.settings.device).type == "cuda"
+        self.path_taken = "graphed" if graphed else "eager"
         for epoch in range(1, epochs + 1):
             self.set_epoch(epoch - 1)
             order = torch.randperm(len(ids)).numpy()
+            costs = []
             for s in range(0, len(ids), self.n_batch):
                 batch = batch_of(ds, ids[order[s:s + self.n_batch]], self.settings.device, self.settings.dtype)
-                if not self._run_batch(batch):
+                if graphed:
+                    self._run_batch_graphed(batch)
+                    costs.append(self.last_cost.clone())  # device tensors: no synchronisation inside the epoch
+                else:
+                    if not self._run_batch(batch):
+                        return False
+                    costs.append(self.last_cost)
+            self.costs = [float(c) for c in costs]  # one synchronisation per epoch
+            if graphed:
+                for gs in self._graphed.values():
+                    gs.check_health()
+                if self.optimizer.skipped_steps() > 0:  # the first NaN cost froze the parameters, like the reference's early exit
+                    print("\nELBO is NaN. Stopping training.")
                     return False
             test_epoch = getattr(self.args, "test_epoch", 0)
             if test_epoch and epoch % test_epoch == 0:

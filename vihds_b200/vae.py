@@ -1,8 +1,8 @@
 """VAE assembly with the reference's surface (vihds/vae.py:13-51): ``BaseVAE(encoder, decoder, device)``,
 ``sample_u``, ``forward(data, samples) -> (result, conditioned_theta, q, p)``, ``build_model``.
 
-``forward`` is where the hot path starts: the encoder (stock PyTorch) produces the dense q table, and everything
-from ``q.sample`` to the per-sample ELBO terms is ONE launch of the fused CUDA kernel (Decoder.fused)."""
+``forward`` is where the hot path starts: the fused encoder kernel (vh_encoder_fwd) produces the dense q table, and
+everything from ``q.sample`` to the per-sample ELBO terms is ONE launch of the fused CUDA kernel (Decoder.fused)."""
 import numpy as np
 import torch
 from torch import nn
