@@ -63,6 +63,65 @@ for mode in ("peer", "nccl"):
 d = float((flats["peer"] - flats["nccl"]).abs().max())
 print("rank %d: max |flat(peer) - flat(nccl)| after 3 steps = %.3e" % (rank, d), flush=True)
 ok = ok and d < 2e-3  # Adam moves every parameter by ~lr = 0.01 per step; fp32 atomics order differs between runs
+# collective NaN verdict: one rank's cost is NaN -> EVERY rank skips the update (and keeps skipping: the guard is sticky)
+n = 5000
+pa = torch.randn(n, generator=torch.Generator().manual_seed(1)).to(dev)
+p0 = pa.clone()
+ma, va = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+hyper = torch.tensor([0.01, 0.9, 0.999, 1e-8], dtype=torch.float64, device=dev)
+step = torch.zeros(4, dtype=torch.int64, device=dev)
+ex = PeerGradientExchange(n, torch.float32, dev, pg)
+for it, bad_rank in enumerate((None, 1 % world, None)):
+    ga = torch.randn(n, generator=torch.Generator().manual_seed(50 + it)).to(dev)
+    cost = torch.tensor([float("nan") if rank == bad_rank else 1.0], device=dev)
+    L.check(lib.vh_adam_allreduce_step(0, n, _p(pa), _p(ga), _p(ma), _p(va), _p(hyper), _p(step), _p(ex.state),
+                                       rank, world, _p(ex.peers), _p(cost), 0.0, None))
+    torch.cuda.synchronize()
+    if it == 0:
+        p1 = pa.clone()
+        ok = ok and not torch.equal(p1, p0) and step.tolist() == [1, 0, 0, 0]
+    else:
+        ok = ok and torch.equal(pa, p1) and step.tolist() == [1, 0, it, 0] and ex.state.tolist()[2:] == [0, it]
+print("rank %d: NaN on one rank -> all ranks skipped: steps %s state %s" % (rank, step.tolist(), ex.state.tolist()), flush=True)
+dist.barrier()
+ex.close()
+
+# rank-count invariance WITHOUT pinning the conditioner: the individuals of a global batch sharded over the ranks must
+# give what one process computes for the whole batch (device conditioner on global sample indices, u sliced, cost / B_global)
+from vihds_b200.distributed import shard_bounds
+Bg, IWs = 6 * world, 16
+res = {}
+for mode in ("global", "sharded"):
+    torch.manual_seed(0)
+    settings, parameters, model, training, host, B, IW, T, rng = bench.build_workload("dr_constant_icml", 0, 1, dev, Bg, IWs)
+    model.want_predict = False
+    lo, hi = shard_bounds(Bg, world, rank) if mode == "sharded" else (0, Bg)
+    gs = GraphedStep(training, hi - lo, IWs, T, b_total=Bg, process_group=pg if mode == "sharded" else None, b_offset=lo)
+    hd = {k: (v if k == "times" else v[lo:hi]).to(dev) for k, v in host.items()}
+    gs.load_batch(hd)
+    if mode == "sharded":
+        gs.load_global_devices(host["dev_1hot"].to(dev))
+    ug = torch.Generator().manual_seed(99)
+    torch.manual_seed(123)  # the conditioner weights come from the torch CPU RNG: same stream on every rank and in both modes
+    costs = []
+    for i in range(3):
+        u = torch.randn(Bg, IWs, parameters.n_theta, generator=ug)
+        gs.load_u(u[lo:hi].contiguous().to(dev))
+        gs.draw_conditioner()
+        c = gs.step().clone()
+        if mode == "sharded":
+            dist.all_reduce(c, group=pg)
+        costs.append(float(c.item()))
+    torch.cuda.synchronize()
+    res[mode] = (costs, training.optimizer.flat.clone())
+    if gs.exchange is not None:
+        dist.barrier()
+        gs.exchange.close()
+dc = max(abs(a - b) / abs(b) for a, b in zip(res["sharded"][0], res["global"][0]))
+dp = float((res["sharded"][1] - res["global"][1]).abs().max())
+print("rank %d: sharded vs one-process global batch: costs rel %.2e, params max abs %.2e (%s | %s)" % (
+    rank, dc, dp, res["sharded"][0], res["global"][0]), flush=True)
+ok = ok and dc < 1e-5 and dp < 2e-3
 dist.barrier()
 print("rank %d %s" % (rank, "PEER_CHECK_OK" if ok else "PEER_CHECK_FAILED"), flush=True)
 os._exit(0 if ok else 1)
