@@ -59,7 +59,13 @@ enum vh_model {
   VH_MODEL_AUTO_CONSTANT_PRECISIONS = 8,  /* models/auto_constant.py:93-132 */
   VH_MODEL_PRPR_CONSTANT = 9,             /* models/prpr_constant.py:61-81 */
   VH_MODEL_PRPR_CONSTANT_PRECISIONS = 10, /* models/prpr_constant.py:84-130 */
-  VH_MODEL_COUNT = 11
+  /* the next four do not run in the reference as shipped (OdeModel.init_with_params / OdeFunc.__init__ arity,
+   * SURVEY.md section 8c); their parity target is the reference under the two-line monkeypatch of oracle/ref_harness.py */
+  VH_MODEL_INDUCER_CONSTANT = 11,             /* models/inducer_constant.py:82-111 */
+  VH_MODEL_INDUCER_CONSTANT_PRECISIONS = 12,  /* models/inducer_constant.py:114-151 */
+  VH_MODEL_DEGRADER_CONSTANT = 13,            /* models/degrader_constant.py:146-207 */
+  VH_MODEL_DEGRADER_CONSTANT_PRECISIONS = 14, /* models/degrader_constant.py:210-269 */
+  VH_MODEL_COUNT = 15
 };
 
 /* params.solver values (vihds/ode.py:75-81) */
@@ -83,7 +89,7 @@ typedef struct vh_problem {
   int dtype;  /* vh_dtype */
   int B, IW, T;
   int P; /* sampled parameters = columns of u (0 in vh_simulate) */
-  int C; /* treatments per individual (2: C6, C12) */
+  int C; /* treatments per individual (2: C6, C12; degrader: 3: + Ara; inducer: 1: Ara) */
   int D; /* device one-hot width (used by the black-box model only) */
   int E; /* rows of `extra` (black-box: E == n_y device offsets ADDED to the sampled y_k, see vh_bb.cuh) */
   int n_hidden; /* NeuralPrecisions hidden width (0 = single linear layer), black-box: precision-net hidden width */

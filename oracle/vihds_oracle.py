@@ -115,13 +115,19 @@ def _treatments(inputs, n_iwae):
     return c6, c12
 
 
+def _pbad(ara, th):
+    """models/inducer_constant.py:48-55, models/degrader_constant.py:79-86: arabinose promoter activity."""
+    nA = torch.clamp(th["nA"], 0.5, 3.0)
+    return (ara.pow(nA) + th["eA"] * th["KAra"].pow(nA)) / (ara.pow(nA) + th["KAra"].pow(nA))
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # white-box right-hand sides
 # ----------------------------------------------------------------------------------------------------------------
 class DrConstantRHS:
     """models/dr_constant.py:14-112 (v1 :62-68, v2 :69-73); relay extension models/relay_constant.py:13-134."""
 
-    def __init__(self, th, inputs, version=1, precisions=None, relay=False):
+    def __init__(self, th, inputs, version=1, precisions=None, relay=False, degrader=False):
         n_iwae = th["r"].shape[1]
         c6, c12 = _treatments(inputs, n_iwae)
         cl = torch.clamp
@@ -144,8 +150,14 @@ class DrConstantRHS:
         if relay:
             self.dlasI, self.dluxI = cl(th["dlasI"], 1e-12, 5.0), cl(th["dluxI"], 1e-12, 5.0)
             self.KC6, self.KC12, self.Klux, self.Klas = th["KC6"], th["KC12"], th["Klux"], th["Klas"]
+        self.degrader = degrader
+        if degrader:  # models/degrader_constant.py:72-88
+            ara = torch.clamp(torch.exp(inputs[:, 2:3]) - 1.0, 1e-12, 1e6).expand(-1, n_iwae)
+            self.aI, self.daiiA = th["aI"], th["daiiA"]
+            self.PBAD = _pbad(ara, th)
+            self.rC6, self.rC12 = th["dA6"] * c6, th["dA12"] * c12
         self.precisions = precisions
-        self.n_species = 12 if relay else 8
+        self.n_species = 12 if relay else (11 if degrader else 8)
 
     def __call__(self, t, state):
         s = state
@@ -174,6 +186,9 @@ class DrConstantRHS:
                 (self.KC6 * self.rc * x * luxI) / (1.0 + luxI / self.Klux),
                 (self.KC12 * self.rc * x * lasI) / (1.0 + lasI / self.Klas),
             ]
+        if self.degrader:  # models/degrader_constant.py:128-131, verbatim (the constant loss is not multiplied by AiiA)
+            aiiA = s[:, :, 8]
+            d += [self.rc * self.aI * self.PBAD - (self.daiiA + (gamma * aiiA)), x * self.rC6 * aiiA, x * self.rC12 * aiiA]
         dX = torch.stack(d, dim=2)
         if self.precisions is not None:
             return torch.cat([dX, self.precisions(t, state, None)], dim=2)
@@ -205,6 +220,32 @@ class GrowthRHS:
         else:
             f530, f480 = state[:, :, 2], state[:, :, 3]
         d += [self.rc * self.a530 - gamma * f530, self.rc * self.a480 - gamma * f480]
+        dX = torch.stack(d, dim=2)
+        if self.precisions is not None:
+            return torch.cat([dX, self.precisions(t, state, None)], dim=2)
+        return dX
+
+
+class InducerRHS:
+    """models/inducer_constant.py:12-84: growth + dilution, YFP expressed from the arabinose promoter PBAD
+    (5 species: OD, RFP, YFP, F530, F480)."""
+
+    def __init__(self, th, inputs, precisions=None):
+        cl = torch.clamp
+        n_iwae = th["r"].shape[1]
+        ara = cl(torch.exp(inputs[:, 0:1]) - 1.0, 1e-12, 1e6).expand(-1, n_iwae)
+        self.r, self.K = cl(th["r"], 0.0, 4.0), cl(th["K"], 0.0, 4.0)
+        self.tlag, self.rc, self.a530, self.a480 = th["tlag"], th["rc"], th["a530"], th["a480"]
+        self.drfp, self.dyfp = cl(th["drfp"], 1e-12, 2.0), cl(th["dyfp"], 1e-12, 2.0)
+        self.aYFP = th["aYFP_Inducer"]
+        self.PBAD = _pbad(ara, th)
+        self.precisions = precisions
+
+    def __call__(self, t, state):
+        x, rfp, yfp, f530, f480 = (state[:, :, i] for i in range(5))
+        gamma = self.r * torch.sigmoid(4.0 * (t - self.tlag)) * (1.0 - x / self.K)
+        d = [gamma * x, self.rc - (gamma + self.drfp) * rfp, self.rc * self.aYFP * self.PBAD - (gamma + self.dyfp) * yfp,
+             self.rc * self.a530 - gamma * f530, self.rc * self.a480 - gamma * f480]
         dX = torch.stack(d, dim=2)
         if self.precisions is not None:
             return torch.cat([dX, self.precisions(t, state, None)], dim=2)
@@ -286,6 +327,8 @@ MODEL_FAMILY = {
     "dr_blackbox": ("blackbox", 0, True),
     "auto_constant": ("auto", 1, False), "auto_constant_precisions": ("auto", 1, True),
     "prpr_constant": ("prpr", 1, False), "prpr_constant_precisions": ("prpr", 1, True),
+    "inducer_constant": ("inducer", 1, False), "inducer_constant_precisions": ("inducer", 1, True),
+    "degrader_constant": ("degrader", 1, False), "degrader_constant_precisions": ("degrader", 1, True),
 }
 
 
@@ -300,7 +343,7 @@ def decode(model, solver, th, times, inputs, dev_1hot, weights=None, params=None
     B, IW = any_th.shape
     zero = torch.zeros(B, IW, dtype=any_th.dtype)
     weights = weights or {}
-    if family in ("dr", "relay"):
+    if family in ("dr", "relay", "degrader"):
         prec = None
         if dyn_prec:
             prec = NeuralPrecisionsOracle({k[len("precisions."):]: v for k, v in weights.items()}, torch.tanh)
@@ -308,9 +351,20 @@ def decode(model, solver, th, times, inputs, dev_1hot, weights=None, params=None
         if family == "relay":
             c6, c12 = _treatments(inputs, IW)
             x0 += [th["init_luxI"], th["init_lasI"], c6, c12]
+        if family == "degrader":  # models/degrader_constant.py:168-196
+            c6, c12 = _treatments(inputs, IW)
+            x0 += [th["init_aiiA"], c6, c12]
         if dyn_prec:
             x0 += [th["init_prec_x"], th["init_prec_rfp"], th["init_prec_yfp"], th["init_prec_cfp"]]
-        f = DrConstantRHS(th, inputs, version=version, precisions=prec, relay=(family == "relay"))
+        f = DrConstantRHS(th, inputs, version=version, precisions=prec, relay=(family == "relay"), degrader=(family == "degrader"))
+    elif family == "inducer":  # models/inducer_constant.py:92-98, :123-142
+        prec = None
+        if dyn_prec:
+            prec = NeuralPrecisionsOracle({k[len("precisions."):]: v for k, v in weights.items()}, torch.tanh)
+        x0 = [th["init_x"], th["init_rfp"], th["init_yfp"], zero, zero]
+        if dyn_prec:
+            x0 += [th["init_prec_x"], th["init_prec_rfp"], th["init_prec_yfp"], th["init_prec_cfp"]]
+        f = InducerRHS(th, inputs, precisions=prec)
     elif family in ("auto", "prpr"):
         prec = None
         if dyn_prec:
@@ -335,6 +389,8 @@ def decode(model, solver, th, times, inputs, dev_1hot, weights=None, params=None
     od = x_states[:, :, 0, :]
     if family in ("blackbox", "auto"):  # models/dr_blackbox.py:112-121, models/auto_constant.py:81-89
         obs = [od, od * x_states[:, :, 1, :], od * x_states[:, :, 2, :], od * x_states[:, :, 3, :]]
+    elif family == "inducer":  # models/inducer_constant.py:102-110
+        obs = [od, od * x_states[:, :, 1, :], od * (x_states[:, :, 2, :] + x_states[:, :, 3, :]), od * x_states[:, :, 4, :]]
     else:
         obs = [od, od * x_states[:, :, 1, :], od * (x_states[:, :, 2, :] + x_states[:, :, 4, :]),
                od * (x_states[:, :, 3, :] + x_states[:, :, 5, :])]

@@ -240,7 +240,7 @@ def run_training_steps(spec="dr_constant_icml", iw=20, k=5, tag=None):
 
 SPECS = ("dr_constant_one", "dr_constant_icml", "dr_blackbox_icml", "relay_constant_precisions", "dr_constant_v2",
          "dr_constant_precisions", "dr_constant_precisions_v2", "auto_constant", "auto_constant_precisions",
-         "prpr_constant", "prpr_constant_precisions")
+         "prpr_constant", "prpr_constant_precisions", "inducer_constant_precisions", "degrader_constant_precisions")
 
 
 def small_models():
@@ -251,11 +251,22 @@ def small_models():
     run_case("prpr_constant", "modeuler", "float32", 8, n_batch=12)
 
 
+def extra_models():
+    """inducer / degrader: broken as shipped like relay, runnable under the same monkeypatch."""
+    run_case("inducer_constant_precisions", "midpoint", "float32", 8, n_batch=12)
+    run_case("inducer_constant_precisions", "midpoint", "float64", 8, n_batch=6)
+    run_case("degrader_constant_precisions", "midpoint", "float32", 8, n_batch=12)
+    run_case("degrader_constant_precisions", "midpoint", "float64", 8, n_batch=6)
+    run_case("degrader_constant_precisions", "modeuler", "float32", 8, n_batch=12)
+
+
 def main(group="all"):
     for spec in SPECS:
         dump_spec(spec)
     if group == "small":
         return small_models()
+    if group == "extra":
+        return extra_models()
     if group == "full":  # BASELINE sizes (B = 36 x IW = 200) of configs 3 and 5, last-timepoint states only
         run_case("dr_blackbox_icml", "midpoint", "float32", 200, traces=False)
         run_case("relay_constant_precisions", "midpoint", "float32", 200, traces=False)
@@ -281,6 +292,7 @@ def main(group="all"):
     run_case("dr_constant_precisions", "midpoint", "float32", 8, n_batch=12)
     run_case("dr_constant_precisions_v2", "midpoint", "float32", 8, n_batch=12)
     small_models()
+    extra_models()
     run_case("dr_blackbox_icml", "midpoint", "float32", 200, traces=False)
     run_case("relay_constant_precisions", "midpoint", "float32", 200, traces=False)
     run_training_steps("dr_constant_icml", 20, 5)

@@ -12,7 +12,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 MODEL_IDS = {"dr_constant": 0, "dr_constant_v2": 1, "dr_constant_precisions": 2, "dr_constant_precisions_v2": 3,
              "relay_constant": 4, "relay_constant_precisions": 5, "dr_blackbox": 6, "auto_constant": 7,
-             "auto_constant_precisions": 8, "prpr_constant": 9, "prpr_constant_precisions": 10}
+             "auto_constant_precisions": 8, "prpr_constant": 9, "prpr_constant_precisions": 10, "inducer_constant": 11,
+             "inducer_constant_precisions": 12, "degrader_constant": 13, "degrader_constant_precisions": 14}
 SOLVER_IDS = {"euler": 0, "midpoint": 1, "rk4": 2, "modeuler": 3, "modeulerwhile": 4}
 
 

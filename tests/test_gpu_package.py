@@ -70,6 +70,8 @@ def pin_conditioner(model, case):
     ("dr_blackbox_icml_midpoint_f32_iw8", "dr_blackbox_icml", None),
     ("auto_constant_precisions_midpoint_f32_iw8", "auto_constant_precisions", (4, 100, 1, 1)),
     ("prpr_constant_midpoint_f32_iw8", "prpr_constant", (4, 200, 1, 1)),
+    ("inducer_constant_precisions_midpoint_f32_iw8", "inducer_constant_precisions", (4, 100, 1, 1)),
+    ("degrader_constant_precisions_midpoint_f32_iw8", "degrader_constant_precisions", (4, 135, 3, 1)),
 ])
 def test_model_forward_cost_backward_match_reference(case_name, spec, dims):
     case = load_case(case_name)

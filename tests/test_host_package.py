@@ -30,7 +30,9 @@ def _config(spec):
 CASES = [("dr_constant_icml_midpoint_f32_iw8", "dr_constant_icml", (4, 86, 2, 7)),
          ("dr_constant_one_midpoint_f32_iw5", "dr_constant_one", (4, 100, 2, 1)),
          ("relay_constant_precisions_midpoint_f32_iw8", "relay_constant_precisions", (4, 99, 2, 1)),
-         ("dr_blackbox_icml_midpoint_f32_iw8", "dr_blackbox_icml", (4, 86, 2, 7))]
+         ("dr_blackbox_icml_midpoint_f32_iw8", "dr_blackbox_icml", (4, 86, 2, 7)),
+         ("inducer_constant_precisions_midpoint_f32_iw8", "inducer_constant_precisions", (4, 100, 1, 1)),
+         ("degrader_constant_precisions_midpoint_f32_iw8", "degrader_constant_precisions", (4, 135, 3, 1))]
 
 
 def test_device_bookkeeping_icml():

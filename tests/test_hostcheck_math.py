@@ -40,7 +40,7 @@ def test_host_math_matches_reference(hc, name):
     p = H.make_problem(case, src, 0 if extra is None else extra.shape[0])
     B, IW, P, T = p.B, p.IW, p.P, p.T
     N = B * IW
-    S = {0: 8, 1: 8, 2: 12, 3: 12, 4: 12, 5: 16, 6: 10, 7: 4, 8: 8, 9: 6, 10: 10}[model]
+    S = {0: 8, 1: 8, 2: 12, 3: 12, 4: 12, 5: 16, 6: 10, 7: 4, 8: 8, 9: 6, 10: 10, 11: 5, 12: 9, 13: 11, 14: 15}[model]
     lo, hi = H.clip_bounds(case)
     keep = dict(
         times=case["times"].astype(dt), u=np.ascontiguousarray(case["u"].reshape(N, P)), q_mu=case["q_mu"].astype(dt),

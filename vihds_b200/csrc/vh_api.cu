@@ -24,13 +24,15 @@ void set_error(const char* fmt, ...) {
   int inst_bwd_f32_m##m(const vh_problem*, const vh_bwd_io*, cudaStream_t); \
   int inst_bwd_f64_m##m(const vh_problem*, const vh_bwd_io*, cudaStream_t);
 VH_DECL_MODEL(0) VH_DECL_MODEL(1) VH_DECL_MODEL(2) VH_DECL_MODEL(3) VH_DECL_MODEL(4) VH_DECL_MODEL(5)
-VH_DECL_MODEL(7) VH_DECL_MODEL(8) VH_DECL_MODEL(9) VH_DECL_MODEL(10)
+VH_DECL_MODEL(7) VH_DECL_MODEL(8) VH_DECL_MODEL(9) VH_DECL_MODEL(10) VH_DECL_MODEL(11) VH_DECL_MODEL(12) VH_DECL_MODEL(13)
+VH_DECL_MODEL(14)
 #undef VH_DECL_MODEL
 typedef int (*fwd_fn)(const vh_problem*, const vh_fwd_io*, cudaStream_t);
 typedef int (*bwd_fn)(const vh_problem*, const vh_bwd_io*, cudaStream_t);
 #define VH_ROW(d, t) {inst_##d##_##t##_m0, inst_##d##_##t##_m1, inst_##d##_##t##_m2, inst_##d##_##t##_m3, inst_##d##_##t##_m4, \
                      inst_##d##_##t##_m5, nullptr /* dr_blackbox: vh_blackbox.cu */, inst_##d##_##t##_m7, inst_##d##_##t##_m8,  \
-                     inst_##d##_##t##_m9, inst_##d##_##t##_m10}
+                     inst_##d##_##t##_m9, inst_##d##_##t##_m10, inst_##d##_##t##_m11, inst_##d##_##t##_m12,                     \
+                     inst_##d##_##t##_m13, inst_##d##_##t##_m14}
 static const fwd_fn kFwd[2][VH_MODEL_COUNT] = {VH_ROW(fwd, f32), VH_ROW(fwd, f64)};
 static const bwd_fn kBwd[2][VH_MODEL_COUNT] = {VH_ROW(bwd, f32), VH_ROW(bwd, f64)};
 #undef VH_ROW
@@ -263,7 +265,9 @@ int vh_model_id(const char* key) {
   static const char* const names[VH_MODEL_COUNT] = {"dr_constant", "dr_constant_v2", "dr_constant_precisions",
                                                     "dr_constant_precisions_v2", "relay_constant",
                                                     "relay_constant_precisions", "dr_blackbox", "auto_constant",
-                                                    "auto_constant_precisions", "prpr_constant", "prpr_constant_precisions"};
+                                                    "auto_constant_precisions", "prpr_constant", "prpr_constant_precisions",
+                                                    "inducer_constant", "inducer_constant_precisions", "degrader_constant",
+                                                    "degrader_constant_precisions"};
   for (int i = 0; i < VH_MODEL_COUNT; ++i)
     if (key && !strcmp(key, names[i])) return i;
   set_error("no kernel for model '%s'", key ? key : "(null)");

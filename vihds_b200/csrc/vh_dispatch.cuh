@@ -10,12 +10,20 @@ namespace vh {
 // white-box families (hand-written RHS + VJP templates): double receiver / relay (DrModel) and growth-only (GrowthModel)
 inline bool model_is_dr_family(int model) {
   return (model >= VH_MODEL_DR_CONSTANT && model <= VH_MODEL_RELAY_CONSTANT_PRECISIONS) ||
-         (model >= VH_MODEL_AUTO_CONSTANT && model <= VH_MODEL_PRPR_CONSTANT_PRECISIONS);
+         (model >= VH_MODEL_AUTO_CONSTANT && model <= VH_MODEL_DEGRADER_CONSTANT_PRECISIONS);
 }
 inline bool model_is_dyn(int model) {
   return model == VH_MODEL_DR_CONSTANT_PRECISIONS || model == VH_MODEL_DR_CONSTANT_PRECISIONS_V2 ||
          model == VH_MODEL_RELAY_CONSTANT_PRECISIONS || model == VH_MODEL_DR_BLACKBOX ||
-         model == VH_MODEL_AUTO_CONSTANT_PRECISIONS || model == VH_MODEL_PRPR_CONSTANT_PRECISIONS;
+         model == VH_MODEL_AUTO_CONSTANT_PRECISIONS || model == VH_MODEL_PRPR_CONSTANT_PRECISIONS ||
+         model == VH_MODEL_INDUCER_CONSTANT_PRECISIONS || model == VH_MODEL_DEGRADER_CONSTANT_PRECISIONS;
+}
+// treatments the right-hand side reads (columns of the batch's `inputs`)
+inline int model_min_treatments(int model) {
+  if (model >= VH_MODEL_DR_CONSTANT && model <= VH_MODEL_RELAY_CONSTANT_PRECISIONS) return 2;
+  if (model == VH_MODEL_DEGRADER_CONSTANT || model == VH_MODEL_DEGRADER_CONSTANT_PRECISIONS) return 3;
+  if (model == VH_MODEL_INDUCER_CONSTANT || model == VH_MODEL_INDUCER_CONSTANT_PRECISIONS) return 1;
+  return 0;
 }
 inline int model_species(int model) {
   switch (model) {
@@ -29,6 +37,12 @@ inline int model_species(int model) {
     case VH_MODEL_PRPR_CONSTANT:
     case VH_MODEL_PRPR_CONSTANT_PRECISIONS:
       return 6;
+    case VH_MODEL_INDUCER_CONSTANT:
+    case VH_MODEL_INDUCER_CONSTANT_PRECISIONS:
+      return 5;
+    case VH_MODEL_DEGRADER_CONSTANT:
+    case VH_MODEL_DEGRADER_CONSTANT_PRECISIONS:
+      return 11;
     default:
       return 8;
   }
@@ -42,8 +56,8 @@ inline const char* build_call(const vh_problem* p, const vh_fwd_io* io, const vh
   if (p->P < 0 || p->P > VH_MAX_SLOTS) return "P out of range (0..VH_MAX_SLOTS)";
   if ((long long)p->B * p->IW > 0x7fffffffLL) return "B*IW exceeds int32";
   a.B = p->B; a.IW = p->IW; a.N = p->B * p->IW; a.T = p->T; a.P = p->P; a.C = p->C; a.D = p->D; a.E = p->E;
-  if (p->C < 2 && p->model >= VH_MODEL_DR_CONSTANT && p->model <= VH_MODEL_RELAY_CONSTANT_PRECISIONS)
-    return "C (treatments) must be >= 2 for the double-receiver / relay models (C6, C12)";
+  if (p->C < model_min_treatments(p->model))
+    return "C (treatments): the double-receiver / relay models read 2 (C6, C12), degrader 3 (+ Ara), inducer 1 (Ara)";
   a.bb_nlat = p->n_z + p->n_x + p->n_y;
   a.bb_ny = p->n_y;
   a.bb_noff = (p->model == VH_MODEL_DR_BLACKBOX && p->P > 0) ? p->E : 0;
@@ -119,12 +133,16 @@ inline int dispatch_solver(int solver, F& f) {
 template <typename R, class F>
 inline int dispatch_dr(int model, int solver, F& f) {
   switch (model) {
-    case VH_MODEL_DR_CONSTANT: return dispatch_solver<DrModel<R, 1, false, false> >(solver, f);
-    case VH_MODEL_DR_CONSTANT_V2: return dispatch_solver<DrModel<R, 2, false, false> >(solver, f);
-    case VH_MODEL_DR_CONSTANT_PRECISIONS: return dispatch_solver<DrModel<R, 1, false, true> >(solver, f);
-    case VH_MODEL_DR_CONSTANT_PRECISIONS_V2: return dispatch_solver<DrModel<R, 2, false, true> >(solver, f);
-    case VH_MODEL_RELAY_CONSTANT: return dispatch_solver<DrModel<R, 1, true, false> >(solver, f);
-    case VH_MODEL_RELAY_CONSTANT_PRECISIONS: return dispatch_solver<DrModel<R, 1, true, true> >(solver, f);
+    case VH_MODEL_DR_CONSTANT: return dispatch_solver<DrModel<R, 1, 0, false> >(solver, f);
+    case VH_MODEL_DR_CONSTANT_V2: return dispatch_solver<DrModel<R, 2, 0, false> >(solver, f);
+    case VH_MODEL_DR_CONSTANT_PRECISIONS: return dispatch_solver<DrModel<R, 1, 0, true> >(solver, f);
+    case VH_MODEL_DR_CONSTANT_PRECISIONS_V2: return dispatch_solver<DrModel<R, 2, 0, true> >(solver, f);
+    case VH_MODEL_RELAY_CONSTANT: return dispatch_solver<DrModel<R, 1, 1, false> >(solver, f);
+    case VH_MODEL_RELAY_CONSTANT_PRECISIONS: return dispatch_solver<DrModel<R, 1, 1, true> >(solver, f);
+    case VH_MODEL_DEGRADER_CONSTANT: return dispatch_solver<DrModel<R, 1, 2, false> >(solver, f);
+    case VH_MODEL_DEGRADER_CONSTANT_PRECISIONS: return dispatch_solver<DrModel<R, 1, 2, true> >(solver, f);
+    case VH_MODEL_INDUCER_CONSTANT: return dispatch_solver<GrowthModel<R, 5, false> >(solver, f);
+    case VH_MODEL_INDUCER_CONSTANT_PRECISIONS: return dispatch_solver<GrowthModel<R, 5, true> >(solver, f);
     case VH_MODEL_AUTO_CONSTANT: return dispatch_solver<GrowthModel<R, 4, false> >(solver, f);
     case VH_MODEL_AUTO_CONSTANT_PRECISIONS: return dispatch_solver<GrowthModel<R, 4, true> >(solver, f);
     case VH_MODEL_PRPR_CONSTANT: return dispatch_solver<GrowthModel<R, 6, false> >(solver, f);

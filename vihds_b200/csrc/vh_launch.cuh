@@ -327,11 +327,11 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
     R prec[4], iprec[4];
     {
       R th[M::NSLOT];
-      R c6, c12;
+      R tc[3];
 #pragma unroll
       for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? thv[s] : R(0);
-      M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
-      M::setup(th, c6, c12, f.c);
+      M::treatments(a.treatments + (size_t)b * a.C, tc);
+      M::setup(th, tc, f.c);
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
         prec[o] = M::DYN ? R(1) : th[S_prec_x + o];
@@ -468,12 +468,12 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
       for (int s = 0; s < M::NSLOT; ++s) gth[s] = R(0);
       {
         R th[M::NSLOT];
-        R c6, c12;
+        R tc[3];
 #pragma unroll
         for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? thv[s] : R(0);
-        M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
+        M::treatments(a.treatments + (size_t)b * a.C, tc);
         M::init_state_vjp(lam, gth);
-        M::setup_vjp(th, c6, c12, f.c, gc, gth);
+        M::setup_vjp(th, tc, f.c, gc, gth);
         if (!M::DYN) {
 #pragma unroll
           for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gprec[o];

@@ -1,7 +1,8 @@
 // Model right-hand sides and their hand-written reverse-mode (VJP) counterparts, one trajectory per call.
 //
-// White-box "double receiver" family (dr_constant v1/v2, relay_constant, +- NeuralPrecisions states):
-//   forward maths   <- models/dr_constant.py:14-112, models/relay_constant.py:13-134 (reference, read-only)
+// White-box "double receiver" family (dr_constant v1/v2, relay_constant, degrader_constant, +- NeuralPrecisions states):
+//   forward maths   <- models/dr_constant.py:14-112, models/relay_constant.py:13-134, models/degrader_constant.py:13-146
+//                      (reference, read-only); growth-only family: auto / prpr / inducer_constant (models/inducer_constant.py)
 //   initial state   <- models/dr_constant.py:133-150, :178-199; models/relay_constant.py:150-178, :220-250
 //   observe         <- vihds/ode.py:84-93
 //   NeuralPrecisions<- vihds/precisions.py:44-94
@@ -24,6 +25,9 @@ enum DrSlot : int {
   S_prec_x, S_prec_rfp, S_prec_yfp, S_prec_cfp,  // constant precisions: prec_*; dynamic: init_prec_*
   S_dlasI, S_dluxI, S_KC6, S_KC12, S_Klux, S_Klas, S_init_luxI, S_init_lasI,  // relay
   S_aYFP_PR, S_aCFP_PR,                                                           // prpr_constant
+  S_nA, S_eA, S_KAra,                                                             // arabinose promoter PBAD (inducer, degrader)
+  S_aYFP_Inducer,                                                                 // inducer_constant
+  S_aI, S_dA6, S_dA12, S_daiiA, S_init_aiiA,                                      // degrader_constant
   DR_NSLOT
 };
 
@@ -34,7 +38,8 @@ static const char* const kDrSlotNames[DR_NSLOT] = {
     "init_x", "init_rfp", "init_yfp", "init_cfp", "init_luxR", "init_lasR",
     "prec_x", "prec_rfp", "prec_yfp", "prec_cfp",
     "dlasI", "dluxI", "KC6", "KC12", "Klux", "Klas", "init_luxI", "init_lasI",
-    "aYFP_PR", "aCFP_PR"};
+    "aYFP_PR", "aCFP_PR",
+    "nA", "eA", "KAra", "aYFP_Inducer", "aI", "dA6", "dA12", "daiiA", "init_aiiA"};
 static const char* const kDrDynPrecNames[4] = {"init_prec_x", "init_prec_rfp", "init_prec_yfp", "init_prec_cfp"};
 
 // per-trajectory constants of the RHS (clamped parameters, Hill fractions, pre-multiplied production rates)
@@ -48,21 +53,52 @@ enum DrConst : int {
   C_p6,  // rc * aR
   C_p7,  // rc * aS
   C_dluxI, C_dlasI, C_k6, /* KC6*rc */ C_k12, /* KC12*rc */ C_Klux, C_Klas,
-  DR_NCONST
+  DR_NCONST,
+  // degrader_constant reuses the extension block: production of AiiA rc*aI*PBAD, its constant loss, dA6*c6, dA12*c12
+  C_cI = C_dluxI, C_daiiA, C_rC6, C_rC12, DG_NCONST
 };
 
-template <typename R, int VERSION_, bool RELAY_, bool DYN_>
+// treatments as the models read them: c = clamp(exp(x) - 1, 1e-12, 1e6) (models/dr_constant.py:26); tc[0..2] = C6, C12, Ara
+// for the receiver models, tc[0] = Ara for inducer_constant
+template <typename R>
+VH_HD R treat_conc(R x) {
+  return clampv(vexp(x) - R(1), R(1e-12), R(1e6));
+}
+
+// PBAD = (A^n + eA K^n) / (A^n + K^n), A = arabinose, n = clamp(nA, 0.5, 3) (models/inducer_constant.py:52-55,
+// models/degrader_constant.py:83-86); vjp w.r.t. (nA, eA, KAra) following torch's pow backward
+template <typename R>
+VH_HD R pbad(R A, R nA_raw, R eA, R K) {
+  const R n = clampv(nA_raw, R(0.5), R(3));
+  const R An = vpow(A, n), Kn = vpow(K, n);
+  return (An + eA * Kn) / (An + Kn);
+}
+template <typename R>
+VH_HD void pbad_vjp(R A, R nA_raw, R eA, R K, R gP, R& gn_raw, R& geA, R& gK) {
+  const R n = clampv(nA_raw, R(0.5), R(3));
+  const R An = vpow(A, n), Kn = vpow(K, n);
+  const R D = An + Kn, P = (An + eA * Kn) / D;
+  const R gN = gP / D, gD = -gN * P;
+  geA = gN * Kn;
+  const R gKn = gN * eA + gD, gAn = gN + gD;
+  gK = gKn * n * vpow(K, n - R(1));
+  gn_raw = (gAn * An * vlog(A) + gKn * Kn * vlog(K)) * clampmask(nA_raw, R(0.5), R(3));
+}
+
+// EXT: 0 = dr_constant, 1 = relay_constant (+ LuxI, LasI, C6, C12), 2 = degrader_constant (+ AiiA, C6, C12)
+template <typename R, int VERSION_, int EXT_, bool DYN_>
 struct DrModel {
   typedef R real;
   static constexpr int VERSION = VERSION_;
-  static constexpr bool RELAY = RELAY_;
+  static constexpr bool RELAY = EXT_ == 1;
+  static constexpr bool DEGR = EXT_ == 2;
   static constexpr bool DYN = DYN_;
   static constexpr bool BLACKBOX = false;
   static constexpr int NSLOT = DR_NSLOT;
-  static constexpr int NS = RELAY ? 12 : 8;      // species (OdeModel.n_species)
-  static constexpr int S = NS + (DYN ? 4 : 0);   // ODE state width
-  static constexpr int NC = RELAY ? DR_NCONST : C_dluxI;
-  static constexpr int NIN = NS + 1;             // NeuralPrecisions inputs: [t, species]
+  static constexpr int NS = RELAY ? 12 : (DEGR ? 11 : 8);  // species (OdeModel.n_species)
+  static constexpr int S = NS + (DYN ? 4 : 0);             // ODE state width
+  static constexpr int NC = RELAY ? DR_NCONST : (DEGR ? DG_NCONST : C_dluxI);
+  static constexpr int NIN = NS + 1;                       // NeuralPrecisions inputs: [t, species]
 
   struct Consts {
     R v[NC];
@@ -71,13 +107,16 @@ struct DrModel {
 
   VH_HD static constexpr bool uses(int s) {
     return (s <= S_nS) || (VERSION == 1 && s >= S_KR6 && s <= S_KS12) || (VERSION == 2 && (s == S_eS6 || s == S_eR12)) ||
-           (s >= S_init_x && s <= S_prec_cfp) || (RELAY && s >= S_dlasI && s <= S_init_lasI);
+           (s >= S_init_x && s <= S_prec_cfp) || (RELAY && s >= S_dlasI && s <= S_init_lasI) ||
+           (DEGR && (s == S_nA || s == S_eA || s == S_KAra || (s >= S_aI && s <= S_init_aiiA)));
   }
+  static constexpr int NTREAT = DEGR ? 3 : 2;
 
-  // treatments -> inducer concentrations, models/dr_constant.py:26
-  VH_HD static void treatments(const R* tr, R& c6, R& c12) {
-    c6 = clampv(vexp(tr[0]) - R(1), R(1e-12), R(1e6));
-    c12 = clampv(vexp(tr[1]) - R(1), R(1e-12), R(1e6));
+  // treatments -> inducer concentrations, models/dr_constant.py:26 (degrader: + arabinose, degrader_constant.py:28-32)
+  VH_HD static void treatments(const R* tr, R* tc) {
+    tc[0] = treat_conc(tr[0]);
+    tc[1] = treat_conc(tr[1]);
+    tc[2] = DEGR ? treat_conc(tr[2]) : R(0);
   }
 
   VH_HD static void hill(R Ka, R Kb, R n, R c6, R c12, R& f) {  // version 1 fraction
@@ -86,7 +125,8 @@ struct DrModel {
     f = (vpow(A, n) + vpow(Bq, n)) / vpow(D, n);
   }
 
-  VH_HD static void setup(const R* th, R c6, R c12, Consts& c) {
+  VH_HD static void setup(const R* th, const R* tc, Consts& c) {
+    const R c6 = tc[0], c12 = tc[1];
     R* v = c.v;
     v[C_r] = clampv(th[S_r], R(0), R(4));
     v[C_K] = clampv(th[S_K], R(0), R(4));
@@ -131,6 +171,12 @@ struct DrModel {
     } else {
       c.iKlux = c.iKlas = R(0);
     }
+    if (DEGR) {  // models/degrader_constant.py:76-88
+      v[C_cI] = th[S_rc] * th[S_aI] * pbad(tc[2], th[S_nA], th[S_eA], th[S_KAra]);
+      v[C_daiiA] = th[S_daiiA];
+      v[C_rC6] = th[S_dA6] * c6;
+      v[C_rC12] = th[S_dA12] * c12;
+    }
     c.iK = R(1) / v[C_K];
   }
 
@@ -150,7 +196,8 @@ struct DrModel {
   }
 
   // gc: cotangent of the constants  ->  gth: cotangent of the theta slots (accumulated)
-  VH_HD static void setup_vjp(const R* th, R c6, R c12, const Consts& c, const Consts& gc, R* gth) {
+  VH_HD static void setup_vjp(const R* th, const R* tc, const Consts& c, const Consts& gc, R* gth) {
+    const R c6 = tc[0], c12 = tc[1];
     const R* g = gc.v;
     gth[S_r] += g[C_r] * clampmask(th[S_r], R(0), R(4));
     gth[S_K] += g[C_K] * clampmask(th[S_K], R(0), R(4));
@@ -205,10 +252,24 @@ struct DrModel {
       gth[S_Klux] += g[C_Klux];
       gth[S_Klas] += g[C_Klas];
     }
+    if (DEGR) {
+      const R P = pbad(tc[2], th[S_nA], th[S_eA], th[S_KAra]);
+      grc += g[C_cI] * th[S_aI] * P;
+      gth[S_aI] += g[C_cI] * rc * P;
+      R gn, ge, gk;
+      pbad_vjp(tc[2], th[S_nA], th[S_eA], th[S_KAra], g[C_cI] * rc * th[S_aI], gn, ge, gk);
+      gth[S_nA] += gn;
+      gth[S_eA] += ge;
+      gth[S_KAra] += gk;
+      gth[S_daiiA] += g[C_daiiA];
+      gth[S_dA6] += g[C_rC6] * c6;
+      gth[S_dA12] += g[C_rC12] * c12;
+    }
     gth[S_rc] += grc;
   }
 
-  VH_HD static void init_state(const R* th, R c6, R c12, R* x) {
+  VH_HD static void init_state(const R* th, const R* tc, R* x) {
+    const R c6 = tc[0], c12 = tc[1];
     x[0] = th[S_init_x];
     x[1] = th[S_init_rfp];
     x[2] = th[S_init_yfp];
@@ -223,6 +284,11 @@ struct DrModel {
       x[10] = c6;
       x[11] = c12;
     }
+    if (DEGR) {  // models/degrader_constant.py:180-196
+      x[8] = th[S_init_aiiA];
+      x[9] = c6;
+      x[10] = c12;
+    }
     if (DYN) {
 #pragma unroll
       for (int o = 0; o < 4; ++o) x[NS + o] = th[S_prec_x + o];
@@ -230,6 +296,7 @@ struct DrModel {
   }
 
   VH_HD static void init_state_vjp(const R* gx, R* gth) {
+    if (DEGR) gth[S_init_aiiA] += gx[8];
     gth[S_init_x] += gx[0];
     gth[S_init_rfp] += gx[1];
     gth[S_init_yfp] += gx[2];
@@ -283,6 +350,11 @@ struct DrModel {
       dx[9] = v[C_rc] * m.P76 - (m.gam + v[C_dlasI]) * x[9];
       dx[10] = vdiv(v[C_k6] * x[0] * x[8], R(1) + x[8] * c.iKlux);
       dx[11] = vdiv(v[C_k12] * x[0] * x[9], R(1) + x[9] * c.iKlas);
+    }
+    if (DEGR) {  // models/degrader_constant.py:128-131 (as written there: the constant loss is not multiplied by AiiA)
+      dx[8] = v[C_cI] - (v[C_daiiA] + m.gam * x[8]);
+      dx[9] = x[0] * v[C_rC6] * x[8];
+      dx[10] = x[0] * v[C_rC12] * x[8];
     }
   }
 
@@ -349,6 +421,17 @@ struct DrModel {
         gc[C_Klas] -= gden * x[9] * (c.iKlas * c.iKlas);
       }
     }
+    if (DEGR) {
+      ggam -= g[8] * x[8];
+      gx[8] -= g[8] * m.gam;
+      gc[C_cI] += g[8];
+      gc[C_daiiA] -= g[8];
+      const R q = g[9] * v[C_rC6] + g[10] * v[C_rC12];
+      gx[0] += q * x[8];
+      gx[8] += q * x[0];
+      gc[C_rC6] += g[9] * x[0] * x[8];
+      gc[C_rC12] += g[10] * x[0] * x[8];
+    }
     // gamma = gr * g,  gr = r * sg,  g = 1 - x0 / K
     const R ggr = ggam * m.g, gg = ggam * m.gr;
     gc[C_r] += ggr * m.sg;
@@ -400,6 +483,8 @@ struct DrModel {
 // (NSP = 6: + YFP, CFP expressed constitutively; models/prpr_constant.py:11-58).  The double-receiver right-hand side
 // with the receiver / promoter terms removed; same slot names, same interface as DrModel.
 // ---------------------------------------------------------------------------------------------------------------
+// inducer_constant (NSP = 5: OD, RFP, YFP, F530, F480; models/inducer_constant.py:12-84): YFP expressed from PBAD, a
+// per-trajectory constant of the arabinose treatment: G_cY = rc * aYFP_Inducer * PBAD.
 enum GrConst : int { G_r = 0, G_K, G_tlag, G_rc, G_drfp, G_dyfp, G_dcfp, G_cY, G_cC, G_p530, G_p480, GR_NCONST };
 
 template <typename R, int NSP_, bool DYN_>
@@ -407,13 +492,16 @@ struct GrowthModel {
   typedef R real;
   static constexpr bool DYN = DYN_, RELAY = false, BLACKBOX = false;
   static constexpr bool PRPR = NSP_ == 6;
+  static constexpr bool IND = NSP_ == 5;
   static constexpr int NSLOT = DR_NSLOT;
   static constexpr int NS = NSP_;
   static constexpr int S = NS + (DYN ? 4 : 0);
   static constexpr int NC = GR_NCONST;
   static constexpr int NIN = NS + 1;
-  static constexpr int I530 = PRPR ? 4 : 2, I480 = PRPR ? 5 : 3;  // state index of the autofluorescence species
-  static_assert(NSP_ == 4 || NSP_ == 6, "auto_constant has 4 species, prpr_constant 6");
+  static constexpr int NTREAT = IND ? 1 : 0;
+  // state index of the autofluorescence species
+  static constexpr int I530 = PRPR ? 4 : (IND ? 3 : 2), I480 = PRPR ? 5 : (IND ? 4 : 3);
+  static_assert(NSP_ == 4 || NSP_ == 6 || NSP_ == 5, "auto_constant has 4 species, inducer_constant 5, prpr_constant 6");
 
   struct Consts {
     R v[NC];
@@ -426,26 +514,31 @@ struct GrowthModel {
   VH_HD static constexpr bool uses(int s) {
     return s == S_r || s == S_K || s == S_tlag || s == S_rc || s == S_a530 || s == S_a480 || s == S_drfp || s == S_init_x ||
            s == S_init_rfp || (s >= S_prec_x && s <= S_prec_cfp) ||
-           (PRPR && (s == S_dyfp || s == S_dcfp || s == S_aYFP_PR || s == S_aCFP_PR || s == S_init_yfp || s == S_init_cfp));
+           (PRPR && (s == S_dyfp || s == S_dcfp || s == S_aYFP_PR || s == S_aCFP_PR || s == S_init_yfp || s == S_init_cfp)) ||
+           (IND && (s == S_dyfp || s == S_aYFP_Inducer || s == S_nA || s == S_eA || s == S_KAra || s == S_init_yfp));
   }
-  VH_HD static void treatments(const R*, R& c6, R& c12) { c6 = c12 = R(0); }  // treatments do not enter these models
+  // treatments do not enter auto / prpr; inducer: arabinose (models/inducer_constant.py:28)
+  VH_HD static void treatments(const R* tr, R* tc) {
+    tc[0] = IND ? treat_conc(tr[0]) : R(0);
+    tc[1] = tc[2] = R(0);
+  }
 
-  VH_HD static void setup(const R* th, R, R, Consts& c) {
+  VH_HD static void setup(const R* th, const R* tc, Consts& c) {
     R* v = c.v;
     v[G_r] = clampv(th[S_r], R(0), R(4));
     v[G_K] = clampv(th[S_K], R(0), R(4));
     v[G_tlag] = th[S_tlag];
     v[G_rc] = th[S_rc];
     v[G_drfp] = clampv(th[S_drfp], R(1e-12), R(2));
-    v[G_dyfp] = PRPR ? clampv(th[S_dyfp], R(1e-12), R(2)) : R(0);
+    v[G_dyfp] = (PRPR || IND) ? clampv(th[S_dyfp], R(1e-12), R(2)) : R(0);
     v[G_dcfp] = PRPR ? clampv(th[S_dcfp], R(1e-12), R(2)) : R(0);
-    v[G_cY] = PRPR ? th[S_rc] * th[S_aYFP_PR] : R(0);
+    v[G_cY] = PRPR ? th[S_rc] * th[S_aYFP_PR] : (IND ? th[S_rc] * th[S_aYFP_Inducer] * pbad(tc[0], th[S_nA], th[S_eA], th[S_KAra]) : R(0));
     v[G_cC] = PRPR ? th[S_rc] * th[S_aCFP_PR] : R(0);
     v[G_p530] = th[S_rc] * th[S_a530];
     v[G_p480] = th[S_rc] * th[S_a480];
     c.iK = R(1) / v[G_K];
   }
-  VH_HD static void setup_vjp(const R* th, R, R, const Consts&, const Consts& gc, R* gth) {
+  VH_HD static void setup_vjp(const R* th, const R* tc, const Consts&, const Consts& gc, R* gth) {
     const R* g = gc.v;
     gth[S_r] += g[G_r] * clampmask(th[S_r], R(0), R(4));
     gth[S_K] += g[G_K] * clampmask(th[S_K], R(0), R(4));
@@ -461,16 +554,28 @@ struct GrowthModel {
       gth[S_aYFP_PR] += g[G_cY] * th[S_rc];
       gth[S_aCFP_PR] += g[G_cC] * th[S_rc];
     }
+    if (IND) {
+      gth[S_dyfp] += g[G_dyfp] * clampmask(th[S_dyfp], R(1e-12), R(2));
+      const R P = pbad(tc[0], th[S_nA], th[S_eA], th[S_KAra]);
+      grc += g[G_cY] * th[S_aYFP_Inducer] * P;
+      gth[S_aYFP_Inducer] += g[G_cY] * th[S_rc] * P;
+      R gn, ge, gk;
+      pbad_vjp(tc[0], th[S_nA], th[S_eA], th[S_KAra], g[G_cY] * th[S_rc] * th[S_aYFP_Inducer], gn, ge, gk);
+      gth[S_nA] += gn;
+      gth[S_eA] += ge;
+      gth[S_KAra] += gk;
+    }
     gth[S_rc] += grc;
   }
 
-  VH_HD static void init_state(const R* th, R, R, R* x) {
+  VH_HD static void init_state(const R* th, const R*, R* x) {
     x[0] = th[S_init_x];
     x[1] = th[S_init_rfp];
     if (PRPR) {
       x[2] = th[S_init_yfp];
       x[3] = th[S_init_cfp];
     }
+    if (IND) x[2] = th[S_init_yfp];
     x[I530] = R(0);
     x[I480] = R(0);
     if (DYN) {
@@ -485,6 +590,7 @@ struct GrowthModel {
       gth[S_init_yfp] += gx[2];
       gth[S_init_cfp] += gx[3];
     }
+    if (IND) gth[S_init_yfp] += gx[2];
     if (DYN) {
 #pragma unroll
       for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gx[NS + o];
@@ -505,6 +611,7 @@ struct GrowthModel {
       dx[2] = v[G_cY] - (m.gam + v[G_dyfp]) * x[2];
       dx[3] = v[G_cC] - (m.gam + v[G_dcfp]) * x[3];
     }
+    if (IND) dx[2] = v[G_cY] - (m.gam + v[G_dyfp]) * x[2];
     dx[I530] = v[G_p530] - m.gam * x[I530];
     dx[I480] = v[G_p480] - m.gam * x[I480];
   }
@@ -534,6 +641,12 @@ struct GrowthModel {
       gc[G_cY] += g[2];
       gc[G_cC] += g[3];
     }
+    if (IND) {
+      ggam -= g[2] * x[2];
+      gx[2] -= g[2] * (m.gam + v[G_dyfp]);
+      gc[G_dyfp] -= g[2] * x[2];
+      gc[G_cY] += g[2];
+    }
     const R ggr = ggam * m.g, gg = ggam * m.gr;
     gc[G_r] += ggr * m.sg;
     gc[G_tlag] -= R(4) * ggr * v[G_r] * m.sg * (R(1) - m.sg);
@@ -546,13 +659,16 @@ struct GrowthModel {
     rhs_vjp_from(x, c, m, g, gx, gcs);
   }
 
-  // prpr: vihds/ode.py:84-93 (default observe); auto: models/auto_constant.py:81-89
+  // prpr: vihds/ode.py:84-93 (default observe); auto: models/auto_constant.py:81-89; inducer: inducer_constant.py:102-110
   VH_HD static void observe(const R* x, R* xp) {
     xp[0] = x[0];
     xp[1] = x[0] * x[1];
     if (PRPR) {
       xp[2] = x[0] * (x[2] + x[4]);
       xp[3] = x[0] * (x[3] + x[5]);
+    } else if (IND) {
+      xp[2] = x[0] * (x[2] + x[3]);
+      xp[3] = x[0] * x[4];
     } else {
       xp[2] = x[0] * x[2];
       xp[3] = x[0] * x[3];
@@ -566,6 +682,12 @@ struct GrowthModel {
       gx[4] += gxp[2] * x[0];
       gx[3] += gxp[3] * x[0];
       gx[5] += gxp[3] * x[0];
+    } else if (IND) {
+      gx[0] += gxp[0] + gxp[1] * x[1] + gxp[2] * (x[2] + x[3]) + gxp[3] * x[4];
+      gx[1] += gxp[1] * x[0];
+      gx[2] += gxp[2] * x[0];
+      gx[3] += gxp[2] * x[0];
+      gx[4] += gxp[3] * x[0];
     } else {
       gx[0] += gxp[0] + gxp[1] * x[1] + gxp[2] * x[2] + gxp[3] * x[3];
       gx[1] += gxp[1] * x[0];

@@ -471,10 +471,10 @@ VH_HD void traj_forward_from(const Call<typename M::real>& a, int n, const typen
   R x[S];
   R prec[4], lprec[4], ll[4];
   {
-    R c6, c12;
-    M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
-    M::setup(th, c6, c12, f.c);
-    M::init_state(th, c6, c12, x);
+    R tc[3];
+    M::treatments(a.treatments + (size_t)b * a.C, tc);
+    M::setup(th, tc, f.c);
+    M::init_state(th, tc, x);
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       prec[o] = M::DYN ? R(1) : th[S_prec_x + o];
@@ -608,10 +608,10 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
     R prec[4], iprec[4];
     {
       R th[M::NSLOT];
-      R lq = R(0), lp = R(0), c6, c12;
+      R lq = R(0), lp = R(0), tc[3];
       load_theta<M, true>(a, n, b, th, lq, lp, sc, false);  // never rewrite theta in the reverse pass
-      M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
-      M::setup(th, c6, c12, f.c);
+      M::treatments(a.treatments + (size_t)b * a.C, tc);
+      M::setup(th, tc, f.c);
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
         prec[o] = M::DYN ? R(1) : th[S_prec_x + o];
@@ -686,11 +686,11 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
     }
     // chain rule back to theta: re-derive theta (cheap) rather than keep it live across the loop
     R th[M::NSLOT];
-    R lq = R(0), lp = R(0), c6, c12;
+    R lq = R(0), lp = R(0), tc[3];
     load_theta<M, true>(a, n, b, th, lq, lp, sc, false);
-    M::treatments(a.treatments + (size_t)b * a.C, c6, c12);
+    M::treatments(a.treatments + (size_t)b * a.C, tc);
     M::init_state_vjp(lam, gth);
-    M::setup_vjp(th, c6, c12, f.c, gc, gth);
+    M::setup_vjp(th, tc, f.c, gc, gth);
     if (!M::DYN) {
 #pragma unroll
       for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gprec[o];

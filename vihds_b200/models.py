@@ -335,6 +335,73 @@ class PRPR_Constant_Precisions(PRPR_Constant):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# inducer (models/inducer_constant.py:82-151) and degrader (models/degrader_constant.py:146-269).  Like relay, the
+# reference classes do not construct as shipped (init_with_params / OdeFunc.__init__ arity); the
+# behaviour reproduced is that of the monkeypatch in oracle/ref_harness.py, pinned by golden cases minted under it.
+# ---------------------------------------------------------------------------------------------------------------
+class Inducer_Constant(OdeModel):
+    kernel_model = "inducer_constant"
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.precisions = ConstantPrecisions(["prec_x", "prec_rfp", "prec_yfp", "prec_cfp"])
+        self.species = ["OD", "RFP", "YFP", "F530", "F480"]
+        self.n_species = 5
+
+    def initialize_state(self, theta, _treatments):
+        zero = torch.zeros_like(theta.init_x)
+        rows = [theta.init_x, theta.init_rfp, theta.init_yfp, zero, zero]
+        if self.precisions.dynamic:
+            rows += [theta.init_prec_x, theta.init_prec_rfp, theta.init_prec_yfp, theta.init_prec_cfp]
+        return torch.stack(rows, dim=2)
+
+    @classmethod
+    def observe(cls, x_sample, _theta):
+        od = x_sample[:, :, 0, :]
+        return torch.stack([od, od * x_sample[:, :, 1, :], od * (x_sample[:, :, 2, :] + x_sample[:, :, 3, :]),
+                            od * x_sample[:, :, 4, :]], dim=2)
+
+
+class Inducer_Constant_Precisions(Inducer_Constant):
+    kernel_model = "inducer_constant_precisions"
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.precisions = NeuralPrecisions(self.n_species, config.params.n_hidden_decoder_precisions, 4)
+
+
+class Degrader_Constant(OdeModel):
+    """Double receiver + AiiA degrader; aR / aS are sampled parameters here (no device conditioning: the reference has
+    it commented out, degrader_constant.py:56-69)."""
+
+    kernel_model = "degrader_constant"
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.precisions = ConstantPrecisions(["prec_x", "prec_rfp", "prec_yfp", "prec_cfp"])
+        self.species = ["OD", "RFP", "YFP", "CFP", "F530", "F480", "LuxR", "LasR", "AiiA", "C6", "C12"]
+        self.n_species = 11
+
+    def initialize_state(self, theta, treatments):
+        zero = torch.zeros_like(theta.init_x)
+        c = torch.clamp(torch.exp(treatments) - 1.0, 1e-12, 1e6)
+        c6, c12 = c[:, 0:1].expand_as(zero), c[:, 1:2].expand_as(zero)
+        rows = [theta.init_x, theta.init_rfp, theta.init_yfp, theta.init_cfp, zero, zero, theta.init_luxR, theta.init_lasR,
+                theta.init_aiiA, c6, c12]
+        if self.precisions.dynamic:
+            rows += [theta.init_prec_x, theta.init_prec_rfp, theta.init_prec_yfp, theta.init_prec_cfp]
+        return torch.stack(rows, dim=2)
+
+
+class Degrader_Constant_Precisions(Degrader_Constant):
+    kernel_model = "degrader_constant_precisions"
+
+    def __init__(self, config):
+        super().__init__(config)
+        self.precisions = NeuralPrecisions(self.n_species, config.params.n_hidden_decoder_precisions, 4)
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # black box (models/dr_blackbox.py:61-125, vihds/ode.py:119-138)
 # ---------------------------------------------------------------------------------------------------------------
 class NeuralStates(nn.Module):
@@ -432,6 +499,10 @@ LOOKUP = {
     "dr_constant_precisions_v2": DR_Constant_Precisions_V2,
     "relay_constant": Relay_Constant,
     "relay_constant_precisions": Relay_Constant_Precisions,
+    "inducer_constant": Inducer_Constant,
+    "inducer_constant_precisions": Inducer_Constant_Precisions,
+    "degrader_constant": Degrader_Constant,
+    "degrader_constant_precisions": Degrader_Constant_Precisions,
 }
 
 
