@@ -37,8 +37,9 @@ def _slice_batch(batch, n):
     })
 
 
-def run_case(spec, solver, dtype, iw, n_batch=None, traces=True, tag=None):
-    args, settings, data, parameters, model, training = H.build_reference(spec, samples=iw, dtype=dtype, solver=solver)
+def run_case(spec, solver, dtype, iw, n_batch=None, traces=True, tag=None, extra_args=()):
+    args, settings, data, parameters, model, training = H.build_reference(spec, samples=iw, dtype=dtype, solver=solver,
+                                                                          extra_args=extra_args)
     from vihds.distributions import TfConstant, TfLogNormal, TfNormal
 
     batch = next(iter(training.train_loader))
@@ -175,10 +176,12 @@ def dump_dataset(spec, tag):
     print("==> %s: %d individuals, T=%d" % (tag, len(ds), ds.n_times))
 
 
-def run_training_steps(spec="dr_constant_icml", iw=20, k=5, tag=None):
+def run_training_steps(spec="dr_constant_icml", iw=20, k=5, tag=None, epochs=None):
     """k consecutive training steps of the reference's own ``Training._run_batch`` (vihds/training.py:324-340) on ONE
     mini-batch: records what is random per step (u from numpy's RNG, the device-conditioner output) and what the
-    reference made of it (the cost of every step, every trainable parameter before the first and after the last step)."""
+    reference made of it (the cost of every step, every trainable parameter before the first and after the last step).
+    ``epochs``: instead of k steps on one batch, run that many passes over the reference's own shuffling train_loader
+    (vihds/training.py:360-366) and record the mini-batch of every step."""
     import time
 
     args, settings, data, parameters, model, training = H.build_reference(spec, samples=iw)
@@ -215,15 +218,28 @@ def run_training_steps(spec="dr_constant_icml", iw=20, k=5, tag=None):
 
     model.train()
     init = {n: _np(w).copy() for n, w in model.named_parameters()}
-    for _ in range(k):
-        assert training._run_batch(time.time(), batch, Log())
+    batches = []
+    if epochs:
+        for _ in range(epochs):
+            for b in training.train_loader:
+                batches.append(b)
+                assert training._run_batch(time.time(), b, Log())
+        k = len(batches)
+        assert len({len(b.inputs) for b in batches}) == 1, "ragged batches are not recorded by this fixture"
+    else:
+        for _ in range(k):
+            assert training._run_batch(time.time(), batch, Log())
     final = {n: _np(w).copy() for n, w in model.named_parameters()}
     names = sorted({n for n, _ in conds}, key=[n for n, _ in conds].index)
     out = {
         "spec": spec, "solver": settings.params.solver, "dtype": "float32", "model": settings.model, "steps": np.array(k),
         "learning_rate": np.array(float(settings.params.learning_rate)),
-        "times": _np(batch.times).astype(np.float32), "inputs": _np(batch.inputs).astype(np.float32),
-        "dev_1hot": _np(batch.dev_1hot).astype(np.float32), "observations": _np(batch.observations).astype(np.float32),
+        "times": _np(batch.times).astype(np.float32),
+        # one batch for all steps, or [K, ...] stacks when the loader was iterated
+        "inputs": (np.stack([_np(b.inputs) for b in batches]) if batches else _np(batch.inputs)).astype(np.float32),
+        "dev_1hot": (np.stack([_np(b.dev_1hot) for b in batches]) if batches else _np(batch.dev_1hot)).astype(np.float32),
+        "observations": (np.stack([_np(b.observations) for b in batches]) if batches else _np(batch.observations)).astype(np.float32),
+        "per_step_batches": np.array(bool(batches)),
         "u": np.stack(us).astype(np.float32), "cond_names": np.array(names),
         "cond": np.stack([np.stack([c for n, c in conds[i * len(names):(i + 1) * len(names)]]) for i in range(k)]).astype(np.float32)
         if names else np.zeros((k, 0), np.float32),
@@ -258,6 +274,11 @@ def extra_models():
     run_case("degrader_constant_precisions", "midpoint", "float32", 8, n_batch=12)
     run_case("degrader_constant_precisions", "midpoint", "float64", 8, n_batch=6)
     run_case("degrader_constant_precisions", "modeuler", "float32", 8, n_batch=12)
+    # NeuralPrecisions WITH a hidden layer on white-box models (--precision_hidden_layers, run_xval.py:38)
+    hid = ("--precision_hidden_layers=5",)
+    run_case("dr_constant_precisions", "midpoint", "float32", 8, n_batch=12, extra_args=hid, tag="dr_constant_precisions_hidden5_midpoint_f32_iw8")
+    run_case("dr_constant_precisions", "midpoint", "float64", 8, n_batch=6, extra_args=hid, tag="dr_constant_precisions_hidden5_midpoint_f64_iw8")
+    run_case("relay_constant_precisions", "modeuler", "float32", 8, n_batch=12, extra_args=hid, tag="relay_constant_precisions_hidden5_modeuler_f32_iw8")
 
 
 def main(group="all"):
@@ -272,7 +293,9 @@ def main(group="all"):
         run_case("relay_constant_precisions", "midpoint", "float32", 200, traces=False)
         return
     if group == "train":
-        return run_training_steps("dr_constant_icml", 20, 5)
+        run_training_steps("dr_constant_icml", 20, 5)
+        # BASELINE config 1: dr_constant_one, IW = 5, whole epochs through the reference's shuffling loader
+        return run_training_steps("dr_constant_one", 5, None, tag="dr_constant_one_epochs4_iw5_train", epochs=4)
     # config 1: every fixed-step solver, fp32; fp64 for the default and the in-repo solver
     for solver in ("midpoint", "rk4", "euler", "modeuler", "modeulerwhile"):
         run_case("dr_constant_one", solver, "float32", 5, n_batch=8)
@@ -296,6 +319,7 @@ def main(group="all"):
     run_case("dr_blackbox_icml", "midpoint", "float32", 200, traces=False)
     run_case("relay_constant_precisions", "midpoint", "float32", 200, traces=False)
     run_training_steps("dr_constant_icml", 20, 5)
+    run_training_steps("dr_constant_one", 5, None, tag="dr_constant_one_epochs4_iw5_train", epochs=4)
     dump_dataset("dr_constant_icml", "dataset_dr_icml")
     dump_dataset("relay_constant_precisions", "dataset_relay")
 

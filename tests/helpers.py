@@ -73,9 +73,11 @@ def flat_weights(case):
         gw = np.concatenate([case["gw:ode_model." + k].reshape(-1) for k in keys])
         return w, gw
     pre = "w:ode_model.precisions."
-    if (pre + "prec_production.weight") not in case or (pre + "prec_hidden.weight") in case:
+    if (pre + "prec_production.weight") not in case:
         return None, None
     order = ["prec_production.weight", "prec_production.bias", "prec_degradation.weight", "prec_degradation.bias"]
+    if (pre + "prec_hidden.weight") in case:  # NeuralPrecisions with a hidden layer (HidPrecNet layout)
+        order = ["prec_hidden.weight", "prec_hidden.bias"] + order
     w = np.concatenate([case[pre + k].reshape(-1) for k in order])
     gw = np.concatenate([case["gw:ode_model.precisions." + k].reshape(-1) for k in order])
     return w, gw
@@ -118,6 +120,8 @@ def make_problem(case, src, E, n_weights_hidden=0):
     p.C, p.D, p.E = case["inputs"].shape[1], case["dev_1hot"].shape[1], E
     for s in range(L.VH_MAX_SLOTS):
         p.slot_src[s] = src[s]
+    if "w:ode_model.precisions.prec_hidden.weight" in case and str(case["model"]) != "dr_blackbox":
+        p.n_hidden = case["w:ode_model.precisions.prec_hidden.weight"].shape[0]  # --precision_hidden_layers of the run
     if str(case["model"]) == "dr_blackbox":
         par = case["params"]
         p.n_hidden, p.n_hidden_states, p.n_latent = par["n_hidden_decoder_precisions"], par["n_hidden_decoder"], par["n_latent_species"]

@@ -102,6 +102,7 @@ int fwd_t(const vh_problem* p, const vh_fwd_io* io) {
     BbFwdRunner<R> f{&a};
     return bb_solver<BbRhs<R, 2, 25, 20, 21> >(p->solver, f);
   }
+  a.n_hidden = (model_is_dyn(p->model) && p->model != VH_MODEL_DR_BLACKBOX) ? p->n_hidden : 0;
   FwdRunner<R> f{&a};
   return dispatch_dr<R>(p->model, p->solver, f);
 }
@@ -113,7 +114,11 @@ int bwd_t(const vh_problem* p, const vh_bwd_io* io) {
     BbBwdRunner<R> f{&a};
     return bb_solver<BbRhs<R, 2, 25, 20, 21> >(p->solver, f);
   }
-  size_t nw = model_is_dyn(p->model) ? (size_t)2 * (4 * (model_species(p->model) + 1) + 4) : 0;  // LinPrecNet::NW
+  const int nin = model_species(p->model) + 1, H = model_is_dyn(p->model) ? p->n_hidden : 0;
+  a.n_hidden = H;
+  // LinPrecNet::NW, or HidPrecNet::num_weights(H) with a hidden layer
+  size_t nw = !model_is_dyn(p->model) ? 0 : (H == 0 ? (size_t)2 * (4 * nin + 4) : (size_t)H * (nin + 1) + 2 * (4 * H + 4));
+  a.nw = (int)nw;
   BwdRunner<R> f{&a, nw};
   return dispatch_dr<R>(p->model, p->solver, f);
 }

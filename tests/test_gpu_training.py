@@ -26,24 +26,40 @@ def _load_reference_parameters(model, z, prefix):
     return sd
 
 
+FIXTURES = {
+    # 5 steps on one icml mini-batch (device conditioner recorded per step)
+    "dr_constant_icml_train5_iw20": ("dr_constant_icml", None),
+    # BASELINE config 1: dr_constant_one, IW = 5, four epochs through the reference's shuffling loader (one 36-individual
+    # mini-batch per epoch; no device conditioner: aR / aS are sampled global-conditioned parameters)
+    "dr_constant_one_epochs4_iw5_train": ("dr_constant_one", (4, 100, 2, 1)),
+}
+
+
 @pytest.mark.parametrize("use_graphs", [True, False])
-def test_five_training_steps_match_the_reference(use_graphs):
-    z = np.load(os.path.join(GOLDEN, "dr_constant_icml_train5_iw20.npz"))
-    settings, par, model, training = build("dr_constant_icml")
+@pytest.mark.parametrize("fixture", sorted(FIXTURES))
+def test_training_steps_match_the_reference(fixture, use_graphs):
+    z = np.load(os.path.join(GOLDEN, fixture + ".npz"))
+    spec, dims = FIXTURES[fixture]
+    settings, par, model, training = build(spec, dims)
     _load_reference_parameters(model, z, "init:")
     assert abs(float(z["learning_rate"]) - training.optimizer.lr) < 1e-12
     K, B, IW, P = z["u"].shape
     T = len(z["times"])
+    per_step = bool(z["per_step_batches"]) if "per_step_batches" in z.files else False
     model.want_predict = False
     gs = GraphedStep(training, B, IW, T, use_graphs=use_graphs)
     assert list(z["cond_names"]) == list(gs.extras)
-    batch = {k: torch.as_tensor(z[k]).cuda() for k in ("times", "inputs", "dev_1hot", "observations")}
-    gs.load_batch(batch)
-    planes = torch.zeros(len(gs.extras), B * IW, device="cuda")
-    gs.extras_override = planes  # the conditioner output the reference drew at each step (fresh random weights per call)
+    dev = lambda a: torch.as_tensor(a).cuda()  # noqa: E731
+    planes = torch.zeros(max(1, len(gs.extras)), B * IW, device="cuda")
+    if gs.extras:
+        gs.extras_override = planes  # the conditioner output the reference drew at each step (fresh random weights per call)
     costs = []
     for i in range(K):
-        planes.copy_(torch.as_tensor(z["cond"][i]).reshape(len(gs.extras), B * IW))
+        pick = (lambda a: a[i]) if per_step else (lambda a: a)
+        gs.load_batch({"times": dev(z["times"]), "inputs": dev(pick(z["inputs"])), "dev_1hot": dev(pick(z["dev_1hot"])),
+                       "observations": dev(pick(z["observations"]))})
+        if gs.extras:
+            planes.copy_(torch.as_tensor(z["cond"][i]).reshape(len(gs.extras), B * IW))
         gs.load_u(torch.as_tensor(z["u"][i]).cuda())
         costs.append(float(gs.step().item()))
     ref = z["losses"]

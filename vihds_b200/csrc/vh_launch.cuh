@@ -64,11 +64,11 @@ __global__ void __launch_bounds__(128) elbo_fwd_kernel(const Call<typename M::re
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* w = reinterpret_cast<R*>(smem_raw);
   if (M::DYN) {
-    for (int i = threadIdx.x; i < NetInfo<M>::NW; i += blockDim.x) w[i] = a.weights[i];
+    for (int i = threadIdx.x; i < a.nw; i += blockDim.x) w[i] = a.weights[i];
     __syncthreads();
   }
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  const SlotScratch<R> sc{w + ((NetInfo<M>::NW + 3) & ~3) + threadIdx.x, (int)blockDim.x};
+  const SlotScratch<R> sc{w + ((a.nw + 3) & ~3) + threadIdx.x, (int)blockDim.x};
   if (n < a.N) traj_forward<M, TB>(a, n, w, sc);
 }
 
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(FWD_TEAM * 32) elbo_fwd_team_kernel(const Call
   R* part = sm + M::NSLOT * 32;       // [2][FWD_TEAM][32]
   R* wsm = part + 2 * FWD_TEAM * 32;  // NeuralPrecisions weights (dynamic-precision models)
   if (M::DYN) {
-    for (int i = threadIdx.x; i < NetInfo<M>::NW; i += blockDim.x) wsm[i] = a.weights[i];
+    for (int i = threadIdx.x; i < a.nw; i += blockDim.x) wsm[i] = a.weights[i];
   }
   for (int s = role; s < M::NSLOT; s += FWD_TEAM) {
     const int src = a.slot_src[s];
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(FWD_TEAM * 32) elbo_fwd_team_kernel(const Call
 template <class M, class TB>
 __global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel(const Call<typename M::real> a) {
   typedef typename M::real R;
-  constexpr int NW = NetInfo<M>::NW;
+  const int NW = a.nw;  // run-time: the NeuralPrecisions net may have a hidden layer of any width <= HidPrecNet::MAXH
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* w = reinterpret_cast<R*>(smem_raw);
   R* gw = w + NW;  // [NW][blockDim.x] per-thread accumulators, conflict-free (consecutive threads, consecutive banks)
@@ -324,6 +324,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
     // both roles need the RHS constants
     Rhs<M> f;
     f.w = M::DYN ? wsm : nullptr;
+    f.nh = 0;  // the warp-specialised form keeps the no-hidden-layer net only (its weight-gradient warp is sized for it)
     R prec[4], iprec[4];
     {
       R th[M::NSLOT];
@@ -564,10 +565,12 @@ struct FwdLauncher {
   int run() {
     const int block = pick_block(a.N);
     const int grid = (a.N + block - 1) / block;
-    const size_t smem = sizeof(R) * (((NetInfo<M>::NW + 3) & ~3) + (size_t)M::NSLOT * block);  // weights | slot scratch
+    const size_t smem = sizeof(R) * (((a.nw + 3) & ~3) + (size_t)M::NSLOT * block);  // weights | slot scratch
     if (use_team<M>(block)) {
       // slot values | partial log-probs | NeuralPrecisions weights
-      const size_t tsm = sizeof(R) * ((size_t)M::NSLOT * 32 + 2 * FWD_TEAM * 32 + NetInfo<M>::NW);
+      const size_t tsm = sizeof(R) * ((size_t)M::NSLOT * 32 + 2 * FWD_TEAM * 32 + a.nw);
+      if (tsm > 48 * 1024)
+        cudaFuncSetAttribute(elbo_fwd_team_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
       elbo_fwd_team_kernel<M, TB><<<(a.N + 31) / 32, FWD_TEAM * 32, tsm, stream>>>(a);
     } else {
       if (smem > 48 * 1024)
@@ -611,13 +614,13 @@ struct BwdLauncher {
   }
   template <class M, class TB>
   int run() {
-    constexpr int NW = NetInfo<M>::NW;
+    const int NW = a.nw;
     int block = pick_block(a.N);
     if (NW > 0 && sizeof(R) * (NW * (block + 1) + M::NSLOT * block) > 200 * 1024) block = 64;
     const int grid = (a.N + block - 1) / block;
     const size_t smem = sizeof(R) * (((NW * (block + 1) + 3) & ~3) + (size_t)M::NSLOT * block);  // w | gw | slot scratch
     cudaError_t e;
-    const bool ws = use_ws<M>(block);
+    const bool ws = use_ws<M>(block) && !(M::DYN && a.n_hidden > 0);  // hidden-layer precision nets: throughput form only
     if (!ws && smem > 48 * 1024) {
       e = cudaFuncSetAttribute(elbo_bwd_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) {
@@ -645,6 +648,17 @@ struct BwdLauncher {
   }
 };
 
+// NeuralPrecisions net of a dynamic-precision white-box model: hidden width and flat weight count of this call
+template <class M>
+const char* set_precision_net(const vh_problem* p, Call<typename M::real>& a) {
+  typedef typename M::real R;
+  a.n_hidden = M::DYN ? p->n_hidden : 0;
+  if (a.n_hidden < 0 || a.n_hidden > HidPrecNet<R, M::NIN>::MAXH)
+    return "NeuralPrecisions hidden width (n_hidden_decoder_precisions) must be in 0..32 for the white-box models";
+  a.nw = !M::DYN ? 0 : (a.n_hidden == 0 ? NetInfo<M>::NW : HidPrecNet<R, M::NIN>::num_weights(a.n_hidden));
+  return nullptr;
+}
+
 template <class M>
 int launch_fwd_model(const vh_problem* p, const vh_fwd_io* io, cudaStream_t stream) {
   typedef typename M::real R;
@@ -654,8 +668,8 @@ int launch_fwd_model(const vh_problem* p, const vh_fwd_io* io, cudaStream_t stre
     return VH_ERR_INVALID;
   }
   f.stream = stream;
-  if (M::DYN && p->n_hidden != 0) {
-    set_error("NeuralPrecisions with a hidden layer (n_hidden=%d) is not implemented for the white-box models yet", p->n_hidden);
+  if (const char* err = set_precision_net<M>(p, f.a)) {
+    set_error("%s", err);
     return VH_ERR_UNSUPPORTED;
   }
   return dispatch_solver<M>(p->solver, f);
@@ -670,8 +684,8 @@ int launch_bwd_model(const vh_problem* p, const vh_bwd_io* io, cudaStream_t stre
     return VH_ERR_INVALID;
   }
   f.stream = stream;
-  if (M::DYN && p->n_hidden != 0) {
-    set_error("NeuralPrecisions with a hidden layer (n_hidden=%d) is not implemented for the white-box models yet", p->n_hidden);
+  if (const char* err = set_precision_net<M>(p, f.a)) {
+    set_error("%s", err);
     return VH_ERR_UNSUPPORTED;
   }
   return dispatch_solver<M>(p->solver, f);

@@ -753,4 +753,80 @@ struct LinPrecNet {
   }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// NeuralPrecisions WITH a hidden layer (n_hidden_decoder_precisions = H >= 1; vihds/precisions.py:63-74, :76-87;
+// reachable through --precision_hidden_layers, run_xval.py:38, config.py:157-158):
+//   h = tanh(W1 [t, species] + b1);  prod = sigmoid(Wp h + bp);  degr = sigmoid(Wd h + bd);  dv = prod - degr * v
+// (no activation on the inputs in this branch: nn.Sequential(prec_hidden, act, prec_production, Sigmoid)).
+// flat weight layout: W1[H][NIN], b1[H], Wp[4][H], bp[4], Wd[4][H], bd[4].  H is a run-time value (<= MAXH).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R, int NIN>
+struct HidPrecNet {
+  static constexpr int MAXH = 32;
+  VH_HD static int num_weights(int H) { return H * (NIN + 1) + 2 * (4 * H + 4); }
+  VH_HD static void hidden(R t, const R* species, const R* w, int H, R* h) {
+    for (int k = 0; k < H; ++k) {
+      const R* w1 = w + k * NIN;
+      R a = w[H * NIN + k] + w1[0] * t;
+#pragma unroll
+      for (int j = 1; j < NIN; ++j) a += w1[j] * species[j - 1];
+      h[k] = vtanh(a);
+    }
+  }
+  VH_HD static void rhs(R t, const R* species, const R* v, const R* w, int H, R* dv) {
+    R h[MAXH];
+    hidden(t, species, w, H, h);
+    const R* wp = w + H * (NIN + 1);
+    const R* wd = wp + 4 * H + 4;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      R zp = wp[4 * H + o], zd = wd[4 * H + o];
+      for (int k = 0; k < H; ++k) {
+        zp += wp[o * H + k] * h[k];
+        zd += wd[o * H + k] * h[k];
+      }
+      dv[o] = sigmoid(zp) - sigmoid(zd) * v[o];
+    }
+  }
+  // gw.add(k, value): element k of the flat weight gradient
+  template <typename GW>
+  VH_HD static void rhs_vjp(R t, const R* species, const R* v, const R* w, int H, const R* g, R* gspecies, R* gv, GW& gw) {
+    R h[MAXH], gh[MAXH];
+    hidden(t, species, w, H, h);
+    for (int k = 0; k < H; ++k) gh[k] = R(0);
+    const int oP = H * (NIN + 1), oD = oP + 4 * H + 4;
+    const R* wp = w + oP;
+    const R* wd = w + oD;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      R zp = wp[4 * H + o], zd = wd[4 * H + o];
+      for (int k = 0; k < H; ++k) {
+        zp += wp[o * H + k] * h[k];
+        zd += wd[o * H + k] * h[k];
+      }
+      const R sp = sigmoid(zp), sd = sigmoid(zd);
+      gv[o] -= g[o] * sd;
+      const R gzp = g[o] * sp * (R(1) - sp), gzd = -g[o] * v[o] * sd * (R(1) - sd);
+      gw.add(oP + 4 * H + o, gzp);
+      gw.add(oD + 4 * H + o, gzd);
+      for (int k = 0; k < H; ++k) {
+        gw.add(oP + o * H + k, gzp * h[k]);
+        gw.add(oD + o * H + k, gzd * h[k]);
+        gh[k] += gzp * wp[o * H + k] + gzd * wd[o * H + k];
+      }
+    }
+    for (int k = 0; k < H; ++k) {
+      const R gpre = gh[k] * (R(1) - h[k] * h[k]);
+      const R* w1 = w + k * NIN;
+      gw.add(H * NIN + k, gpre);
+      gw.add(k * NIN, gpre * t);
+#pragma unroll
+      for (int j = 1; j < NIN; ++j) {
+        gw.add(k * NIN + j, gpre * species[j - 1]);
+        gspecies[j - 1] += gpre * w1[j];
+      }
+    }
+  }
+};
+
 }  // namespace vh

@@ -65,6 +65,7 @@ struct Call {
   int slot_src[VH_MAX_SLOTS];
   int bb_nlat, bb_ny, bb_noff;   // dr_blackbox: latent-parameter count (n_z + n_x + n_y), its conditioned tail n_y, offset rows
   R bb_init_latent, bb_init_prec;
+  int n_hidden, nw;              // NeuralPrecisions of the white-box models: hidden width (0 = none), flat weight count
   int n_free;                    // theta columns no model slot reads (they still carry log-prob terms)
   int free_cols[VH_MAX_SLOTS];
   int col_slot[VH_MAX_SLOTS];    // inverse of slot_src: the model slot column k feeds, or -1
@@ -121,6 +122,7 @@ struct Rhs {
   static constexpr int S = M::S;
   typename M::Consts c;
   const R* w;  // NeuralPrecisions weights (shared memory on the device), unused for constant precisions
+  int nh;      // hidden width of the NeuralPrecisions net (0: no hidden layer)
 
   VH_HD void eval(R t, const R* x, R* dx) const {
     Mid m;
@@ -130,14 +132,24 @@ struct Rhs {
   VH_HD void eval_keep(R t, const R* x, R* dx, Mid& m) const {
     M::mid(t, x, c, m);
     M::rhs_from(x, c, m, dx);
-    if (M::DYN) LinPrecNet<R, M::NIN>::rhs(t, x, x + M::NS, w, dx + M::NS);
+    if (M::DYN) {
+      if (nh == 0)
+        LinPrecNet<R, M::NIN>::rhs(t, x, x + M::NS, w, dx + M::NS);
+      else
+        HidPrecNet<R, M::NIN>::rhs(t, x, x + M::NS, w, nh, dx + M::NS);
+    }
   }
   // intermediates only (last stage of a step: its derivative is not needed to rebuild any stage state)
   VH_HD void keep_only(R t, const R* x, Mid& m) const { M::mid(t, x, c, m); }
   template <typename GW>
   VH_HD void vjp_kept(R t, const R* x, const Mid& m, const R* g, R* gx, typename M::Consts& gc, GW& gw) const {
     M::rhs_vjp_from(x, c, m, g, gx, gc);
-    if (M::DYN) LinPrecNet<R, M::NIN>::rhs_vjp(t, x, x + M::NS, w, g + M::NS, gx, gx + M::NS, gw);
+    if (M::DYN) {
+      if (nh == 0)
+        LinPrecNet<R, M::NIN>::rhs_vjp(t, x, x + M::NS, w, g + M::NS, gx, gx + M::NS, gw);
+      else
+        HidPrecNet<R, M::NIN>::rhs_vjp(t, x, x + M::NS, w, nh, g + M::NS, gx, gx + M::NS, gw);
+    }
   }
   template <typename GW>
   VH_HD void vjp(R t, const R* x, const R* g, R* gx, typename M::Consts& gc, GW& gw) const {
@@ -468,6 +480,7 @@ VH_HD void traj_forward_from(const Call<typename M::real>& a, int n, const typen
   const int T = a.T;
   Rhs<M> f;
   f.w = w;
+  f.nh = a.n_hidden;
   R x[S];
   R prec[4], lprec[4], ll[4];
   {
@@ -605,6 +618,7 @@ VH_HD void traj_backward(const Call<typename M::real>& a, int n, bool active, co
   if (active) {
     Rhs<M> f;
     f.w = w;
+    f.nh = a.n_hidden;
     R prec[4], iprec[4];
     {
       R th[M::NSLOT];
