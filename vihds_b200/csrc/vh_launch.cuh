@@ -9,6 +9,7 @@
 #include <stdlib.h>
 
 #include "vh_dispatch.cuh"
+#include "vh_lane.cuh"
 
 namespace vh {
 
@@ -103,6 +104,9 @@ struct BwdBounds {
 // NeuralPrecisions weights in shared memory next to it.
 #ifndef VH_FWD_TEAM
 #define VH_FWD_TEAM 4
+#endif
+#ifndef VH_FWD_LANE_DEFAULT
+#define VH_FWD_LANE_DEFAULT 0
 #endif
 constexpr int FWD_TEAM = VH_FWD_TEAM;
 template <class M, class TB>
@@ -561,11 +565,31 @@ struct FwdLauncher {
     const int mode = (!m || !*m) ? -1 : atoi(m);
     return mode >= 0 ? mode != 0 : block == 32;
   }
+  // VIHDS_FWD_LANE=0|1: the lane-split forward kernel (vh_lane.cuh: 8 lanes per trajectory) for dr_constant v1 / v2 in
+  // fp32; default: on for latency-bound launches (see DESIGN.md section 4 for the measurement)
+  template <class M>
+  static bool use_lane(int block) {
+    const char* m = getenv("VIHDS_FWD_LANE");
+    const int mode = (!m || !*m) ? -1 : atoi(m);
+    return mode >= 0 ? mode != 0 : VH_FWD_LANE_DEFAULT && block == 32;
+  }
   template <class M, class TB>
   int run() {
     const int block = pick_block(a.N);
     const int grid = (a.N + block - 1) / block;
     const size_t smem = sizeof(R) * (((a.nw + 3) & ~3) + (size_t)M::NSLOT * block);  // weights | slot scratch
+    if constexpr (LaneOk<M>::value) {
+      if (use_lane<M>(block)) {
+        constexpr int TPC = LANE_WARPS * LANE_TRAJ_PER_WARP;
+        elbo_fwd_lane_kernel<M, TB><<<(a.N + TPC - 1) / TPC, LANE_WARPS * 32, sizeof(float) * M::NSLOT * TPC, stream>>>(a);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+          set_error("elbo_fwd_lane_kernel launch failed: %s", cudaGetErrorString(e));
+          return VH_ERR_CUDA;
+        }
+        return VH_OK;
+      }
+    }
     if (use_team<M>(block)) {
       // slot values | partial log-probs | NeuralPrecisions weights
       const size_t tsm = sizeof(R) * ((size_t)M::NSLOT * 32 + 2 * FWD_TEAM * 32 + a.nw);
