@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define VH_ABI_VERSION 2
+#define VH_ABI_VERSION 3
 
 enum vh_status {
   VH_OK = 0,
@@ -146,6 +146,14 @@ typedef struct vh_bwd_io {
   void* d_q_prec;                /* out [B][P] */
   void* d_extra;                 /* out [E][N] or NULL */
   void* d_weights;               /* out flat, same layout as weights (zeroed by the call) or NULL */
+  /* IWAE reduction fused into the reverse launch (the training step's vh_iwae_fwd_bwd + vh_elbo_terms_bwd as ONE launch;
+   * vihds/training.py:134-148 and the unit upstream gradient of elbo.backward(), :334).  iwae_b_total > 0: the upstream
+   * gradients are derived inside the kernel from the forward call's outputs fwd.logp_by_species / logp_theta / logq_theta
+   * (all three required; g_logp_* must be NULL) and iwae_cost[0] receives -mean_b(logsumexp_i log_w - log IW) with the
+   * mean's denominator iwae_b_total (zeroed by the call).  Available where the latency-form reverse kernel runs
+   * (B*IW <= 18,944, white-box models without a hidden-layer precision net); VH_ERR_UNSUPPORTED otherwise. */
+  void* iwae_cost;               /* out [1] or NULL */
+  int iwae_b_total;              /* 0: not fused */
 } vh_bwd_io;
 
 int vh_abi_version(void);
@@ -274,6 +282,13 @@ typedef struct vh_encoder_grads {
 
 int vh_encoder_fwd(const vh_encoder_desc* e, const vh_encoder_io* io, void* stream);
 int vh_encoder_bwd(const vh_encoder_desc* e, const vh_encoder_io* io, const vh_encoder_grads* g, void* stream);
+/* vh_encoder_bwd followed by vh_adam_step_dev(zero_grad = 1) over the flat parameter vector the g_* buffers are views of,
+ * with the hidden-layer weight gradient formed inside the optimiser launch (two launches instead of three: the end of
+ * Training._run_batch, vihds/training.py:334-337, on one GPU).  param / grad / exp_avg / exp_avg_sq / hyper / step /
+ * guard as for vh_adam_step_dev.  Small batches only (B <= 128); VH_ERR_UNSUPPORTED otherwise. */
+int vh_encoder_bwd_adam(const vh_encoder_desc* e, const vh_encoder_io* io, const vh_encoder_grads* g, size_t n, void* param,
+                        void* grad, void* exp_avg, void* exp_avg_sq, const void* hyper, void* step, const void* guard,
+                        void* stream);
 
 /* Device conditioner (vihds/ode.py:43-58 OdeModel.device_conditioner with param = ones, :99-116 DeviceConditioner):
  * out[k][n] = (plus_one[k] ? 1 : 0) + relu(dot(w[k], dev_1hot[m % B_global] * rel[k])),  m = (b_offset + b)*IW + i,

@@ -38,7 +38,7 @@ class vh_fwd_io(C.Structure):
 
 
 class vh_bwd_io(C.Structure):
-    _fields_ = [("fwd", vh_fwd_io)] + [(n, C.c_void_p) for n in _BWD_FIELDS]
+    _fields_ = [("fwd", vh_fwd_io)] + [(n, C.c_void_p) for n in _BWD_FIELDS] + [("iwae_cost", C.c_void_p), ("iwae_b_total", C.c_int)]
 
 
 class vh_encoder_desc(C.Structure):
@@ -107,7 +107,9 @@ def load():
     lib.vh_device_conditioner.argtypes = [C.c_int] * 7 + [C.c_void_p] * 6
     lib.vh_encoder_fwd.argtypes = [C.POINTER(vh_encoder_desc), C.POINTER(vh_encoder_io), C.c_void_p]
     lib.vh_encoder_bwd.argtypes = [C.POINTER(vh_encoder_desc), C.POINTER(vh_encoder_io), C.POINTER(vh_encoder_grads), C.c_void_p]
-    if lib.vh_abi_version() != 2:
+    lib.vh_encoder_bwd_adam.argtypes = ([C.POINTER(vh_encoder_desc), C.POINTER(vh_encoder_io), C.POINTER(vh_encoder_grads), C.c_size_t] +
+                                        [C.c_void_p] * 8)
+    if lib.vh_abi_version() != 3:
         raise RuntimeError("vihds_b200: ABI version mismatch")
     _lib = lib
     return lib

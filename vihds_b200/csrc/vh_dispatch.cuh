@@ -106,6 +106,14 @@ inline const char* build_call(const vh_problem* p, const vh_fwd_io* io, const vh
     a.theta = nullptr;     // never written by the reverse sweep
     if (p->P > 0 && (!a.d_q_mu || !a.d_q_prec)) return "backward with P > 0 needs d_q_mu and d_q_prec";
     if (model_is_dyn(p->model) && !a.d_weights) return "backward of a dynamic-precision model needs d_weights";
+    if (bio->iwae_b_total > 0) {
+      if (!bio->iwae_cost || !a.logp_species || !a.logp_theta || !a.logq_theta)
+        return "fused IWAE: iwae_cost and the forward call's logp_by_species / logp_theta / logq_theta are required";
+      if (a.g_logp_species || a.g_logp_theta || a.g_logq_theta) return "fused IWAE: g_logp_* must be NULL";
+      if (p->model == VH_MODEL_DR_BLACKBOX) return "fused IWAE: not available for dr_blackbox";
+      a.iw_b_total = bio->iwae_b_total;
+      a.iw_cost = (R*)bio->iwae_cost;
+    }
   }
   if (p->model == VH_MODEL_DR_BLACKBOX) {
     if (a.bb_nlat + p->C + p->D > 48) return "black-box: n_z + n_x + n_y + C + D exceeds 48";

@@ -442,6 +442,65 @@ __global__ void __launch_bounds__(256) enc_lin_wgrad_small_kernel(const EncDims 
   p.g_lin_w[e] += a0 + a1;
 }
 
+// Small batches, single GPU: the hidden-layer weight gradient AND the Adam update of the whole flat parameter vector in one
+// launch (vh_encoder_bwd_adam).  One thread per parameter of the flat vector; threads inside the view of lin_w first form
+// their gradient entry (the B-deep sum above) -- it never travels through memory -- everybody then applies Adam exactly
+// as adam_dev_kernel does (vh_api.cu: device-side step counter and hyper-parameters, NaN guard, gradient cleared).
+template <typename R>
+__global__ void __launch_bounds__(256) enc_lin_wgrad_adam_kernel(const EncDims d, const EncPtrs<R> p, size_t n, long long lin_off,
+                                                                 R* __restrict__ prm, R* __restrict__ g, R* __restrict__ m,
+                                                                 R* __restrict__ v, const double* __restrict__ hyper,
+                                                                 long long* step, const R* __restrict__ guard) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ R s_bc[2];
+  __shared__ int s_skip;
+  if (threadIdx.x == 0) {
+    const double t = (double)(*(volatile long long*)step + 1);
+    s_bc[0] = (R)(1.0 - pow(hyper[1], t));
+    s_bc[1] = (R)sqrt(1.0 - pow(hyper[2], t));
+    const R c = guard ? *guard : R(0);
+    s_skip = (c != c) || (guard && *(volatile long long*)(step + 2) != 0);
+  }
+  __syncthreads();
+  const bool skip = s_skip != 0;
+  if (i < n) {
+    R gi = g[i];
+    const long long e = (long long)i - lin_off;
+    if (!skip && e >= 0 && e < (long long)d.H * d.NLIN) {
+      const int o = (int)(e / d.NLIN), c = (int)(e % d.NLIN);
+      R a0 = R(0), a1 = R(0);
+      int b = 0;
+#pragma unroll 6
+      for (; b + 1 < d.B; b += 2) {
+        a0 += p.d_pre[(size_t)b * d.H + o] * p.pooled[(size_t)b * d.NLIN + c];
+        a1 += p.d_pre[(size_t)(b + 1) * d.H + o] * p.pooled[(size_t)(b + 1) * d.NLIN + c];
+      }
+      if (b < d.B) a0 += p.d_pre[(size_t)b * d.H + o] * p.pooled[(size_t)b * d.NLIN + c];
+      gi += a0 + a1;
+    }
+    if (!skip) {
+      const double lr = hyper[0], b1d = hyper[1], b2d = hyper[2];
+      const R b1 = (R)b1d, b2 = (R)b2d, eps = (R)hyper[3];
+      const R mi = m[i] + (gi - m[i]) * (R(1) - b1);
+      const R vi = b2 * v[i] + (R(1) - b2) * gi * gi;
+      m[i] = mi;
+      v[i] = vi;
+      const R denom = vsqrt(vi) / s_bc[1] + eps;
+      prm[i] -= ((R)lr / s_bc[0]) * (mi / denom);
+    }
+    g[i] = R(0);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd((unsigned long long*)(step + 1), 1ULL);
+    if (ticket == (unsigned long long)gridDim.x - 1) {
+      step[1] = 0;
+      step[skip ? 2 : 0] += 1;
+    }
+  }
+}
+
 // device conditioner (vihds/ode.py:43-58, :99-116) including the reference's repeat/reshape quirk: sample n = b*IW + i
 // of the GLOBAL batch receives the conditioner output of individual n % B_global.  A rank that holds the slab of
 // individuals [b_offset, b_offset + B) passes the global one-hot table, so the result does not depend on the rank count.
@@ -547,14 +606,28 @@ static int enc_fwd_t(const EncDims& d, const vh_encoder_io* io, cudaStream_t s) 
   return 0;
 }
 
+struct AdamArgs {
+  size_t n;
+  void *param, *grad, *exp_avg, *exp_avg_sq;
+  const void *hyper, *guard;
+  void* step;
+};
+
 template <typename R>
-static int enc_bwd_t(const EncDims& d, const vh_encoder_io* io, const vh_encoder_grads* g, cudaStream_t s) {
+static int enc_bwd_t(const EncDims& d, const vh_encoder_io* io, const vh_encoder_grads* g, cudaStream_t s, const AdamArgs* ad = nullptr) {
   EncPtrs<R> p = {};
   fill_ptrs<R>(io, g, p);
   if (enc_group<R>(d) == 4)
     enc_bwd_g<R, 4>(d, p, s);
   else
     enc_bwd_g<R, 1>(d, p, s);
+  if (ad) {  // B <= 128 (checked by the caller): weight gradient of the hidden layer + Adam over the flat vector, one launch
+    const long long lin_off = (long long)(p.g_lin_w - (R*)ad->grad);
+    enc_lin_wgrad_adam_kernel<R><<<(unsigned)((ad->n + 255) / 256), 256, 0, s>>>(
+        d, p, ad->n, lin_off, (R*)ad->param, (R*)ad->grad, (R*)ad->exp_avg, (R*)ad->exp_avg_sq, (const double*)ad->hyper,
+        (long long*)ad->step, (const R*)ad->guard);
+    return 0;
+  }
   if (d.B <= 128) {
     const int n = d.H * d.NLIN;
     enc_lin_wgrad_small_kernel<R><<<(n + 255) / 256, 256, 0, s>>>(d, p);
@@ -625,6 +698,41 @@ int vh_device_conditioner(int dtype, int B, int IW, int D, int n_cond, int B_glo
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) {
     set_error("conditioner_kernel launch failed: %s", cudaGetErrorString(ce));
+    return VH_ERR_CUDA;
+  }
+  return VH_OK;
+}
+
+int vh_encoder_bwd_adam(const vh_encoder_desc* e, const vh_encoder_io* io, const vh_encoder_grads* g, size_t n, void* param,
+                        void* grad, void* exp_avg, void* exp_avg_sq, const void* hyper, void* step, const void* guard,
+                        void* stream) {
+  EncDims d;
+  if (const char* err = fill_dims(e, d)) {
+    set_error("vh_encoder_bwd_adam: %s", err);
+    return VH_ERR_INVALID;
+  }
+  if (!io || !g || !g->d_q_mu || !g->d_q_prec || !g->g_conv_w || !g->g_conv_b || !g->g_lin_w || !g->g_lin_b || !g->d_pre ||
+      !io->q_prec || !io->pooled || !io->enc || (d.nl > 0 && (!g->g_local_w || !g->g_local_b)) || (d.ng > 0 && !g->g_gcond_w) ||
+      (d.nglob > 0 && !g->g_global_free) || !param || !grad || !exp_avg || !exp_avg_sq || !hyper || !step || n == 0) {
+    set_error("vh_encoder_bwd_adam: missing buffer");
+    return VH_ERR_INVALID;
+  }
+  const size_t es = e->dtype == VH_F64 ? 8 : 4;
+  const char *gl = (const char*)g->g_lin_w, *g0 = (const char*)grad;
+  if (d.B > 128 || gl < g0 || gl + es * (size_t)d.H * d.NLIN > g0 + es * n) {
+    set_error("vh_encoder_bwd_adam: needs B <= 128 and g_lin_w inside the flat gradient vector (use vh_encoder_bwd + vh_adam_step_dev)");
+    return VH_ERR_UNSUPPORTED;
+  }
+  AdamArgs ad = {n, param, grad, exp_avg, exp_avg_sq, hyper, guard, step};
+  if (e->dtype == VH_F32) enc_bwd_t<float>(d, io, g, (cudaStream_t)stream, &ad);
+  else if (e->dtype == VH_F64) enc_bwd_t<double>(d, io, g, (cudaStream_t)stream, &ad);
+  else {
+    set_error("unknown dtype %d", e->dtype);
+    return VH_ERR_INVALID;
+  }
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) {
+    set_error("enc_bwd / enc_lin_wgrad_adam launch failed: %s", cudaGetErrorString(ce));
     return VH_ERR_CUDA;
   }
   return VH_OK;

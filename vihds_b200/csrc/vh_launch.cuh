@@ -283,6 +283,70 @@ struct WgradRing {
   }
 };
 
+// IWAE reduction in the prologue of the reverse launch (vihds/training.py:134-148 and the unit upstream gradient of
+// elbo.backward(), :334): every CTA reduces the IW log-weights of the (one or two) individuals its 32 trajectories belong
+// to -- 1,200 floats from L2, all warps of the team -- instead of a separate one-block-per-individual launch.  Returns
+// d cost / d log_w of this lane's trajectory; the CTA that holds an individual's first sample adds its term to the cost.
+// Same arithmetic as iwae_fwd_kernel (vh_api.cu): max-shifted logsumexp, NaN log-weights surface in the cost.
+template <typename R>
+__device__ R iwae_upstream_in_kernel(const Call<R>& a, int n, bool active, R* red /* >= 2 * nwarps + 2 elements */) {
+  const unsigned full = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const int n_first = blockIdx.x * 32, n_last = min(a.N - 1, n_first + 31);
+  const int b_first = n_first / a.IW, b_last = n_last / a.IW, b_mine = n / a.IW;
+  const R inv_b = R(1) / R(a.iw_b_total);
+  auto logw = [&](size_t m) {
+    const R* l = a.logp_species + m * 4;
+    return ((l[0] + l[1]) + (l[2] + l[3])) + a.logp_theta[m] - a.logq_theta[m];
+  };
+  R lse_mine = R(0);
+  for (int bb = b_first; bb <= b_last; ++bb) {
+    const size_t base = (size_t)bb * a.IW;
+    R mx = -INFINITY;
+    bool has_nan = false;
+    for (int i = tid; i < a.IW; i += blockDim.x) {
+      const R v = logw(base + i);
+      has_nan |= (v != v);
+      mx = v > mx ? v : mx;
+    }
+    R nanf = has_nan ? R(1) : R(0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const R other = __shfl_xor_sync(full, mx, o);
+      mx = other > mx ? other : mx;
+      nanf += __shfl_xor_sync(full, nanf, o);
+    }
+    __syncthreads();
+    if (lane == 0) {
+      red[warp] = mx;
+      red[nwarp + warp] = nanf;
+    }
+    __syncthreads();
+    mx = red[0];
+    nanf = red[nwarp];
+    for (int w = 1; w < nwarp; ++w) {
+      mx = red[w] > mx ? red[w] : mx;
+      nanf += red[nwarp + w];
+    }
+    const R shift = (mx == -INFINITY || mx == INFINITY) ? R(0) : mx;
+    R se = R(0);
+    for (int i = tid; i < a.IW; i += blockDim.x) se += vexp(logw(base + i) - shift);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(full, se, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = se;
+    __syncthreads();
+    se = red[0];
+    for (int w = 1; w < nwarp; ++w) se += red[w];
+    R lse = vlog(se) + shift;
+    if (nanf > R(0)) lse = NAN;
+    if (bb == b_mine) lse_mine = lse;
+    if (tid == 0 && base >= (size_t)n_first) atomicAdd(a.iw_cost, -(lse - vlog(R(a.IW))) * inv_b);
+  }
+  __syncthreads();
+  return active ? -vexp(logw((size_t)n) - lse_mine) * inv_b : R(0);
+}
+
 template <class M, class TB>
 __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<typename M::real> a) {
   typedef typename M::real R;
@@ -308,8 +372,11 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
   if (M::DYN) {
     for (int i = threadIdx.x; i < NW; i += blockDim.x) wsm[i] = a.weights[i];
   }
-  const R glq = (a.g_logq_theta && active) ? a.g_logq_theta[n] : R(0);
-  const R glp = (a.g_logp_theta && active) ? a.g_logp_theta[n] : R(0);
+  // upstream gradients: handed in, or (fused IWAE) derived here from the forward call's per-sample terms
+  const bool iwae = a.iw_b_total > 0;
+  const R gup = iwae ? iwae_upstream_in_kernel(a, n, active, ring) : R(0);
+  const R glq = iwae ? -gup : ((a.g_logq_theta && active) ? a.g_logq_theta[n] : R(0));
+  const R glp = iwae ? gup : ((a.g_logp_theta && active) ? a.g_logp_theta[n] : R(0));
   // theta of this trajectory: warp r fetches columns r, r + WS_WARPS, ... (read back from the forward's theta planes,
   // or re-sampled) and the slots without a column that it owns; the values stay in shared memory for the epilogue
   for (int s = role; s < M::NSLOT; s += WS_WARPS) {
@@ -392,7 +459,7 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
 #pragma unroll
       for (int o = 0; o < 4; ++o) {
         gprec[o] = R(0);
-        gl[o] = (a.g_logp_species && active) ? a.g_logp_species[(size_t)n * 4 + o] : R(0);
+        gl[o] = iwae ? gup : ((a.g_logp_species && active) ? a.g_logp_species[(size_t)n * 4 + o] : R(0));
       }
       const R* obs = a.obs ? a.obs + (size_t)b * 4 * T : nullptr;
       const R* gxs = a.g_x_states ? a.g_x_states + (size_t)(T - 1) * slab + n : nullptr;
@@ -645,6 +712,11 @@ struct BwdLauncher {
     const size_t smem = sizeof(R) * (((NW * (block + 1) + 3) & ~3) + (size_t)M::NSLOT * block);  // w | gw | slot scratch
     cudaError_t e;
     const bool ws = use_ws<M>(block) && !(M::DYN && a.n_hidden > 0);  // hidden-layer precision nets: throughput form only
+    if (a.iw_b_total > 0 && !ws) {
+      set_error("vh_elbo_terms_bwd_iwae: the fused IWAE reduction exists in the latency-form reverse kernel only "
+                "(N <= %d, no hidden-layer precision net); use vh_iwae_fwd_bwd + vh_elbo_terms_bwd", 148 * 4 * 32);
+      return VH_ERR_UNSUPPORTED;
+    }
     if (!ws && smem > 48 * 1024) {
       e = cudaFuncSetAttribute(elbo_bwd_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) {
@@ -652,15 +724,19 @@ struct BwdLauncher {
         return VH_ERR_CUDA;
       }
     }
+    bool cost_cleared = a.iw_b_total == 0;
     if (a.d_q_mu && a.P > 0) {
       const size_t nq = (size_t)a.B * a.P;
-      if (a.d_q_prec == a.d_q_mu + nq) {  // adjacent tables: one memset node
-        cudaMemsetAsync(a.d_q_mu, 0, sizeof(R) * 2 * nq, stream);
+      if (a.d_q_prec == a.d_q_mu + nq) {  // adjacent tables (and the cost right behind them): one memset node
+        const bool with_cost = !cost_cleared && a.iw_cost == a.d_q_mu + 2 * nq;
+        cudaMemsetAsync(a.d_q_mu, 0, sizeof(R) * (2 * nq + (with_cost ? 1 : 0)), stream);
+        cost_cleared |= with_cost;
       } else {
         cudaMemsetAsync(a.d_q_mu, 0, sizeof(R) * nq, stream);
         cudaMemsetAsync(a.d_q_prec, 0, sizeof(R) * nq, stream);
       }
     }
+    if (!cost_cleared) cudaMemsetAsync(a.iw_cost, 0, sizeof(R), stream);
     if (NW > 0) cudaMemsetAsync(a.d_weights, 0, sizeof(R) * NW, stream);
     launch_bwd_variant<M, TB>(ws, grid, block, smem);
     e = cudaGetLastError();

@@ -76,6 +76,10 @@ struct Call {
   // reverse only
   const R *g_logp_species, *g_logp_theta, *g_logq_theta, *g_theta, *g_x_states, *g_x_predict;
   R *d_q_mu, *d_q_prec, *d_extra, *d_weights;
+  // reverse with the IWAE reduction fused in (vh_elbo_terms_bwd_iwae): the upstream gradients are derived in the kernel
+  // from the forward call's per-sample terms (logp_species / logp_theta / logq_theta above, read as inputs)
+  int iw_b_total;  // denominator of the batch mean; 0: upstream gradients come from g_logp_* as usual
+  R* iw_cost;      // [1], accumulated: -(logsumexp_i log_w - log IW) / b_total per individual
 };
 
 // weight-gradient accumulator handles -------------------------------------------------------------------------

@@ -239,9 +239,15 @@ class GraphedStep(object):
         self.prob = ode.problem(enc.names, enc.kinds, prior, self.extras, dev, dt)
         S = self.prob.S
         N = self.N
-        self.buf = Settings(theta=z(P, N), x_states=z(T, S, N), lpx=z(N, 4), lp=z(N), lq=z(N), cost=z(1), log_w=z(N), w=z(N),
-                            g_lpx=z(N, 4), g_lp=z(N), g_lq=z(N), d_q=z(2, B, P))
-        self.buf.d_q_mu, self.buf.d_q_prec = self.buf.d_q[0], self.buf.d_q[1]  # adjacent: cleared by one memset
+        self.buf = Settings(theta=z(P, N), x_states=z(T, S, N), lpx=z(N, 4), lp=z(N), lq=z(N), log_w=z(N), w=z(N),
+                            g_lpx=z(N, 4), g_lp=z(N), g_lq=z(N), d_q_cost=z(2 * B * P + 1))
+        # d_q_mu | d_q_prec | cost adjacent: the reverse launch clears all three with one memset node
+        self.buf.d_q = self.buf.d_q_cost[:2 * B * P].view(2, B, P)
+        self.buf.cost = self.buf.d_q_cost[2 * B * P:]
+        self.buf.d_q_mu, self.buf.d_q_prec = self.buf.d_q[0], self.buf.d_q[1]
+        # IWAE reduction inside the reverse launch where the latency-form kernel runs (one launch less per step)
+        self.fuse_iwae = (os.environ.get("VIHDS_FUSE_IWAE", "1") != "0" and N <= 148 * 4 * 32 and ode.kernel_model != "dr_blackbox"
+                          and not (self.prob.dynamic_precisions and self.prob.net.get("n_hidden", 0) > 0))
         self.buf.cost_sum = z(1)  # NCCL path: sum of the ranks' costs (guard of the Adam update)
         self.d_weights = z(self.prob.n_weights) if self.prob.n_weights else None
         self.d_extra = z(len(self.extras), N) if (self.extras and hasattr(ode, "offset_layer")) else None
@@ -317,9 +323,13 @@ class GraphedStep(object):
             observations=_ptr(bt.observations), weights=_ptr(self.weights), theta=_ptr(b.theta),
             x_states=_ptr(b.x_states), x_predict=None, logp_by_species=_ptr(b.lpx), logp_theta=_ptr(b.lp),
             logq_theta=_ptr(b.lq))
-        self._bio = L.vh_bwd_io(fwd=self._fio, g_logp_by_species=_ptr(b.g_lpx), g_logp_theta=_ptr(b.g_lp),
-                                g_logq_theta=_ptr(b.g_lq), d_q_mu=_ptr(b.d_q_mu), d_q_prec=_ptr(b.d_q_prec),
-                                d_extra=_ptr(self.d_extra), d_weights=_ptr(self.d_weights))
+        if self.fuse_iwae:
+            self._bio = L.vh_bwd_io(fwd=self._fio, d_q_mu=_ptr(b.d_q_mu), d_q_prec=_ptr(b.d_q_prec), d_extra=_ptr(self.d_extra),
+                                    d_weights=_ptr(self.d_weights), iwae_cost=_ptr(b.cost), iwae_b_total=self.b_total)
+        else:
+            self._bio = L.vh_bwd_io(fwd=self._fio, g_logp_by_species=_ptr(b.g_lpx), g_logp_theta=_ptr(b.g_lp),
+                                    g_logq_theta=_ptr(b.g_lq), d_q_mu=_ptr(b.d_q_mu), d_q_prec=_ptr(b.d_q_prec),
+                                    d_extra=_ptr(self.d_extra), d_weights=_ptr(self.d_weights))
         vdt = self.prob.vh_dtype
         self._iwae_args = (vdt, self.B, self.IW, self.b_total, _ptr(b.lpx), _ptr(b.lp), _ptr(b.lq), _ptr(b.cost),
                            _ptr(b.log_w), _ptr(b.w), _ptr(b.g_lpx), _ptr(b.g_lp), _ptr(b.g_lq))
@@ -329,7 +339,8 @@ class GraphedStep(object):
         """The hot path: three launches of libvihds_b200.so on the current stream (arguments pre-built)."""
         lib, s = self.prob.lib, _stream()
         L.check(lib.vh_elbo_terms_fwd(self._p_ref, self._fio_ref, s))
-        L.check(lib.vh_iwae_fwd_bwd(*self._iwae_args, s))
+        if not self.fuse_iwae:
+            L.check(lib.vh_iwae_fwd_bwd(*self._iwae_args, s))
         if self.ev_hot is not None:
             self.ev_hot[0].record()
         L.check(lib.vh_elbo_terms_bwd(self._p_ref, self._bio_ref, s))
@@ -340,13 +351,7 @@ class GraphedStep(object):
         """encoder backward, ONE gradient all-reduce, fused Adam (captured)."""
         opt = self.tr.optimizer  # its gradient vector is clean here: prepare() cleared it once, every step clears it again
         outs, grads = [], []
-        if self.fused_encoder:
-            g = [p.grad for p in self.model.encoder.fused_parameters()]
-            gr = L.vh_encoder_grads(d_q_mu=_ptr(self.buf.d_q_mu), d_q_prec=_ptr(self.buf.d_q_prec), g_conv_w=_ptr(g[0]),
-                                    g_conv_b=_ptr(g[1]), g_lin_w=_ptr(g[2]), g_lin_b=_ptr(g[3]), g_local_w=_nz(g[4]),
-                                    g_local_b=_nz(g[5]), g_gcond_w=_nz(g[6]), g_global_free=_nz(g[7]), d_pre=_ptr(self.enc_dpre))
-            L.check(self.prob.lib.vh_encoder_bwd(C.byref(self.enc_desc), C.byref(self._enc_io), C.byref(gr), _stream()))
-        else:
+        if not self.fused_encoder:
             outs, grads = [self.q_mu, self.q_prec], [self.buf.d_q_mu, self.buf.d_q_prec]
         if self.weights is not None and self.weights.requires_grad:
             outs.append(self.weights)
@@ -356,8 +361,22 @@ class GraphedStep(object):
             grads.append(self.d_extra)
         if outs:
             torch.autograd.backward(outs, grads)
+        gr = None
+        if self.fused_encoder:
+            g = [p.grad for p in self.model.encoder.fused_parameters()]
+            gr = L.vh_encoder_grads(d_q_mu=_ptr(self.buf.d_q_mu), d_q_prec=_ptr(self.buf.d_q_prec), g_conv_w=_ptr(g[0]),
+                                    g_conv_b=_ptr(g[1]), g_lin_w=_ptr(g[2]), g_lin_b=_ptr(g[3]), g_local_w=_nz(g[4]),
+                                    g_local_b=_nz(g[5]), g_gcond_w=_nz(g[6]), g_global_free=_nz(g[7]), d_pre=_ptr(self.enc_dpre))
         # the cost guards the update ON THE DEVICE: a NaN cost (NaN gradients) must not reach the parameters or the Adam
         # moments before the host has looked at it (vihds/training.py:331-336 checks before optimizer.step())
+        if gr is not None and self.pg is None and self.B <= 128 and os.environ.get("VIHDS_FUSE_ADAM", "1") != "0":
+            # one GPU, small batch: encoder backward, then the hidden-layer weight gradient + Adam in ONE launch
+            L.check(self.prob.lib.vh_encoder_bwd_adam(
+                C.byref(self.enc_desc), C.byref(self._enc_io), C.byref(gr), opt.flat.numel(), _ptr(opt.flat), _ptr(opt.grad),
+                _ptr(opt.exp_avg), _ptr(opt.exp_avg_sq), _ptr(opt.hyper), _ptr(opt.step_dev), _ptr(self.buf.cost), _stream()))
+            return
+        if gr is not None:
+            L.check(self.prob.lib.vh_encoder_bwd(C.byref(self.enc_desc), C.byref(self._enc_io), C.byref(gr), _stream()))
         if self.exchange is not None:
             opt.step_exchange(self.exchange, guard=self.buf.cost)  # exchange over NVLink peer memory + Adam, one launch
         else:
