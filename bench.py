@@ -459,7 +459,8 @@ def run_workload(name, a, rank, local_rank, world, device, pg, primary):
     res["dtype"] = "f32" if settings.dtype == torch.float32 else "f64"
     # launches of libvihds_b200.so per step: enc_fwd, [conditioner,] elbo_fwd, [iwae_fwd_bwd unless fused into] elbo_bwd,
     # enc_bwd, [enc_lin_wgrad unless fused into] adam / exchange+adam (also clears the gradient vector, bumps the step counter)
-    fused_adam = gs.fused_encoder and world == 1 and B <= 128 and os.environ.get("VIHDS_FUSE_ADAM", "1") != "0"
+    fused_adam = (gs.fused_encoder and (world == 1 or gs.exchange is not None) and B <= 128 and
+                  os.environ.get("VIHDS_FUSE_ADAM", "1") != "0")
     res["launches_per_step"] = 7 + (1 if gs.rel else 0) - (1 if gs.fuse_iwae else 0) - (1 if fused_adam else 0)
     res["fusions"] = {"iwae_in_reverse_launch": bool(gs.fuse_iwae), "lin_wgrad_in_adam_launch": bool(fused_adam)}
     res["_objects"] = (settings, parameters, model, host, B, IW, T)

@@ -251,6 +251,19 @@ int vh_peer_buffer_destroy(void* dev_ptr);
 int vh_adam_allreduce_step(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq,
                            const void* hyper, void* step, void* state, int rank, int world, const void* peers,
                            const void* guard, double timeout_s, void* stream);
+/* Same, with the encoder's hidden-layer weight gradient formed on the way to the peers (the data-parallel counterpart of
+ * vh_encoder_bwd_adam): entries [offset, offset + H*NLIN) of the flat gradient receive sum_b d_pre[b][o] * pooled[b][c]
+ * (d_pre [B][H], pooled [B][NLIN]: what vh_encoder_bwd leaves / vh_encoder_fwd saved) before they are pushed.  The
+ * caller runs the encoder backward WITHOUT that weight gradient (vh_encoder_grads.skip_lin_wgrad).  B <= 128. */
+typedef struct vh_lin_wgrad {
+  const void* d_pre;
+  const void* pooled;
+  int B, H, NLIN;
+  long long offset; /* of the hidden-layer weight view inside the flat vector, in elements */
+} vh_lin_wgrad;
+int vh_adam_allreduce_step_wgrad(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq,
+                                 const void* hyper, void* step, void* state, int rank, int world, const void* peers,
+                                 const void* guard, double timeout_s, const vh_lin_wgrad* wg, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Fused amortised encoder q(theta | x, d) (vihds/encoders.py:16-55 ConditionalEncoder, :126-253 Q_Local / Q_Global_Cond
@@ -277,7 +290,8 @@ typedef struct vh_encoder_io {
 typedef struct vh_encoder_grads {
   const void *d_q_mu, *d_q_prec; /* [B][P] */
   void *g_conv_w, *g_conv_b, *g_lin_w, *g_lin_b, *g_local_w, *g_local_b, *g_gcond_w, *g_global_free;
-  void* d_pre; /* workspace [B][H] */
+  void* d_pre; /* workspace [B][H]: cotangent of the hidden layer's pre-activations (kept: input of the weight gradient) */
+  int skip_lin_wgrad; /* != 0: leave g_lin_w alone (vh_adam_allreduce_step_wgrad forms it inside the exchange launch) */
 } vh_encoder_grads;
 
 int vh_encoder_fwd(const vh_encoder_desc* e, const vh_encoder_io* io, void* stream);

@@ -56,7 +56,12 @@ class vh_encoder_io(C.Structure):
 class vh_encoder_grads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "d_q_mu", "d_q_prec", "g_conv_w", "g_conv_b", "g_lin_w", "g_lin_b", "g_local_w", "g_local_b", "g_gcond_w",
-        "g_global_free", "d_pre")]
+        "g_global_free", "d_pre")] + [("skip_lin_wgrad", C.c_int)]
+
+
+class vh_lin_wgrad(C.Structure):
+    _fields_ = [("d_pre", C.c_void_p), ("pooled", C.c_void_p), ("B", C.c_int), ("H", C.c_int), ("NLIN", C.c_int),
+                ("offset", C.c_longlong)]
 
 
 _lib = None
@@ -103,6 +108,8 @@ def load():
     lib.vh_peer_buffer_destroy.argtypes = [C.c_void_p]
     lib.vh_adam_allreduce_step.argtypes = ([C.c_int, C.c_size_t] + [C.c_void_p] * 7 +
                                            [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p])
+    lib.vh_adam_allreduce_step_wgrad.argtypes = ([C.c_int, C.c_size_t] + [C.c_void_p] * 7 +
+                                                 [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.POINTER(vh_lin_wgrad), C.c_void_p])
     lib.vh_iwae_fwd_bwd.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 10
     lib.vh_device_conditioner.argtypes = [C.c_int] * 7 + [C.c_void_p] * 6
     lib.vh_encoder_fwd.argtypes = [C.POINTER(vh_encoder_desc), C.POINTER(vh_encoder_io), C.c_void_p]

@@ -621,6 +621,7 @@ static int enc_bwd_t(const EncDims& d, const vh_encoder_io* io, const vh_encoder
     enc_bwd_g<R, 4>(d, p, s);
   else
     enc_bwd_g<R, 1>(d, p, s);
+  if (g && g->skip_lin_wgrad) return 0;  // formed inside the exchange launch (vh_adam_allreduce_step_wgrad)
   if (ad) {  // B <= 128 (checked by the caller): weight gradient of the hidden layer + Adam over the flat vector, one launch
     const long long lin_off = (long long)(p.g_lin_w - (R*)ad->grad);
     enc_lin_wgrad_adam_kernel<R><<<(unsigned)((ad->n + 255) / 256), 256, 0, s>>>(

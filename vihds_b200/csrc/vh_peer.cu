@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(size_t n, size_t n_
                                                              const double* __restrict__ hyper, long long* step,
                                                              long long* state, int rank, int world,
                                                              unsigned char* const* __restrict__ peers,
-                                                             const R* __restrict__ guard, unsigned long long timeout_ns) {
+                                                             const R* __restrict__ guard, unsigned long long timeout_ns,
+                                                             const R* __restrict__ wg_dpre, const R* __restrict__ wg_pooled,
+                                                             int wg_B, int wg_H, int wg_NLIN, long long wg_off) {
   if (*(volatile long long*)(state + 2) != 0) return;  // the exchange has failed before: nothing may be applied
   const unsigned long long epoch = (unsigned long long)*(volatile long long*)state;
   const double t = (double)(*(volatile long long*)step + 1);
@@ -66,8 +68,23 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(size_t n, size_t n_
   if (threadIdx.x == 0) s_skip = s_last = 0;
   // A. push
   for (size_t i = i0; i < n; i += stride) {
-    const R val = g[i];
+    R val = g[i];
     g[i] = R(0);
+    // optional: the encoder's hidden-layer weight gradient dW[o][c] = sum_b d_pre[b][o] pooled[b][c] is formed here, on its
+    // way to the peers, instead of by a launch of its own (small batches; vh_encoder.cu enc_lin_wgrad_small_kernel)
+    const long long e = (long long)i - wg_off;
+    if (wg_dpre && e >= 0 && e < (long long)wg_H * wg_NLIN) {
+      const int o = (int)(e / wg_NLIN), c = (int)(e % wg_NLIN);
+      R a0 = R(0), a1 = R(0);
+      int b = 0;
+#pragma unroll 6
+      for (; b + 1 < wg_B; b += 2) {
+        a0 += wg_dpre[(size_t)b * wg_H + o] * wg_pooled[(size_t)b * wg_NLIN + c];
+        a1 += wg_dpre[(size_t)(b + 1) * wg_H + o] * wg_pooled[(size_t)(b + 1) * wg_NLIN + c];
+      }
+      if (b < wg_B) a0 += wg_dpre[(size_t)b * wg_H + o] * wg_pooled[(size_t)b * wg_NLIN + c];
+      val += a0 + a1;
+    }
     for (int r = 0; r < world; ++r) {
       R* inbox = reinterpret_cast<R*>(peers[r] + PEER_FLAG_BYTES);
       inbox[((size_t)par * world + rank) * n_pad + i] = val;
@@ -193,9 +210,9 @@ int vh_peer_buffer_open(const void* handle64, void** dev_ptr) {
 int vh_peer_buffer_close(void* dev_ptr) { return cudaIpcCloseMemHandle(dev_ptr) == cudaSuccess ? VH_OK : VH_ERR_CUDA; }
 int vh_peer_buffer_destroy(void* dev_ptr) { return cudaFree(dev_ptr) == cudaSuccess ? VH_OK : VH_ERR_CUDA; }
 
-int vh_adam_allreduce_step(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq, const void* hyper,
-                           void* step, void* state, int rank, int world, const void* peers, const void* guard,
-                           double timeout_s, void* stream) {
+static int allreduce_step(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq, const void* hyper,
+                          void* step, void* state, int rank, int world, const void* peers, const void* guard, double timeout_s,
+                          const vh_lin_wgrad* wg, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || !hyper || !step || !state || !peers || n == 0 || world < 1 ||
       world > VH_PEER_MAX_WORLD || rank < 0 || rank >= world) {
     set_error("vh_adam_allreduce_step: bad arguments");
@@ -216,11 +233,16 @@ int vh_adam_allreduce_step(int dtype, size_t n, void* param, void* grad, void* e
   if (dtype == VH_F32)
     adam_allreduce_kernel<float><<<grid, block, 0, s>>>(n, n_pad, (float*)param, (float*)grad, (float*)exp_avg,
                                                          (float*)exp_avg_sq, (const double*)hyper, (long long*)step,
-                                                         (long long*)state, rank, world, pp, (const float*)guard, tns);
+                                                         (long long*)state, rank, world, pp, (const float*)guard, tns,
+                                                         (const float*)(wg ? wg->d_pre : nullptr), (const float*)(wg ? wg->pooled : nullptr),
+                                                         wg ? wg->B : 0, wg ? wg->H : 0, wg ? wg->NLIN : 0, wg ? wg->offset : 0);
   else if (dtype == VH_F64)
     adam_allreduce_kernel<double><<<grid, block, 0, s>>>(n, n_pad, (double*)param, (double*)grad, (double*)exp_avg,
                                                           (double*)exp_avg_sq, (const double*)hyper, (long long*)step,
-                                                          (long long*)state, rank, world, pp, (const double*)guard, tns);
+                                                          (long long*)state, rank, world, pp, (const double*)guard, tns,
+                                                          (const double*)(wg ? wg->d_pre : nullptr),
+                                                          (const double*)(wg ? wg->pooled : nullptr), wg ? wg->B : 0,
+                                                          wg ? wg->H : 0, wg ? wg->NLIN : 0, wg ? wg->offset : 0);
   else {
     set_error("unknown dtype %d", dtype);
     return VH_ERR_INVALID;
@@ -231,6 +253,25 @@ int vh_adam_allreduce_step(int dtype, size_t n, void* param, void* grad, void* e
     return VH_ERR_CUDA;
   }
   return VH_OK;
+}
+
+int vh_adam_allreduce_step(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq, const void* hyper,
+                           void* step, void* state, int rank, int world, const void* peers, const void* guard,
+                           double timeout_s, void* stream) {
+  return allreduce_step(dtype, n, param, grad, exp_avg, exp_avg_sq, hyper, step, state, rank, world, peers, guard, timeout_s,
+                        nullptr, stream);
+}
+
+int vh_adam_allreduce_step_wgrad(int dtype, size_t n, void* param, void* grad, void* exp_avg, void* exp_avg_sq,
+                                 const void* hyper, void* step, void* state, int rank, int world, const void* peers,
+                                 const void* guard, double timeout_s, const vh_lin_wgrad* wg, void* stream) {
+  if (wg && (!wg->d_pre || !wg->pooled || wg->B <= 0 || wg->B > 128 || wg->H <= 0 || wg->NLIN <= 0 || wg->offset < 0 ||
+             (size_t)wg->offset + (size_t)wg->H * wg->NLIN > n)) {
+    set_error("vh_adam_allreduce_step_wgrad: bad vh_lin_wgrad (B must be 1..128, the weight view must lie inside the flat vector)");
+    return VH_ERR_INVALID;
+  }
+  return allreduce_step(dtype, n, param, grad, exp_avg, exp_avg_sq, hyper, step, state, rank, world, peers, guard, timeout_s, wg,
+                        stream);
 }
 
 }  // extern "C"

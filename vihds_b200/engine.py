@@ -298,10 +298,19 @@ class FlatAdam(object):
     def zero_grad(self):
         self.grad.zero_()
 
-    def step_exchange(self, exchange, guard=None):
+    def step_exchange(self, exchange, guard=None, lin_wgrad=None):
         """Data-parallel step: sum the ranks' gradients over NVLink peer memory and apply Adam in ONE launch
         (distributed.PeerGradientExchange); the gradient vector is cleared.  guard: this rank's cost (device tensor):
         a NaN cost on ANY rank makes every rank skip the update (vihds/training.py:331-336)."""
+        if lin_wgrad is not None:  # (d_pre [B,H], pooled [B,NLIN], gradient view of the hidden-layer weight)
+            d_pre, pooled, gview = lin_wgrad
+            wg = L.vh_lin_wgrad(d_pre=_ptr(d_pre), pooled=_ptr(pooled), B=d_pre.shape[0], H=d_pre.shape[1], NLIN=pooled.shape[1],
+                                offset=(gview.data_ptr() - self.grad.data_ptr()) // self.grad.element_size())
+            L.check(L.load().vh_adam_allreduce_step_wgrad(
+                self.vdt, self.flat.numel(), _ptr(self.flat), _ptr(self.grad), _ptr(self.exp_avg), _ptr(self.exp_avg_sq),
+                _ptr(self.hyper), _ptr(self.step_dev), _ptr(exchange.state), exchange.rank, exchange.world, _ptr(exchange.peers),
+                _ptr(guard), float(exchange.timeout_s), C.byref(wg), _stream()))
+            return
         L.check(L.load().vh_adam_allreduce_step(self.vdt, self.flat.numel(), _ptr(self.flat), _ptr(self.grad),
                                                 _ptr(self.exp_avg), _ptr(self.exp_avg_sq), _ptr(self.hyper),
                                                 _ptr(self.step_dev), _ptr(exchange.state), exchange.rank, exchange.world,

@@ -375,10 +375,14 @@ class GraphedStep(object):
                 C.byref(self.enc_desc), C.byref(self._enc_io), C.byref(gr), opt.flat.numel(), _ptr(opt.flat), _ptr(opt.grad),
                 _ptr(opt.exp_avg), _ptr(opt.exp_avg_sq), _ptr(opt.hyper), _ptr(opt.step_dev), _ptr(self.buf.cost), _stream()))
             return
+        fuse_wg = (gr is not None and self.exchange is not None and self.B <= 128 and os.environ.get("VIHDS_FUSE_ADAM", "1") != "0")
         if gr is not None:
+            gr.skip_lin_wgrad = int(fuse_wg)  # formed inside the exchange launch instead
             L.check(self.prob.lib.vh_encoder_bwd(C.byref(self.enc_desc), C.byref(self._enc_io), C.byref(gr), _stream()))
         if self.exchange is not None:
-            opt.step_exchange(self.exchange, guard=self.buf.cost)  # exchange over NVLink peer memory + Adam, one launch
+            # gradient exchange over NVLink peer memory + Adam (+ the hidden-layer weight gradient): one launch
+            opt.step_exchange(self.exchange, guard=self.buf.cost,
+                              lin_wgrad=(self.enc_dpre, self.enc_pooled, self.model.encoder.fused_parameters()[2].grad) if fuse_wg else None)
         else:
             if self.pg is not None:
                 torch.distributed.all_reduce(opt.grad, group=self.pg)
