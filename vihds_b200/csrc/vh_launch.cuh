@@ -208,7 +208,7 @@ template <class M, class TB>
 struct WsRing {
   typedef typename M::real R;
   typedef StageData<Rhs<M>, TB> SD;
-  static constexpr int KN = sizeof(typename M::Mid) / sizeof(R);
+  static constexpr int KN = sizeof(typename Rhs<M>::Kept) / sizeof(R);  // species intermediates (+ NeuralPrecisions activations)
   static constexpr int NITEM = M::S + SD::nk * M::S + TB::s * KN;
   static constexpr int SLOT = NITEM * 32;  // elements per ring slot
   __device__ static void put(R* slot, int lane, const R* x, const SD& sd) {

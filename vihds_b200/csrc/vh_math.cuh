@@ -28,7 +28,19 @@ VH_HD_NOINLINE float vpow(float x, float y) { return powf(x, y); }
 VH_HD_NOINLINE double vpow(double x, double y) { return pow(x, y); }
 VH_HD float vsqrt(float x) { return sqrtf(x); }
 VH_HD double vsqrt(double x) { return sqrt(x); }
-VH_HD float vtanh(float x) { return tanhf(x); }
+// fp32 on the device: tanh on the SFU, 1 - 2 / (exp(2x) + 1) with ex2.approx + rcp.approx (6 instructions instead of the
+// ~25 of tanhf; absolute error <= 3e-7, the class of fp32 round-off).  The NeuralPrecisions nets evaluate 9..14 of them
+// per right-hand-side evaluation.  Host build and fp64 keep the library function.
+VH_HD float vtanh(float x) {
+#if defined(__CUDA_ARCH__)
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+  return fmaf(-2.f, r, 1.f);
+#else
+  return tanhf(x);
+#endif
+}
 VH_HD double vtanh(double x) { return tanh(x); }
 
 // Division inside the time loop.  IEEE `a / b` in fp32 costs ~12 SASS instructions, a convergence barrier and a
@@ -71,9 +83,24 @@ VH_HD double ld_early(const double* p) {
 #endif
 }
 
+// fp32 on the device: sigmoid on the SFU (ex2.approx + rcp.approx, 4 instructions instead of ~14, and the head of the
+// dependent chain of every right-hand-side evaluation).  The argument product carries |z| 2^-24 of error, i.e. an absolute
+// error in sigma of at most sigma (1 - sigma) |z| 1e-7 < 4e-7; +-inf saturate, NaN propagates.  Host build and fp64:
+// 1 / (1 + exp(-z)).
+VH_HD float sigmoid_impl(float z) {
+#if defined(__CUDA_ARCH__)
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+#else
+  return vdiv(1.f, 1.f + vexp(-z));
+#endif
+}
+VH_HD double sigmoid_impl(double z) { return vdiv(1.0, 1.0 + vexp(-z)); }
 template <typename R>
 VH_HD R sigmoid(R z) {
-  return vdiv(R(1), R(1) + vexp(-z));
+  return sigmoid_impl(z);
 }
 
 // torch.clamp semantics: NaN propagates (both comparisons false); gradient passes on the CLOSED interval.

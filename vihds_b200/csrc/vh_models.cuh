@@ -705,51 +705,58 @@ struct GrowthModel {
 template <typename R, int NIN>
 struct LinPrecNet {
   static constexpr int NW = 2 * (4 * NIN + 4);
+  // what an evaluation leaves for its VJP: the tanh'd inputs and the eight sigmoids (recomputing them was 13 tanh + 8
+  // sigmoids per VJP at relay's 13 inputs -- the bulk of the reverse sweep of the *_precisions models)
+  struct Kept {
+    R a[NIN], sp[4], sd[4];
+  };
   // species = xin[1..NIN), v = current precision states
-  VH_HD static void rhs(R t, const R* species, const R* v, const R* w, R* dv) {
-    R a[NIN];
-    a[0] = vtanh(t);
+  VH_HD static void rhs_keep(R t, const R* species, const R* v, const R* w, R* dv, Kept& k) {
+    k.a[0] = vtanh(t);
 #pragma unroll
-    for (int j = 1; j < NIN; ++j) a[j] = vtanh(species[j - 1]);
+    for (int j = 1; j < NIN; ++j) k.a[j] = vtanh(species[j - 1]);
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
       R zp = w[4 * NIN + o], zd = w[(4 * NIN + 4) + 4 * NIN + o];
 #pragma unroll
       for (int j = 0; j < NIN; ++j) {
-        zp += w[o * NIN + j] * a[j];
-        zd += w[(4 * NIN + 4) + o * NIN + j] * a[j];
+        zp += w[o * NIN + j] * k.a[j];
+        zd += w[(4 * NIN + 4) + o * NIN + j] * k.a[j];
       }
-      dv[o] = sigmoid(zp) - sigmoid(zd) * v[o];
+      k.sp[o] = sigmoid(zp);
+      k.sd[o] = sigmoid(zd);
+      if (dv) dv[o] = k.sp[o] - k.sd[o] * v[o];
     }
+  }
+  VH_HD static void rhs(R t, const R* species, const R* v, const R* w, R* dv) {
+    Kept k;
+    rhs_keep(t, species, v, w, dv, k);
   }
   // gw: this thread's weight-gradient accumulators, element k at gw[k * gstride]
   template <typename GW>
-  VH_HD static void rhs_vjp(R t, const R* species, const R* v, const R* w, const R* g, R* gspecies, R* gv, GW& gw) {
-    R a[NIN], ga[NIN];
-    a[0] = vtanh(t);
-#pragma unroll
-    for (int j = 1; j < NIN; ++j) a[j] = vtanh(species[j - 1]);
+  VH_HD static void rhs_vjp_kept(const Kept& k, const R* v, const R* w, const R* g, R* gspecies, R* gv, GW& gw) {
+    R ga[NIN];
 #pragma unroll
     for (int j = 0; j < NIN; ++j) ga[j] = R(0);
     R gzp[4], gzd[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
-      R zp = w[4 * NIN + o], zd = w[(4 * NIN + 4) + 4 * NIN + o];
-#pragma unroll
-      for (int j = 0; j < NIN; ++j) {
-        zp += w[o * NIN + j] * a[j];
-        zd += w[(4 * NIN + 4) + o * NIN + j] * a[j];
-      }
-      const R sp = sigmoid(zp), sd = sigmoid(zd);
+      const R sp = k.sp[o], sd = k.sd[o];
       gv[o] -= g[o] * sd;
       gzp[o] = g[o] * sp * (R(1) - sp);
       gzd[o] = -g[o] * v[o] * sd * (R(1) - sd);
 #pragma unroll
       for (int j = 0; j < NIN; ++j) ga[j] += gzp[o] * w[o * NIN + j] + gzd[o] * w[(4 * NIN + 4) + o * NIN + j];
     }
-    gw.template outer<NIN>(a, gzp, gzd);  // weight gradients (in place, or handed to another warp)
+    gw.template outer<NIN>(k.a, gzp, gzd);  // weight gradients (in place, or handed to another warp)
 #pragma unroll
-    for (int j = 1; j < NIN; ++j) gspecies[j - 1] += ga[j] * (R(1) - a[j] * a[j]);
+    for (int j = 1; j < NIN; ++j) gspecies[j - 1] += ga[j] * (R(1) - k.a[j] * k.a[j]);
+  }
+  template <typename GW>
+  VH_HD static void rhs_vjp(R t, const R* species, const R* v, const R* w, const R* g, R* gspecies, R* gv, GW& gw) {
+    Kept k;
+    rhs_keep(t, species, v, w, (R*)nullptr, k);
+    rhs_vjp_kept(k, v, w, g, gspecies, gv, gw);
   }
 };
 

@@ -116,12 +116,24 @@ struct StridedGW {  // element k of this thread's accumulators lives at base[k *
 };
 
 // full right-hand side over the ODE state (species + dynamic-precision states) ---------------------------------
+// what a stage evaluation hands to its VJP: the species intermediates and, for dynamic precisions, the activations of the
+// NeuralPrecisions net (no hidden layer).  Plain R members only: the warp-specialised kernel ships it as an R array.
+template <class M, bool DYN>
+struct RhsKept {
+  typename M::Mid m;
+  typename LinPrecNet<typename M::real, M::NIN>::Kept p;
+};
+template <class M>
+struct RhsKept<M, false> {
+  typename M::Mid m;
+};
+
 template <class M>
 struct Rhs {
   typedef typename M::real R;
   typedef R real;
   typedef typename M::Mid Mid;
-  typedef Mid Kept;                  // what eval_keep hands to vjp_kept
+  typedef RhsKept<M, M::DYN> Kept;
   typedef typename M::Consts Grad;   // cotangent accumulator of the per-trajectory constants
   static constexpr int S = M::S;
   typename M::Consts c;
@@ -130,12 +142,11 @@ struct Rhs {
 
   VH_HD void eval(R t, const R* x, R* dx) const {
     Mid m;
-    eval_keep(t, x, dx, m);
-  }
-  // same, handing back the species intermediates so that the reverse sweep need not recompute them
-  VH_HD void eval_keep(R t, const R* x, R* dx, Mid& m) const {
     M::mid(t, x, c, m);
     M::rhs_from(x, c, m, dx);
+    net_rhs(t, x, dx);
+  }
+  VH_HD void net_rhs(R t, const R* x, R* dx) const {
     if (M::DYN) {
       if (nh == 0)
         LinPrecNet<R, M::NIN>::rhs(t, x, x + M::NS, w, dx + M::NS);
@@ -143,23 +154,43 @@ struct Rhs {
         HidPrecNet<R, M::NIN>::rhs(t, x, x + M::NS, w, nh, dx + M::NS);
     }
   }
+  // same, handing back the intermediates so that the reverse sweep need not recompute them
+  VH_HD void eval_keep(R t, const R* x, R* dx, Kept& k) const {
+    M::mid(t, x, c, k.m);
+    M::rhs_from(x, c, k.m, dx);
+    keep_net(t, x, dx + M::NS, k);
+  }
   // intermediates only (last stage of a step: its derivative is not needed to rebuild any stage state)
-  VH_HD void keep_only(R t, const R* x, Mid& m) const { M::mid(t, x, c, m); }
+  VH_HD void keep_only(R t, const R* x, Kept& k) const {
+    M::mid(t, x, c, k.m);
+    keep_net(t, x, (R*)nullptr, k);
+  }
+  VH_HD void keep_net(R t, const R* x, R* dv, RhsKept<M, true>& k) const {
+    if (nh == 0)
+      LinPrecNet<R, M::NIN>::rhs_keep(t, x, x + M::NS, w, dv, k.p);
+    else if (dv)
+      HidPrecNet<R, M::NIN>::rhs(t, x, x + M::NS, w, nh, dv);  // hidden-layer nets recompute in their VJP
+  }
+  VH_HD void keep_net(R, const R*, R*, RhsKept<M, false>&) const {}
   template <typename GW>
-  VH_HD void vjp_kept(R t, const R* x, const Mid& m, const R* g, R* gx, typename M::Consts& gc, GW& gw) const {
-    M::rhs_vjp_from(x, c, m, g, gx, gc);
-    if (M::DYN) {
-      if (nh == 0)
-        LinPrecNet<R, M::NIN>::rhs_vjp(t, x, x + M::NS, w, g + M::NS, gx, gx + M::NS, gw);
-      else
-        HidPrecNet<R, M::NIN>::rhs_vjp(t, x, x + M::NS, w, nh, g + M::NS, gx, gx + M::NS, gw);
-    }
+  VH_HD void vjp_kept(R t, const R* x, const Kept& k, const R* g, R* gx, typename M::Consts& gc, GW& gw) const {
+    M::rhs_vjp_from(x, c, k.m, g, gx, gc);
+    net_vjp(t, x, k, g, gx, gw);
   }
   template <typename GW>
+  VH_HD void net_vjp(R t, const R* x, const RhsKept<M, true>& k, const R* g, R* gx, GW& gw) const {
+    if (nh == 0)
+      LinPrecNet<R, M::NIN>::rhs_vjp_kept(k.p, x + M::NS, w, g + M::NS, gx, gx + M::NS, gw);
+    else
+      HidPrecNet<R, M::NIN>::rhs_vjp(t, x, x + M::NS, w, nh, g + M::NS, gx, gx + M::NS, gw);
+  }
+  template <typename GW>
+  VH_HD void net_vjp(R, const R*, const RhsKept<M, false>&, const R*, R*, GW&) const {}
+  template <typename GW>
   VH_HD void vjp(R t, const R* x, const R* g, R* gx, typename M::Consts& gc, GW& gw) const {
-    Mid m;
-    M::mid(t, x, c, m);
-    vjp_kept(t, x, m, g, gx, gc, gw);
+    Kept k;
+    keep_only(t, x, k);
+    vjp_kept(t, x, k, g, gx, gc, gw);
   }
 };
 
