@@ -292,6 +292,8 @@ typedef struct vh_encoder_grads {
   void *g_conv_w, *g_conv_b, *g_lin_w, *g_lin_b, *g_local_w, *g_local_b, *g_gcond_w, *g_global_free;
   void* d_pre; /* workspace [B][H]: cotangent of the hidden layer's pre-activations (kept: input of the weight gradient) */
   int skip_lin_wgrad; /* != 0: leave g_lin_w alone (vh_adam_allreduce_step_wgrad forms it inside the exchange launch) */
+  void* dpool; /* optional workspace [B][F*NP]: with it, batches of >= 256 individuals run the hidden layer's backward as
+                * GEMMs (as the forward call does on its own); NULL: one monolithic launch per individual group */
 } vh_encoder_grads;
 
 int vh_encoder_fwd(const vh_encoder_desc* e, const vh_encoder_io* io, void* stream);

@@ -304,13 +304,15 @@ def test_training_run_prints_finite_elbo(spec, capsys):
     assert all(np.isfinite(float(l.split("=")[-1])) for l in lines)
 
 
-def test_fused_encoder_large_batch_grouped_path():
-    """B = 601 (>= 4 x 148: four individuals per CTA, ragged last group) against the stock-PyTorch encoder."""
+@pytest.mark.parametrize("B", [300, 601, 130])
+def test_fused_encoder_large_batch_paths(B):
+    """Against the stock-PyTorch encoder: B = 300 and 601 take the GEMM path of the hidden layer (conv + pool | GEMM | tanh +
+    heads forward; heads | two GEMMs | pool + conv backward), with one individual per CTA resp. four (>= 4 x 148, ragged last
+    group); B = 130 the monolithic kernels with the B-split weight-gradient kernel."""
     case = load_case("dr_constant_icml_midpoint_f32_iw8")
     settings, par, model, training = build("dr_constant_icml")
     enc = model.encoder
     small = batch_from_case(case)
-    B = 601
     idx = torch.arange(B, device="cuda") % small.inputs.shape[0]
     g = torch.Generator(device="cuda").manual_seed(1)
     batch = Settings(times=small.times, inputs=small.inputs[idx].contiguous(), dev_1hot=small.dev_1hot[idx].contiguous(),

@@ -56,7 +56,7 @@ class vh_encoder_io(C.Structure):
 class vh_encoder_grads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "d_q_mu", "d_q_prec", "g_conv_w", "g_conv_b", "g_lin_w", "g_lin_b", "g_local_w", "g_local_b", "g_gcond_w",
-        "g_global_free", "d_pre")] + [("skip_lin_wgrad", C.c_int)]
+        "g_global_free", "d_pre")] + [("skip_lin_wgrad", C.c_int), ("dpool", C.c_void_p)]
 
 
 class vh_lin_wgrad(C.Structure):

@@ -26,6 +26,8 @@ struct EncDims {
   int L1, NCV, NP, NLIN;    // T-1, conv outputs per filter, pooled outputs per filter, F*NP
   int nin_l, nin_g;
   int stage;                // kernels copy their weights into shared memory up front (cp.async) -- see stage_async
+  int phase;                // 0: whole chain in one launch; large batches run the hidden layer as GEMMs (enc_gemm_kernel)
+                            // between two launches of these kernels: 1 = the part before it, 2 = the part after it
 };
 
 template <typename R>
@@ -34,6 +36,7 @@ struct EncPtrs {
   R *q_mu, *q_prec, *pooled, *enc;
   const R *d_q_mu, *d_q_prec;
   R *g_conv_w, *g_conv_b, *g_lin_w, *g_lin_b, *g_local_w, *g_local_b, *g_gcond_w, *g_global_free, *d_pre;
+  R* dpool_g;  // large batches: cotangent of the pooled features [B][NLIN], produced by the GEMM between the two phases
 };
 
 template <typename R>
@@ -78,6 +81,90 @@ __host__ __device__ inline int up4(int n) { return (n + 3) & ~3; }
 // Everything here is latency-bound (36 CTAs for the icml batch), so the loops that read weights from global memory
 // keep several independent loads in flight: the hidden layer accumulates up to ENC_OPW outputs per warp at once, the
 // heads use one warp per row.
+// ---------------------------------------------------------------------------------------------------------------
+// The hidden layer of the encoder at LARGE batches is three GEMMs (B individuals x NLIN pooled features x H units):
+//   forward   pre[b][o]   = sum_i pooled[b][i] W[o][i]          (M, N, K) = (B, H, NLIN)
+//   backward  dpool[b][i] = sum_o d_pre[b][o] W[o][i]           (B, NLIN, H)
+//   weights   dW[o][i]   += sum_b d_pre[b][o] pooled[b][i]      (H, NLIN, B)
+// Done per individual inside the monolithic kernels, every CTA streams the whole weight matrix from L2 (1 MB at T = 500)
+// and the weight gradient is a B-deep sum per thread: 156 + 218 + 99 us at B = 1,024.  One shared-memory tiled SIMT GEMM
+// with general strides serves all three: 64 x 64 tile per CTA, 16-deep k chunks, 4 x 4 outputs per thread, split-K over
+// blockIdx.z with atomicAdd (C must be zeroed, or hold the value to accumulate into).  fp32 / fp64 FMAs: the problem is
+// 250 MFLOP, a latency / bandwidth matter, not one for the tensor cores.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(256) enc_gemm_kernel(int M, int N, int K, const R* __restrict__ A, long long sam, long long sak,
+                                                       const R* __restrict__ Bm, long long sbk, long long sbn, R* __restrict__ C,
+                                                       long long ldc, int k_per_split) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ R As[TK][TM + 4];
+  __shared__ R Bs[TK][TN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  const int k_lo = blockIdx.z * k_per_split, k_hi = min(K, k_lo + k_per_split);
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each a 4 x 4 block: rows ty*4.., columns tx*4..
+  R acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = R(0);
+  for (int k0 = k_lo; k0 < k_hi; k0 += TK) {
+    // tile loads: consecutive threads along whichever index is contiguous in memory
+#pragma unroll
+    for (int e = tid; e < TM * TK; e += 256) {
+      int mm, kk;
+      if (sak == 1) { kk = e % TK; mm = e / TK; } else { mm = e % TM; kk = e / TM; }
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < M && k < k_hi) ? A[(long long)m * sam + (long long)k * sak] : R(0);
+    }
+#pragma unroll
+    for (int e = tid; e < TN * TK; e += 256) {
+      int nn, kk;
+      if (sbk == 1) { kk = e % TK; nn = e / TK; } else { nn = e % TN; kk = e / TN; }
+      const int n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < N && k < k_hi) ? Bm[(long long)k * sbk + (long long)n * sbn] : R(0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < TK; ++kk) {
+      R a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) atomicAdd(C + (long long)m * ldc + n, acc[i][j]);
+    }
+  }
+}
+
+// C += A B with split-K sized so that the grid covers the machine about twice
+template <typename R>
+static void enc_gemm(int M, int N, int K, const R* A, long long sam, long long sak, const R* Bm, long long sbk, long long sbn, R* C,
+                     long long ldc, cudaStream_t s) {
+  const int gm = (M + 63) / 64, gn = (N + 63) / 64;
+  int splits = (2 * 148 + gm * gn - 1) / (gm * gn);
+  const int max_splits = (K + 63) / 64;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const int k_per_split = (((K + splits - 1) / splits) + 15) / 16 * 16;
+  dim3 grid(gn, gm, (K + k_per_split - 1) / k_per_split);
+  enc_gemm_kernel<R><<<grid, 256, 0, s>>>(M, N, K, A, sam, sak, Bm, sbk, sbn, C, ldc, k_per_split);
+}
+
 #define ENC_THREADS 512
 #define ENC_OPW 4
 // G individuals per CTA: the hidden-layer weight matrix (H x NLIN, 1 MB at T = 500) is the only large operand and
@@ -115,7 +202,22 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, c
   }
   for (int i = tid; i < ncw + d.F; i += nt) cw[i] = i < ncw ? p.conv_w[i] : p.conv_b[i - ncw];
   const R inv_pool = R(1) / R(d.PL);
-  for (int g = 0; g < ngr; ++g) {
+  if (d.phase == 2) {
+    // after the GEMM: p.enc holds the hidden layer's pre-activations (without bias); tanh in place, then the heads
+    for (int e = tid; e < ngr * d.nin_l; e += nt) {
+      const int g = e / d.nin_l, i = e % d.nin_l, b = b0 + g;
+      R v;
+      if (i < d.H) {
+        v = vtanh(p.enc[(size_t)b * d.H + i] + lin_b[i]);
+        p.enc[(size_t)b * d.H + i] = v;
+      } else {
+        const int j = i - d.H;
+        v = (d.lt && j < d.C) ? p.inputs[(size_t)b * d.C + j] : p.dev[(size_t)b * d.D + (j - (d.lt ? d.C : 0))];
+      }
+      xloc[e] = v;
+    }
+  }
+  for (int g = 0; g < ngr && d.phase != 2; ++g) {
     const int b = b0 + g;
     const R* obs = p.obs + (size_t)b * d.NS * d.T;
     __syncthreads();  // delta / conv scratch of the previous individual fully consumed
@@ -149,9 +251,10 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, c
   }
   if (d.stage) cp_async_commit_wait_all();
   __syncthreads();
+  if (d.phase == 1) return;  // pooled features are in global memory: the hidden layer runs as a GEMM
   // hidden layer: each warp owns outputs o0, o0 + nw, ... and accumulates ENC_OPW of them for all G individuals per
   // pass over the inputs
-  for (int o0 = warp; o0 < d.H; o0 += nw * ENC_OPW) {
+  for (int o0 = warp; o0 < d.H && d.phase == 0; o0 += nw * ENC_OPW) {
     R acc[ENC_OPW][G];
 #pragma unroll
     for (int q = 0; q < ENC_OPW; ++q)
@@ -260,7 +363,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
       delta[i] = obs[c * d.T + j + 1] - obs[c * d.T + j];
     }
   }
-  for (int e = tid; e < ngr * d.nin_l; e += nt) {
+  for (int e = tid; e < ngr * d.nin_l && d.phase != 2; e += nt) {
     const int g = e / d.nin_l, i = e % d.nin_l, b = b0 + g;
     R v;
     if (i < d.H)
@@ -271,7 +374,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
     }
     xloc[e] = v;
   }
-  for (int e = tid; e < ngr * (ncond + d.nglob); e += nt) {
+  for (int e = tid; e < ngr * (ncond + d.nglob) && d.phase != 2; e += nt) {
     const int g = e / (ncond + d.nglob), k = e % (ncond + d.nglob), b = b0 + g;
     dfree[g * nfr + 2 * k] = p.d_q_mu[(size_t)b * d.P + k];
     dfree[g * nfr + 2 * k + 1] = p.d_q_prec[(size_t)b * d.P + k] * p.q_prec[(size_t)b * d.P + k];  // d exp(log_prec)
@@ -281,7 +384,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
   // Small batches: gridDim.y CTAs share one individual, each taking the conv filters f = blockIdx.y (mod gridDim.y) and
   // their pooled columns -- the heavy phases below (dpool, dconv, conv weight gradients) need no exchange between
   // them; the cheap head part above is recomputed by each and only CTA y = 0 publishes its gradients.
-  const bool lead = blockIdx.y == 0;
+  const bool lead = blockIdx.y == 0 && d.phase != 2;  // phase 2 (after the GEMM) has no head part: phase 1 did it
   // parameter gradients of the heads and the global free parameters: summed over the CTA's individuals, then one atomic
   for (int j = tid; lead && j < 2 * d.nglob; j += nt) {
     R a = R(0);
@@ -308,7 +411,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
     }
     atomicAdd(p.g_gcond_w + e, a);
   }
-  for (int e = tid; e < G * d.H; e += nt) {
+  for (int e = tid; e < G * d.H && d.phase != 2; e += nt) {
     const int g = e / d.H, o = e % d.H;
     R gp = R(0);
     if (g < ngr) {
@@ -326,8 +429,12 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
     for (int g = 0; g < ngr; ++g) a += dpre[g * d.H + o];
     atomicAdd(p.g_lin_b + o, a);
   }
+  if (d.phase == 1) return;  // d_pre is in global memory: dpool and the weight gradient are GEMMs
+  if (d.phase == 2) {        // ... and here dpool comes back
+    for (int e = tid; e < ngr * d.NLIN; e += nt) dpool[e] = p.dpool_g[(size_t)b0 * d.NLIN + e];
+  }
   // cotangent of the pooled features: dpool[g][i] = sum_o W[o][i] dpre[g][o]   (each weight loaded once for G individuals)
-  for (int li = tid; li < nfl * d.NP; li += nt) {
+  for (int li = tid; li < nfl * d.NP && d.phase == 0; li += nt) {
     const int i = (fy + (li / d.NP) * nfy) * d.NP + li % d.NP;
     R acc[G];
 #pragma unroll
@@ -532,6 +639,7 @@ static const char* fill_dims(const vh_encoder_desc* e, EncDims& d) {
   d.nin_l = d.H + (d.lt ? d.C : 0) + (d.ld ? d.D : 0);
   d.nin_g = (d.gt ? d.C : 0) + (d.gd ? d.D : 0);
   d.stage = 0;
+  d.phase = 0;
   if (d.B <= 0 || d.NP <= 0 || d.H <= 0) return "encoder: B, n_hidden must be positive and T long enough for the conv + pool";
   if (d.ng > 0 && d.nin_g == 0) return "encoder: global-conditioned parameters need a conditioning input";
   return nullptr;
@@ -549,6 +657,7 @@ static void fill_ptrs(const vh_encoder_io* io, const vh_encoder_grads* g, EncPtr
     p.g_conv_w = (R*)g->g_conv_w; p.g_conv_b = (R*)g->g_conv_b; p.g_lin_w = (R*)g->g_lin_w; p.g_lin_b = (R*)g->g_lin_b;
     p.g_local_w = (R*)g->g_local_w; p.g_local_b = (R*)g->g_local_b; p.g_gcond_w = (R*)g->g_gcond_w;
     p.g_global_free = (R*)g->g_global_free; p.d_pre = (R*)g->d_pre;
+    p.dpool_g = (R*)g->dpool;
   }
 }
 
@@ -595,10 +704,23 @@ static int enc_group(const EncDims& d) {
   return (d.B >= 4 * 148 && smem4 <= 200 * 1024) ? 4 : 1;
 }
 
+// large batches: conv + pool | GEMM | tanh + heads
+static bool enc_gemm_path(const EncDims& d) { return d.B >= 256; }
+
 template <typename R>
 static int enc_fwd_t(const EncDims& d, const vh_encoder_io* io, cudaStream_t s) {
   EncPtrs<R> p = {};
   fill_ptrs<R>(io, nullptr, p);
+  if (enc_gemm_path(d)) {
+    EncDims d1 = d, d2 = d;
+    d1.phase = 1;
+    d2.phase = 2;
+    cudaMemsetAsync(p.enc, 0, sizeof(R) * (size_t)d.B * d.H, s);
+    if (enc_group<R>(d) == 4) enc_fwd_g<R, 4>(d1, p, s); else enc_fwd_g<R, 1>(d1, p, s);
+    enc_gemm<R>(d.B, d.H, d.NLIN, p.pooled, d.NLIN, 1, p.lin_w, 1, d.NLIN, p.enc, d.H, s);  // pre = pooled W^T
+    if (enc_group<R>(d) == 4) enc_fwd_g<R, 4>(d2, p, s); else enc_fwd_g<R, 1>(d2, p, s);
+    return 0;
+  }
   if (enc_group<R>(d) == 4)
     enc_fwd_g<R, 4>(d, p, s);
   else
@@ -617,6 +739,17 @@ template <typename R>
 static int enc_bwd_t(const EncDims& d, const vh_encoder_io* io, const vh_encoder_grads* g, cudaStream_t s, const AdamArgs* ad = nullptr) {
   EncPtrs<R> p = {};
   fill_ptrs<R>(io, g, p);
+  if (enc_gemm_path(d) && p.dpool_g) {
+    EncDims d1 = d, d2 = d;
+    d1.phase = 1;
+    d2.phase = 2;
+    cudaMemsetAsync(p.dpool_g, 0, sizeof(R) * (size_t)d.B * d.NLIN, s);
+    if (enc_group<R>(d) == 4) enc_bwd_g<R, 4>(d1, p, s); else enc_bwd_g<R, 1>(d1, p, s);
+    enc_gemm<R>(d.B, d.NLIN, d.H, p.d_pre, d.H, 1, p.lin_w, d.NLIN, 1, p.dpool_g, d.NLIN, s);       // dpool = d_pre W
+    enc_gemm<R>(d.H, d.NLIN, d.B, p.d_pre, 1, d.H, p.pooled, d.NLIN, 1, p.g_lin_w, d.NLIN, s);      // dW += d_pre^T pooled
+    if (enc_group<R>(d) == 4) enc_bwd_g<R, 4>(d2, p, s); else enc_bwd_g<R, 1>(d2, p, s);
+    return 0;
+  }
   if (enc_group<R>(d) == 4)
     enc_bwd_g<R, 4>(d, p, s);
   else

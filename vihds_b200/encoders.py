@@ -62,6 +62,7 @@ class FusedEncoder(torch.autograd.Function):
         d_mu = torch.zeros_like(q_prec) if d_mu is None else d_mu.contiguous()
         d_prec = torch.zeros_like(q_prec) if d_prec is None else d_prec.contiguous()
         d_pre = torch.empty_like(feats)
+        dpool = torch.empty_like(pooled) if feats.shape[0] >= 256 else None  # large batches: backward through GEMMs
         io = L.vh_encoder_io(observations=_ptr(obs), inputs=_ptr(inputs), dev_1hot=_ptr(dev_1hot), conv_w=_ptr(conv_w),
                              conv_b=_ptr(conv_b), lin_w=_ptr(lin_w), lin_b=_ptr(lin_b), local_w=_ptr(local_w),
                              local_b=_ptr(local_b), gcond_w=_ptr(gcond_w), global_free=_ptr(global_free),
@@ -69,7 +70,7 @@ class FusedEncoder(torch.autograd.Function):
                              enc=_ptr(feats))
         gr = L.vh_encoder_grads(d_q_mu=_ptr(d_mu), d_q_prec=_ptr(d_prec), g_conv_w=_ptr(g[0]), g_conv_b=_ptr(g[1]),
                                 g_lin_w=_ptr(g[2]), g_lin_b=_ptr(g[3]), g_local_w=_ptr(g[4]), g_local_b=_ptr(g[5]),
-                                g_gcond_w=_ptr(g[6]), g_global_free=_ptr(g[7]), d_pre=_ptr(d_pre))
+                                g_gcond_w=_ptr(g[6]), g_global_free=_ptr(g[7]), d_pre=_ptr(d_pre), dpool=_ptr(dpool))
         L.check(lib.vh_encoder_bwd(C.byref(ctx.desc), C.byref(io), C.byref(gr), C.c_void_p(torch.cuda.current_stream().cuda_stream)))
         return (None, None, None, None) + tuple(g)
 

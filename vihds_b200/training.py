@@ -235,6 +235,8 @@ class GraphedStep(object):
             self.q_mu, self.q_prec = z(B, P), z(B, P)
             self.enc_pooled = z(B, enc.conditional.lin.weight.shape[1])
             self.enc_feats, self.enc_dpre = z(B, enc.conditional.n_outputs), z(B, enc.conditional.n_outputs)
+            # large batches: workspace for the hidden layer's backward as GEMMs (cotangent of the pooled features)
+            self.enc_dpool = z(B, enc.conditional.lin.weight.shape[1]) if B >= 256 else None
         prior = m.prior_tables(dt)
         self.prob = ode.problem(enc.names, enc.kinds, prior, self.extras, dev, dt)
         S = self.prob.S
@@ -366,7 +368,8 @@ class GraphedStep(object):
             g = [p.grad for p in self.model.encoder.fused_parameters()]
             gr = L.vh_encoder_grads(d_q_mu=_ptr(self.buf.d_q_mu), d_q_prec=_ptr(self.buf.d_q_prec), g_conv_w=_ptr(g[0]),
                                     g_conv_b=_ptr(g[1]), g_lin_w=_ptr(g[2]), g_lin_b=_ptr(g[3]), g_local_w=_nz(g[4]),
-                                    g_local_b=_nz(g[5]), g_gcond_w=_nz(g[6]), g_global_free=_nz(g[7]), d_pre=_ptr(self.enc_dpre))
+                                    g_local_b=_nz(g[5]), g_gcond_w=_nz(g[6]), g_global_free=_nz(g[7]), d_pre=_ptr(self.enc_dpre),
+                                    dpool=_ptr(self.enc_dpool))
         # the cost guards the update ON THE DEVICE: a NaN cost (NaN gradients) must not reach the parameters or the Adam
         # moments before the host has looked at it (vihds/training.py:331-336 checks before optimizer.step())
         if gr is not None and self.pg is None and self.B <= 128 and os.environ.get("VIHDS_FUSE_ADAM", "1") != "0":
