@@ -331,3 +331,13 @@ class FlatAdam(object):
 
     def clear_skipped(self):
         self.step_dev[2] = 0
+
+    def state_snapshot(self):
+        """Copies of (parameters, first / second moments, step counters): what a checkpoint of the optimiser holds."""
+        return [t.clone() for t in (self.flat, self.exp_avg, self.exp_avg_sq, self.step_dev)]
+
+    def restore_state(self, snap):
+        """In-place restore of a ``state_snapshot`` (addresses captured in CUDA graphs stay valid); clears the gradient."""
+        for t, s in zip((self.flat, self.exp_avg, self.exp_avg_sq, self.step_dev), snap):
+            t.copy_(s)
+        self.grad.zero_()

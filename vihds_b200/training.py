@@ -214,11 +214,19 @@ class GraphedStep(object):
         for k, shape in (("inputs", (B, Cn)), ("dev_1hot", (B, Dn)), ("observations", (B, 4, T))):
             spans[k] = (off, off + int(np.prod(shape)), shape)
             off += int(np.prod(shape))
-        self._batch_dev, self._batch_spans = z(off), spans
-        self.batch = Settings(times=z(T), **{k: self._batch_dev[a:b].view(shape) for k, (a, b, shape) in spans.items()})
-        self.u = z(self.N, P)
+        self._batch_spans = spans
         self.extras = list(ode.conditioned) if m.decoder.condition_on_device else []
-        self.cond_w = z(max(1, len(self.extras)), Dn)
+        # TWO sets of input buffers (per-individual batch, u, conditioner weights): the end-to-end entry copies the next
+        # step's inputs into one set while the device still computes on the other (``step_from_host``); each set has its
+        # own pair of captured graphs.  ``step()`` and the ``load_*`` calls act on the selected set (set 0 unless
+        # ``step_from_host`` has been used).  The time grid belongs to the data set and is shared.
+        times = z(T)
+        self._slots = []
+        for _ in range(2):
+            bd = z(off)
+            self._slots.append(Settings(batch_dev=bd, u=z(self.N, P), cond_w=z(max(1, len(self.extras)), Dn),
+                                        batch=Settings(times=times, **{k: bd[a:b].view(shape) for k, (a, b, shape) in spans.items()})))
+        self._select(0)
         self.rel = [torch.as_tensor(np.asarray(ode.relevance[n])).to(device=dev, dtype=dt) for n in self.extras
                     if n in ode.relevance]
         if self.rel:
@@ -265,6 +273,25 @@ class GraphedStep(object):
         self.ready = False
         self.steps_done = 0
         self.ev_hot = None  # optional (start, end) CUDA events around the reverse-sweep kernel (forces the eager path)
+
+    def _select(self, slot):
+        """Make input set ``slot`` the one the ``load_*`` calls fill and ``step()`` computes on."""
+        sl = self._slots[slot]
+        self._slot = slot
+        self._batch_dev, self.batch, self.u, self.cond_w = sl.batch_dev, sl.batch, sl.u, sl.cond_w
+        for k, v in getattr(self, "_slot_attrs", {}).get(slot, {}).items():
+            setattr(self, k, v)
+
+    _PER_SLOT = ("q_mu", "q_prec", "extra", "extra_grad", "weights", "_enc_io", "_p", "_fio", "_bio", "_iwae_args", "_p_ref",
+                 "_fio_ref", "_bio_ref")
+
+    @property
+    def g_pre(self):
+        return self._graphs[self._slot][0]
+
+    @property
+    def g_rest(self):
+        return self._graphs[self._slot][1]
 
     # -- the three segments -------------------------------------------------------------------------------------
     def _pre(self):
@@ -417,15 +444,26 @@ class GraphedStep(object):
         # two graphs: everything up to the ODE kernels' inputs (the end-to-end entry slips the copy of u underneath it),
         # and the rest -- ODE forward, IWAE, reverse sweep, encoder backward, all-reduce, Adam.  With the hot launches
         # issued eagerly between two graphs the host needed ~155 us per step, as long as the device.
-        self.g_pre, self.g_rest = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.g_pre):
-            self._pre()
-        self._build_descriptors()
-        self.g_pre.replay()
-        with torch.cuda.graph(self.g_rest, pool=self.g_pre.pool()):
-            self._hot()
-            self._post()
-        torch.cuda.synchronize()
+        # One pair per input set (the kernel arguments hold the set's addresses).
+        self._graphs, self._slot_attrs, pool, keep = [None] * len(self._slots), {}, None, self._slot
+        for slot in sorted(range(len(self._slots)), key=lambda k: k == keep):  # the selected set last
+            self._select(slot)
+            if slot != keep:  # the capture passes compute on this set's buffers: give them the loaded set's contents
+                for k in ("batch_dev", "u", "cond_w"):
+                    self._slots[slot][k].copy_(self._slots[keep][k])
+            g_pre, g_rest = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_pre, pool=pool):
+                self._pre()
+            pool = g_pre.pool()
+            self._build_descriptors()
+            g_pre.replay()
+            with torch.cuda.graph(g_rest, pool=pool):
+                self._hot()
+                self._post()
+            self._graphs[slot] = (g_pre, g_rest)
+            # what the captured launches of this set read and wrote (graph-pool tensors, argument structs)
+            self._slot_attrs[slot] = {k: getattr(self, k, None) for k in self._PER_SLOT}
+            torch.cuda.synchronize()
         for t, s in zip((opt.flat, opt.exp_avg, opt.exp_avg_sq, opt.step_dev), snap):
             t.copy_(s)  # warm-up and capture passes must not count as training steps
         self.ready = True
@@ -449,9 +487,8 @@ class GraphedStep(object):
 
     def load_batch(self, batch, non_blocking=True):
         src = batch["times"]  # the time grid belongs to the data set: skip the copy while the same storage is handed in
-        tag = (src.data_ptr(), src._version, src.numel(), tuple(src.stride()))
-        if getattr(self, "_times_tag", None) != tag:
-            self._times_tag = tag
+        if self._times_differ(src):
+            self._times_tag = self._tag_of(src)
             self.batch.times.copy_(src, non_blocking=non_blocking)
         keys = ("inputs", "dev_1hot", "observations")
         if any(batch[k].is_cuda for k in keys):
@@ -471,6 +508,13 @@ class GraphedStep(object):
         self._h2d(self._batch_dev, self._bhost[sl])
         self._bev[sl].record()
         self._bslot = sl ^ 1
+
+    @staticmethod
+    def _tag_of(src):
+        return (src.data_ptr(), src._version, src.numel(), tuple(src.stride()))
+
+    def _times_differ(self, src):
+        return getattr(self, "_times_tag", None) != self._tag_of(src)
 
     def _h2d(self, dst, src):
         """Asynchronous copy of a contiguous (pinned) host tensor into a static device buffer on the current stream: one
@@ -531,34 +575,45 @@ class GraphedStep(object):
 
     def step_from_host(self, batch, u):
         """The public end-to-end step: ``batch`` (times, inputs, dev_1hot, observations) and ``u`` [B, IW, P] are HOST
-        tensors (pinned for asynchronous copies).  The small batch tensors and the conditioner weights go first, the
-        encoder graph is launched, and the 1 MB of ``u`` -- which only the ODE kernel needs -- travels on a copy stream
-        underneath it.  Returns the cost (device tensor, no sync)."""
+        tensors (pinned for asynchronous copies).  Returns the cost (device tensor, no sync; valid until the next step).
+
+        The inputs go into the input set the previous call did NOT use, on a copy stream: in a stream of calls the copies
+        of step i + 1 (1 MB of u at the icml size, 18 MB at the synthetic one) run while the device computes step i.
+        The small batch tensors and the conditioner weights go first and release the encoder graph; u -- which only the
+        ODE kernel needs -- releases the second graph."""
         self.prepare()
         cur = torch.cuda.current_stream()
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream()
-            self._u_ready, self._u_free = torch.cuda.Event(), torch.cuda.Event()
-            self._u_free.record(cur)
-        # the small copies first: host-to-device copies of all streams queue on one copy engine, and the encoder graph
-        # must not wait behind the big one (18 MB of u at the synthetic size)
-        self.load_batch(batch)
-        self.draw_conditioner()
+            n = len(self._slots)
+            self._in_ready = [torch.cuda.Event() for _ in range(n)]
+            self._u_ready = [torch.cuda.Event() for _ in range(n)]
+            self._set_free = [torch.cuda.Event() for _ in range(n)]
+            for e in self._set_free:
+                e.record(cur)  # whatever the caller queued on the compute stream so far (load_* / step()) comes first
+        slot = self._slot ^ 1
+        self._select(slot)
         with torch.cuda.stream(self._copy_stream):
-            self._copy_stream.wait_event(self._u_free)  # the previous step's reverse sweep still reads the old u
+            self._copy_stream.wait_event(self._set_free[slot])  # the step that last computed on this set has finished
+            if self._times_differ(batch["times"]):
+                self._copy_stream.wait_stream(cur)  # the (shared) time grid is about to change: nothing may still read it
+            self.load_batch(batch)
+            self.draw_conditioner()
+            self._in_ready[slot].record(self._copy_stream)
             self.load_u(u)
-            self._u_ready.record(self._copy_stream)
+            self._u_ready[slot].record(self._copy_stream)
+        cur.wait_event(self._in_ready[slot])
         if self.use_graphs:
             self.g_pre.replay()
-            cur.wait_event(self._u_ready)
+            cur.wait_event(self._u_ready[slot])
             self.g_rest.replay()
         else:
             self._pre()
             self._build_descriptors()
-            cur.wait_event(self._u_ready)
+            cur.wait_event(self._u_ready[slot])
             self._hot()
             self._post()
-        self._u_free.record(cur)
+        self._set_free[slot].record(cur)
         self.predraw_conditioner()
         self.steps_done += 1
         return self.buf.cost
@@ -574,5 +629,7 @@ class GraphedStep(object):
             self._build_descriptors()
             self._hot()
             self._post()
+        if hasattr(self, "_set_free"):  # step_from_host is in use as well: its copies must not overtake this step
+            self._set_free[self._slot].record()
         self.steps_done += 1
         return self.buf.cost
