@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define VH_ABI_VERSION 3
+#define VH_ABI_VERSION 4
 
 enum vh_status {
   VH_OK = 0,
@@ -154,6 +154,12 @@ typedef struct vh_bwd_io {
    * (B*IW <= 18,944, white-box models without a hidden-layer precision net); VH_ERR_UNSUPPORTED otherwise. */
   void* iwae_cost;               /* out [1] or NULL */
   int iwae_b_total;              /* 0: not fused */
+  /* non-zero: the caller zeroed d_q_mu, d_q_prec, d_weights and iwae_cost on this stream BEFORE the forward launch
+   * (vh_elbo_terms_fwd) of the same step.  The call then adds no memset between the two kernels, and the latency-form
+   * reverse kernel is launched with programmatic stream serialization: it becomes resident under the forward kernel's
+   * tail and starts the moment that grid has completed (VIHDS_PDL=0 turns the launch attribute off).  Honoured by the
+   * white-box models; the dr_blackbox launcher clears its outputs regardless. */
+  int outputs_cleared;
 } vh_bwd_io;
 
 int vh_abi_version(void);

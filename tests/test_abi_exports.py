@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert "vh_elbo_terms_fwd" in syms and "vh_elbo_terms_bwd" in syms and len(syms) >= 15
     for s in syms:
         assert hasattr(lib, s), "libvihds_b200.so does not export %s" % s
-    assert lib.vh_abi_version() == 3
+    assert lib.vh_abi_version() == 4
 
 
 def test_registry_helpers():

@@ -38,7 +38,8 @@ class vh_fwd_io(C.Structure):
 
 
 class vh_bwd_io(C.Structure):
-    _fields_ = [("fwd", vh_fwd_io)] + [(n, C.c_void_p) for n in _BWD_FIELDS] + [("iwae_cost", C.c_void_p), ("iwae_b_total", C.c_int)]
+    _fields_ = [("fwd", vh_fwd_io)] + [(n, C.c_void_p) for n in _BWD_FIELDS] + [("iwae_cost", C.c_void_p), ("iwae_b_total", C.c_int),
+                                                                                      ("outputs_cleared", C.c_int)]
 
 
 class vh_encoder_desc(C.Structure):
@@ -116,7 +117,7 @@ def load():
     lib.vh_encoder_bwd.argtypes = [C.POINTER(vh_encoder_desc), C.POINTER(vh_encoder_io), C.POINTER(vh_encoder_grads), C.c_void_p]
     lib.vh_encoder_bwd_adam.argtypes = ([C.POINTER(vh_encoder_desc), C.POINTER(vh_encoder_io), C.POINTER(vh_encoder_grads), C.c_size_t] +
                                         [C.c_void_p] * 8)
-    if lib.vh_abi_version() != 3:
+    if lib.vh_abi_version() != 4:
         raise RuntimeError("vihds_b200: ABI version mismatch")
     _lib = lib
     return lib

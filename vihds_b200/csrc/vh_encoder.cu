@@ -15,6 +15,7 @@
 
 #include "../../include/vihds_b200.h"
 #include "vh_math.cuh"
+#include "vh_pdl.cuh"
 
 namespace vh {
 void set_error(const char* fmt, ...);
@@ -167,6 +168,72 @@ static void enc_gemm(int M, int N, int K, const R* A, long long sam, long long s
 
 #define ENC_THREADS 512
 #define ENC_OPW 4
+// Hidden layer of the forward kernel: enc[g][o] = tanh(b[o] + sum_i W[o][i] pooled[g][i]).  Each warp owns outputs o0,
+// o0 + nw, ... and accumulates ENC_OPW of them for all G individuals per pass over the inputs; a lane takes 16 bytes of
+// consecutive inputs at a time (one 16-byte load per operand and four (two) multiply-adds -- as scalar loads the loop
+// spent ~12 instructions per multiply-add).  Rows that are not 16-byte aligned take the scalar loop.
+template <typename R, int G>
+__device__ __forceinline__ void enc_hidden_layer(const EncDims& d, const R* __restrict__ lin_w, const R* __restrict__ lin_b,
+                                                 const R* __restrict__ pooled, R* __restrict__ xloc, R* __restrict__ enc_out,
+                                                 int b0, int ngr, int warp, int lane, int nw) {
+  constexpr int V = 16 / sizeof(R);
+  struct alignas(16) Vec { R v[V]; };
+  const bool vec = d.NLIN % V == 0 && ((size_t)lin_w & 15) == 0 && ((size_t)pooled & 15) == 0;
+  for (int o0 = warp; o0 < d.H; o0 += nw * ENC_OPW) {
+    R acc[ENC_OPW][G];
+#pragma unroll
+    for (int q = 0; q < ENC_OPW; ++q)
+#pragma unroll
+      for (int g = 0; g < G; ++g) acc[q][g] = R(0);
+    if (vec) {
+      const int nv = d.NLIN / V;
+#pragma unroll 2
+      for (int i = lane; i < nv; i += 32) {
+        Vec x[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) x[g] = reinterpret_cast<const Vec*>(pooled + (size_t)g * d.NLIN)[i];
+#pragma unroll
+        for (int q = 0; q < ENC_OPW; ++q) {
+          const int o = min(o0 + q * nw, d.H - 1);  // surplus slots redo the last row (discarded below): no branch here
+          const Vec w = reinterpret_cast<const Vec*>(lin_w + (size_t)o * d.NLIN)[i];
+#pragma unroll
+          for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int e = 0; e < V; ++e) acc[q][g] += w.v[e] * x[g].v[e];
+        }
+      }
+    } else {
+#pragma unroll 2
+      for (int i = lane; i < d.NLIN; i += 32) {
+        R x[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) x[g] = pooled[(size_t)g * d.NLIN + i];
+#pragma unroll
+        for (int q = 0; q < ENC_OPW; ++q) {
+          const int o = o0 + q * nw;
+          if (o < d.H) {
+            const R w = lin_w[(size_t)o * d.NLIN + i];
+#pragma unroll
+            for (int g = 0; g < G; ++g) acc[q][g] += w * x[g];
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < ENC_OPW; ++q) {
+      const int o = o0 + q * nw;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const R a = warp_sum(acc[q][g]);
+        if (lane == 0 && o < d.H && g < ngr) {
+          const R e = vtanh(a + lin_b[o]);
+          xloc[g * d.nin_l + o] = e;
+          enc_out[(size_t)(b0 + g) * d.H + o] = e;
+        }
+      }
+    }
+  }
+}
 // G individuals per CTA: the hidden-layer weight matrix (H x NLIN, 1 MB at T = 500) is the only large operand and
 // every CTA streams all of it from L2; with G > 1 each weight is loaded once and used G times (large batches).
 template <typename R, int G>
@@ -174,7 +241,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, c
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* delta = reinterpret_cast<R*>(smem_raw);
   R* conv = delta + d.NS * d.L1;
-  R* pooled = conv + d.F * d.NCV;                 // [G][NLIN]
+  R* pooled = delta + up4(d.NS * d.L1 + d.F * d.NCV);  // [G][NLIN], 16-byte aligned (vector loads in the hidden layer)
   R* xloc = pooled + (size_t)G * d.NLIN;          // [G][nin_l]
   R* freev = xloc + G * d.nin_l;                  // [G][2*(nl+ng)]
   R* cw = freev + G * 2 * (d.nl + d.ng);          // conv weights [F][NS][K] + bias [F]
@@ -229,15 +296,26 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, c
       xloc[g * d.nin_l + d.H + i] =
           (d.lt && i < d.C) ? p.inputs[(size_t)b * d.C + i] : p.dev[(size_t)b * d.D + (i - (d.lt ? d.C : 0))];
     __syncthreads();
-    for (int i = tid; i < d.F * d.NCV; i += nt) {
-      const int f = i / d.NCV, j = i % d.NCV;
-      R a = cw[ncw + f];
+    // conv: a thread per (position j, pair of filters) -- every input sample is loaded once for two multiply-adds and
+    // the filter taps are warp-wide broadcasts
+    const int nfp = (d.F + 1) >> 1;
+    for (int i = tid; i < nfp * d.NCV; i += nt) {
+      const int fp = i / d.NCV, j = i - fp * d.NCV;
+      const int f0 = 2 * fp, f1 = min(f0 + 1, d.F - 1);
+      R a0 = cw[ncw + f0], a1 = cw[ncw + f1];
       for (int c = 0; c < d.NS; ++c) {
-        const R* w = cw + (f * d.NS + c) * d.K;
+        const R* w0 = cw + (f0 * d.NS + c) * d.K;
+        const R* w1 = cw + (f1 * d.NS + c) * d.K;
         const R* x = delta + c * d.L1 + j;
-        for (int k = 0; k < d.K; ++k) a += w[k] * x[k];
+#pragma unroll 5
+        for (int k = 0; k < d.K; ++k) {
+          const R xv = x[k];
+          a0 += w0[k] * xv;
+          a1 += w1[k] * xv;
+        }
       }
-      conv[i] = a;
+      conv[f0 * d.NCV + j] = a0;
+      if (f1 != f0) conv[f1 * d.NCV + j] = a1;
     }
     __syncthreads();
     for (int i = tid; i < d.NLIN; i += nt) {
@@ -252,41 +330,12 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, c
   if (d.stage) cp_async_commit_wait_all();
   __syncthreads();
   if (d.phase == 1) return;  // pooled features are in global memory: the hidden layer runs as a GEMM
-  // hidden layer: each warp owns outputs o0, o0 + nw, ... and accumulates ENC_OPW of them for all G individuals per
-  // pass over the inputs
-  for (int o0 = warp; o0 < d.H && d.phase == 0; o0 += nw * ENC_OPW) {
-    R acc[ENC_OPW][G];
-#pragma unroll
-    for (int q = 0; q < ENC_OPW; ++q)
-#pragma unroll
-      for (int g = 0; g < G; ++g) acc[q][g] = R(0);
-#pragma unroll 2
-    for (int i = lane; i < d.NLIN; i += 32) {
-      R x[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) x[g] = pooled[(size_t)g * d.NLIN + i];
-#pragma unroll
-      for (int q = 0; q < ENC_OPW; ++q) {
-        const int o = o0 + q * nw;
-        if (o < d.H) {
-          const R w = lin_w[(size_t)o * d.NLIN + i];
-#pragma unroll
-          for (int g = 0; g < G; ++g) acc[q][g] += w * x[g];
-        }
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < ENC_OPW; ++q) {
-      const int o = o0 + q * nw;
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const R a = warp_sum(acc[q][g]);
-        if (lane == 0 && o < d.H && g < ngr) {
-          const R e = vtanh(a + lin_b[o]);
-          xloc[g * d.nin_l + o] = e;
-          p.enc[(size_t)(b0 + g) * d.H + o] = e;
-        }
-      }
+  if (d.phase == 0) {
+    if (d.stage) {  // two call sites: the staged copy is read with shared-memory loads, not generic ones
+      R* st = delta + up4((int)(cw - delta) + ncw + d.F);
+      enc_hidden_layer<R, G>(d, st, st + up4(d.H * d.NLIN), pooled, xloc, p.enc, b0, ngr, warp, lane, nw);
+    } else {
+      enc_hidden_layer<R, G>(d, p.lin_w, p.lin_b, pooled, xloc, p.enc, b0, ngr, warp, lane, nw);
     }
   }
   __syncthreads();
@@ -342,6 +391,11 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const int b0 = blockIdx.x * G;
   const int ngr = min(G, d.B - b0);
+  // Launched with programmatic stream serialization (vh_pdl.cuh): the weight staging and the reads of this step's encoder
+  // forward outputs below run under the tail of the preceding launch (the reverse sweep that produces d_q_mu / d_q_prec);
+  // pdl_wait() stands in front of the first read of those.  The launch after this one (hidden-layer weight gradient +
+  // Adam) may become resident right away: it prefetches the optimiser state and waits for this grid.
+  pdl_trigger();
   // this CTA's filters: f = fy, fy + nfy, ...;  local filter index lf = f / nfy
   const int fy = blockIdx.y, nfy = gridDim.y;
   const int nfl = (d.F - fy + nfy - 1) / nfy;  // number of filters handled here
@@ -351,9 +405,19 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
   R* wl = delta + up4((int)(dpre - delta) + G * d.H);
   if (d.stage) {
     R* s_local_w = wl + up4(d.H * ncol);
-    for (int e = tid; e < d.H * ncol; e += nt) {
-      const int o = e / ncol, li = e % ncol;
-      cp_async_bytes(wl + e, p.lin_w + (size_t)o * d.NLIN + (fy + (li / d.NP) * nfy) * d.NP + li % d.NP, sizeof(R));
+    // per (output o, local filter lf) one contiguous run of NP weights: a warp per run, 16-byte copies when the runs are
+    // 16-byte aligned on both sides (as element-wise 4-byte copies with two divisions each this loop was 39 % of the
+    // kernel's instructions at the icml size)
+    {
+      constexpr int V = 16 / sizeof(R);
+      const bool v16 = d.NP % V == 0 && d.NLIN % V == 0 && ((size_t)p.lin_w & 15) == 0;
+      const int cpr = v16 ? d.NP / V : d.NP, step = v16 ? V : 1, bytes = v16 ? 16 : (int)sizeof(R);
+      for (int run = warp; run < d.H * nfl; run += nw) {
+        const int o = run / nfl, lf = run - o * nfl;
+        const R* src = p.lin_w + (size_t)o * d.NLIN + (fy + lf * nfy) * d.NP;
+        R* dst = wl + o * ncol + lf * d.NP;
+        for (int c = lane; c < cpr; c += 32) cp_async_bytes(dst + c * step, src + c * step, bytes);
+      }
     }
     stage_async(s_local_w, p.local_w, 2 * d.nl * d.nin_l, tid, nt);
     local_w = s_local_w;
@@ -374,6 +438,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
     }
     xloc[e] = v;
   }
+  pdl_wait();
   for (int e = tid; e < ngr * (ncond + d.nglob) && d.phase != 2; e += nt) {
     const int g = e / (ncond + d.nglob), k = e % (ncond + d.nglob), b = b0 + g;
     dfree[g * nfr + 2 * k] = p.d_q_mu[(size_t)b * d.P + k];
@@ -466,19 +531,29 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_bwd_kernel(const EncDims d, c
       dconv[f * d.NCV + j] = a * inv_pool;
     }
     __syncthreads();
-    // conv weight / bias gradients of this CTA's filters: one warp per weight, lanes over the NCV positions
+    // conv weight / bias gradients of this CTA's filters: four threads per weight, each a quarter of the NCV positions
+    // (a warp per weight spent 128 instructions per weight, most of them on the 5-level reduction of a 76-term sum)
     const int wpf = d.NS * d.K + 1;  // weights + bias per filter
-    for (int le = warp; le < nfl * wpf; le += nw) {
-      const int f = fy + (le / wpf) * nfy, r = le % wpf;
+    for (int le0 = 0; le0 < nfl * wpf; le0 += nt >> 2) {  // trip count uniform over the CTA (shuffles below)
+      const int le = le0 + (tid >> 2), q = tid & 3;
+      const bool on = le < nfl * wpf;
+      const int lf = on ? le / wpf : 0, r = on ? le - lf * wpf : 0, f = fy + lf * nfy;
+      const bool bias = r >= d.NS * d.K;
+      const int c = bias ? 0 : r / d.K, k = bias ? 0 : r - c * d.K;
+      const R* dc = dconv + f * d.NCV;
+      const R* dl = delta + c * d.L1 + k;
       R a = R(0);
-      if (r < d.NS * d.K) {
-        const int c = r / d.K, k = r % d.K;
-        for (int j = lane; j < d.NCV; j += 32) a += dconv[f * d.NCV + j] * delta[c * d.L1 + j + k];
-      } else {
-        for (int j = lane; j < d.NCV; j += 32) a += dconv[f * d.NCV + j];
+      if (on) {
+        if (bias) {
+          for (int j = q; j < d.NCV; j += 4) a += dc[j];
+        } else {
+#pragma unroll 4
+          for (int j = q; j < d.NCV; j += 4) a += dc[j] * dl[j];
+        }
       }
-      a = warp_sum(a);
-      if (lane == 0) atomicAdd(r < d.NS * d.K ? p.g_conv_w + f * d.NS * d.K + r : p.g_conv_b + f, a);
+      a += __shfl_xor_sync(0xffffffffu, a, 1);
+      a += __shfl_xor_sync(0xffffffffu, a, 2);
+      if (on && q == 0) atomicAdd(bias ? p.g_conv_b + f : p.g_conv_w + f * d.NS * d.K + r, a);
     }
   }
 }
@@ -608,6 +683,97 @@ __global__ void __launch_bounds__(256) enc_lin_wgrad_adam_kernel(const EncDims d
   }
 }
 
+// The same launch with 16 bytes of consecutive parameters per thread (4 fp32 / 2 fp64): used when the view of lin_w starts
+// on a 16-byte boundary of the flat vector and NLIN is a multiple of the vector width, so that a thread's parameters
+// share their row o and their pooled columns are one 16-byte load.  The optimiser state (parameter, gradient, both
+// moments) is fetched BEFORE the B-deep sum: its (cold, DRAM) round trip overlaps the sum's L2 round trips instead of
+// following them.
+template <typename R>
+__global__ void __launch_bounds__(64) enc_lin_wgrad_adam_vec_kernel(const EncDims d, const EncPtrs<R> p, size_t n, long long lin_off,
+                                                                    R* __restrict__ prm, R* __restrict__ g, R* __restrict__ m,
+                                                                    R* __restrict__ v, const double* __restrict__ hyper,
+                                                                    long long* step, const R* __restrict__ guard) {
+  constexpr int V = 16 / sizeof(R);
+  struct alignas(16) Vec { R v[V]; };
+  const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V;  // n is a multiple of V (checked by the launcher)
+  __shared__ R s_bc[2];
+  __shared__ int s_skip;
+  const bool on = i < n;
+  Vec pv = {}, gv = {}, mv = {}, vv = {};
+  if (on) {  // nobody writes these before this kernel does: fetched under the preceding launch's tail (vh_pdl.cuh)
+    pv = *reinterpret_cast<const Vec*>(prm + i);
+    mv = *reinterpret_cast<const Vec*>(m + i);
+    vv = *reinterpret_cast<const Vec*>(v + i);
+  }
+  pdl_wait();  // the gradient vector, d_pre and the guard come from the launches before
+  if (on) gv = *reinterpret_cast<const Vec*>(g + i);
+  if (threadIdx.x == 0) {
+    const double t = (double)(*(volatile long long*)step + 1);
+    s_bc[0] = (R)(1.0 - pow(hyper[1], t));
+    s_bc[1] = (R)sqrt(1.0 - pow(hyper[2], t));
+    const R c = guard ? *guard : R(0);
+    s_skip = (c != c) || (guard && *(volatile long long*)(step + 2) != 0);
+  }
+  __syncthreads();
+  const bool skip = s_skip != 0;
+  if (on) {
+    const long long e = (long long)i - lin_off;
+    if (!skip && e >= 0 && e < (long long)d.H * d.NLIN) {
+      const int o = (int)(e / d.NLIN), c = (int)(e - (long long)o * d.NLIN);
+      Vec a0 = {}, a1 = {};
+      const R* dp = p.d_pre + o;
+      const R* pl = p.pooled + c;
+      int b = 0;
+#pragma unroll 6
+      for (; b + 1 < d.B; b += 2) {
+        const R w0 = dp[(size_t)b * d.H], w1 = dp[(size_t)(b + 1) * d.H];
+        const Vec x0 = *reinterpret_cast<const Vec*>(pl + (size_t)b * d.NLIN);
+        const Vec x1 = *reinterpret_cast<const Vec*>(pl + (size_t)(b + 1) * d.NLIN);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          a0.v[k] += w0 * x0.v[k];
+          a1.v[k] += w1 * x1.v[k];
+        }
+      }
+      if (b < d.B) {
+        const R w0 = dp[(size_t)b * d.H];
+        const Vec x0 = *reinterpret_cast<const Vec*>(pl + (size_t)b * d.NLIN);
+#pragma unroll
+        for (int k = 0; k < V; ++k) a0.v[k] += w0 * x0.v[k];
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) gv.v[k] += a0.v[k] + a1.v[k];
+    }
+    if (!skip) {
+      const double lr = hyper[0], b1d = hyper[1], b2d = hyper[2];
+      const R b1 = (R)b1d, b2 = (R)b2d, eps = (R)hyper[3];
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        const R gi = gv.v[k];
+        const R mi = mv.v[k] + (gi - mv.v[k]) * (R(1) - b1);
+        const R vi = b2 * vv.v[k] + (R(1) - b2) * gi * gi;
+        mv.v[k] = mi;
+        vv.v[k] = vi;
+        const R denom = vsqrt(vi) / s_bc[1] + eps;
+        pv.v[k] -= ((R)lr / s_bc[0]) * (mi / denom);
+      }
+      *reinterpret_cast<Vec*>(m + i) = mv;
+      *reinterpret_cast<Vec*>(v + i) = vv;
+      *reinterpret_cast<Vec*>(prm + i) = pv;
+    }
+    *reinterpret_cast<Vec*>(g + i) = Vec{};
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd((unsigned long long*)(step + 1), 1ULL);
+    if (ticket == (unsigned long long)gridDim.x - 1) {
+      step[1] = 0;
+      step[skip ? 2 : 0] += 1;
+    }
+  }
+}
+
 // device conditioner (vihds/ode.py:43-58, :99-116) including the reference's repeat/reshape quirk: sample n = b*IW + i
 // of the GLOBAL batch receives the conditioner output of individual n % B_global.  A rank that holds the slab of
 // individuals [b_offset, b_offset + B) passes the global one-hot table, so the result does not depend on the rank count.
@@ -695,7 +861,7 @@ static void enc_bwd_g(const EncDims& d, const EncPtrs<R>& p, cudaStream_t s) {
   if (dd.stage) smem += staged;
   if (smem > 48 * 1024) cudaFuncSetAttribute(enc_bwd_kernel<R, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid((d.B + G - 1) / G, fsplit);
-  enc_bwd_kernel<R, G><<<grid, ENC_THREADS, smem, s>>>(dd, p);
+  launch_maybe_pdl(enc_bwd_kernel<R, G>, grid, dim3(ENC_THREADS), smem, s, true, dd, p);
 }
 // individuals per CTA: 1 while the batch does not fill the machine anyway, 4 for large batches (if it fits shared memory)
 template <typename R>
@@ -757,6 +923,15 @@ static int enc_bwd_t(const EncDims& d, const vh_encoder_io* io, const vh_encoder
   if (g && g->skip_lin_wgrad) return 0;  // formed inside the exchange launch (vh_adam_allreduce_step_wgrad)
   if (ad) {  // B <= 128 (checked by the caller): weight gradient of the hidden layer + Adam over the flat vector, one launch
     const long long lin_off = (long long)(p.g_lin_w - (R*)ad->grad);
+    constexpr int V = 16 / sizeof(R);
+    const size_t al = (size_t)ad->param | (size_t)ad->grad | (size_t)ad->exp_avg | (size_t)ad->exp_avg_sq | (size_t)p.pooled;
+    if (ad->n % V == 0 && lin_off % V == 0 && d.NLIN % V == 0 && (al & 15) == 0) {
+      const size_t nthr = ad->n / V;
+      launch_maybe_pdl(enc_lin_wgrad_adam_vec_kernel<R>, dim3((unsigned)((nthr + 63) / 64)), dim3(64), 0, s, true, d, p, ad->n,
+                       lin_off, (R*)ad->param, (R*)ad->grad, (R*)ad->exp_avg, (R*)ad->exp_avg_sq, (const double*)ad->hyper,
+                       (long long*)ad->step, (const R*)ad->guard);
+      return 0;
+    }
     enc_lin_wgrad_adam_kernel<R><<<(unsigned)((ad->n + 255) / 256), 256, 0, s>>>(
         d, p, ad->n, lin_off, (R*)ad->param, (R*)ad->grad, (R*)ad->exp_avg, (R*)ad->exp_avg_sq, (const double*)ad->hyper,
         (long long*)ad->step, (const R*)ad->guard);

@@ -10,6 +10,7 @@
 
 #include "vh_dispatch.cuh"
 #include "vh_lane.cuh"
+#include "vh_pdl.cuh"
 
 namespace vh {
 
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(FWD_TEAM * 32) elbo_fwd_team_kernel(const Call
   typedef typename M::real R;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* sm = reinterpret_cast<R*>(smem_raw);
+  pdl_trigger();  // the reverse launch may become resident now; it blocks in pdl_wait() until this grid has completed
   const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * 32 + lane;
   const bool active = n0 < a.N;
@@ -354,6 +356,8 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
   constexpr int S = M::S;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* ring = reinterpret_cast<R*>(smem_raw);
+  pdl_wait();     // launched under the forward kernel's tail (vh_bwd_io.outputs_cleared): everything below reads its outputs
+  pdl_trigger();  // the next launch on the stream (encoder backward) may stage its weights while this grid runs
   const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * 32 + lane;
   const bool active = n0 < a.N;
@@ -681,6 +685,7 @@ template <typename R>
 struct BwdLauncher {
   Call<R> a;
   cudaStream_t stream;
+  bool outputs_cleared = false;  // vh_bwd_io.outputs_cleared: no memset nodes; the latency-form kernel launches under the forward's tail
   // warp-specialised kernel: latency-bound launches (the 32-thread-CTA regime), every white-box model.
   // VIHDS_BWD_WS=0|1 overrides (tests / measurements; read per call).
   template <class M>
@@ -698,7 +703,7 @@ struct BwdLauncher {
                                        (size_t)((NetInfo<M>::NW + 3) & ~3) + 2 * (M::NIN + 8) * 32);
       if (ring > 48 * 1024)
         cudaFuncSetAttribute(elbo_bwd_ws_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
-      elbo_bwd_ws_kernel<M, TB><<<(a.N + 31) / 32, WS_WARPS * 32, ring, stream>>>(a);
+      launch_maybe_pdl(elbo_bwd_ws_kernel<M, TB>, dim3((a.N + 31) / 32), dim3(WS_WARPS * 32), ring, stream, outputs_cleared, a);
     } else {
       elbo_bwd_kernel<M, TB><<<grid, block, smem, stream>>>(a);
     }
@@ -724,8 +729,8 @@ struct BwdLauncher {
         return VH_ERR_CUDA;
       }
     }
-    bool cost_cleared = a.iw_b_total == 0;
-    if (a.d_q_mu && a.P > 0) {
+    bool cost_cleared = a.iw_b_total == 0 || outputs_cleared;
+    if (a.d_q_mu && a.P > 0 && !outputs_cleared) {
       const size_t nq = (size_t)a.B * a.P;
       if (a.d_q_prec == a.d_q_mu + nq) {  // adjacent tables (and the cost right behind them): one memset node
         const bool with_cost = !cost_cleared && a.iw_cost == a.d_q_mu + 2 * nq;
@@ -737,7 +742,7 @@ struct BwdLauncher {
       }
     }
     if (!cost_cleared) cudaMemsetAsync(a.iw_cost, 0, sizeof(R), stream);
-    if (NW > 0) cudaMemsetAsync(a.d_weights, 0, sizeof(R) * NW, stream);
+    if (NW > 0 && !outputs_cleared) cudaMemsetAsync(a.d_weights, 0, sizeof(R) * NW, stream);
     launch_bwd_variant<M, TB>(ws, grid, block, smem);
     e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -784,6 +789,7 @@ int launch_bwd_model(const vh_problem* p, const vh_bwd_io* io, cudaStream_t stre
     return VH_ERR_INVALID;
   }
   f.stream = stream;
+  f.outputs_cleared = io->outputs_cleared != 0;
   if (const char* err = set_precision_net<M>(p, f.a)) {
     set_error("%s", err);
     return VH_ERR_UNSUPPORTED;

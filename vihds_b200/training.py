@@ -258,6 +258,8 @@ class GraphedStep(object):
         # IWAE reduction inside the reverse launch where the latency-form kernel runs (one launch less per step)
         self.fuse_iwae = (os.environ.get("VIHDS_FUSE_IWAE", "1") != "0" and N <= 148 * 4 * 32 and ode.kernel_model != "dr_blackbox"
                           and not (self.prob.dynamic_precisions and self.prob.net.get("n_hidden", 0) > 0))
+        self.one_graph = os.environ.get("VIHDS_ONE_GRAPH", "1") != "0"
+        self.outputs_cleared = ode.kernel_model != "dr_blackbox"  # see _pre
         self.buf.cost_sum = z(1)  # NCCL path: sum of the ranks' costs (guard of the Adam update)
         self.d_weights = z(self.prob.n_weights) if self.prob.n_weights else None
         self.d_extra = z(len(self.extras), N) if (self.extras and hasattr(ode, "offset_layer")) else None
@@ -279,7 +281,12 @@ class GraphedStep(object):
         sl = self._slots[slot]
         self._slot = slot
         self._batch_dev, self.batch, self.u, self.cond_w = sl.batch_dev, sl.batch, sl.u, sl.cond_w
-        for k, v in getattr(self, "_slot_attrs", {}).get(slot, {}).items():
+        self._apply(slot, "split")
+
+    def _apply(self, slot, kind):
+        """Point the introspection attributes (q_mu, weights, argument structs ...) at what the captured launches of
+        (input set, graph kind) read and write; kind: "split" = g_pre + g_rest, "all" = the one-graph form."""
+        for k, v in getattr(self, "_slot_attrs", {}).get((slot, kind), {}).items():
             setattr(self, k, v)
 
     _PER_SLOT = ("q_mu", "q_prec", "extra", "extra_grad", "weights", "_enc_io", "_p", "_fio", "_bio", "_iwae_args", "_p_ref",
@@ -302,11 +309,18 @@ class GraphedStep(object):
         # the device conditioner does not depend on the encoder: it runs on a forked branch (a parallel node of the
         # captured graph) and joins before the ODE kernel
         fork = bool(self.extras) and getattr(self, "extras_override", None) is None and not hasattr(ode, "offset_layer")
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_side"):
+            self._side = torch.cuda.Stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            # outputs the reverse launch accumulates into, cleared HERE (a parallel branch of the captured graph) instead of
+            # by a memset node between the forward and the reverse kernel: vh_bwd_io.outputs_cleared
+            if self.outputs_cleared:
+                self.buf.d_q_cost.zero_()
+                if self.d_weights is not None:
+                    self.d_weights.zero_()
         if fork:
-            cur = torch.cuda.current_stream()
-            if not hasattr(self, "_side"):
-                self._side = torch.cuda.Stream()
-            self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
                 if not self._global_devices_loaded:
                     raise RuntimeError("sharded step with a device conditioner: call load_global_devices(dev_1hot of the "
@@ -335,10 +349,10 @@ class GraphedStep(object):
             self.extra = ode.conditioned_extras(self.B, self.IW, self.batch.dev_1hot)  # trainable: gradient flows back
             self.extra_grad = True
         elif self.extras:
-            cur.wait_stream(self._side)
             self.extra = self.extra_static
         else:
             self.extra = None
+        cur.wait_stream(self._side)
         w = ode.flat_weights()
         self.weights = w.contiguous() if w is not None else None
 
@@ -354,11 +368,13 @@ class GraphedStep(object):
             logq_theta=_ptr(b.lq))
         if self.fuse_iwae:
             self._bio = L.vh_bwd_io(fwd=self._fio, d_q_mu=_ptr(b.d_q_mu), d_q_prec=_ptr(b.d_q_prec), d_extra=_ptr(self.d_extra),
-                                    d_weights=_ptr(self.d_weights), iwae_cost=_ptr(b.cost), iwae_b_total=self.b_total)
+                                    d_weights=_ptr(self.d_weights), iwae_cost=_ptr(b.cost), iwae_b_total=self.b_total,
+                                    outputs_cleared=int(self.outputs_cleared))
         else:
             self._bio = L.vh_bwd_io(fwd=self._fio, g_logp_by_species=_ptr(b.g_lpx), g_logp_theta=_ptr(b.g_lp),
                                     g_logq_theta=_ptr(b.g_lq), d_q_mu=_ptr(b.d_q_mu), d_q_prec=_ptr(b.d_q_prec),
-                                    d_extra=_ptr(self.d_extra), d_weights=_ptr(self.d_weights))
+                                    d_extra=_ptr(self.d_extra), d_weights=_ptr(self.d_weights),
+                                    outputs_cleared=int(self.outputs_cleared))
         vdt = self.prob.vh_dtype
         self._iwae_args = (vdt, self.B, self.IW, self.b_total, _ptr(b.lpx), _ptr(b.lp), _ptr(b.lq), _ptr(b.cost),
                            _ptr(b.log_w), _ptr(b.w), _ptr(b.g_lpx), _ptr(b.g_lp), _ptr(b.g_lq))
@@ -460,10 +476,22 @@ class GraphedStep(object):
             with torch.cuda.graph(g_rest, pool=pool):
                 self._hot()
                 self._post()
-            self._graphs[slot] = (g_pre, g_rest)
             # what the captured launches of this set read and wrote (graph-pool tensors, argument structs)
-            self._slot_attrs[slot] = {k: getattr(self, k, None) for k in self._PER_SLOT}
+            self._slot_attrs[(slot, "split")] = {k: getattr(self, k, None) for k in self._PER_SLOT}
+            g_all = None
+            if self.one_graph:
+                # the whole step as ONE graph (``step()``, and ``step_from_host`` when the copy of u has already landed): no
+                # graph-to-graph boundary between the encoder forward and the ODE kernels
+                g_all = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_all, pool=pool):
+                    self._pre()
+                    self._build_descriptors()
+                    self._hot()
+                    self._post()
+                self._slot_attrs[(slot, "all")] = {k: getattr(self, k, None) for k in self._PER_SLOT}
+            self._graphs[slot] = (g_pre, g_rest, g_all)
             torch.cuda.synchronize()
+        self._apply(keep, "split")
         for t, s in zip((opt.flat, opt.exp_avg, opt.exp_avg_sq, opt.step_dev), snap):
             t.copy_(s)  # warm-up and capture passes must not count as training steps
         self.ready = True
@@ -603,7 +631,13 @@ class GraphedStep(object):
             self.load_u(u)
             self._u_ready[slot].record(self._copy_stream)
         cur.wait_event(self._in_ready[slot])
-        if self.use_graphs:
+        if self.use_graphs and self._graphs[slot][2] is not None and not self._set_free[slot ^ 1].query():
+            # a stream of steps (the previous one is still running): this step's copies run under it -- the one-graph form
+            cur.wait_event(self._u_ready[slot])
+            self._apply(slot, "all")
+            self._graphs[slot][2].replay()
+        elif self.use_graphs:  # the device is idle: start the encoder while u is still on its way
+            self._apply(slot, "split")
             self.g_pre.replay()
             cur.wait_event(self._u_ready[slot])
             self.g_rest.replay()
@@ -622,8 +656,13 @@ class GraphedStep(object):
         """One step on whatever the static buffers hold.  Returns the cost (device tensor, no sync)."""
         self.prepare()
         if self.use_graphs and self.ev_hot is None:
-            self.g_pre.replay()
-            self.g_rest.replay()
+            g_all = self._graphs[self._slot][2]
+            if g_all is not None:
+                self._apply(self._slot, "all")
+                g_all.replay()
+            else:
+                self.g_pre.replay()
+                self.g_rest.replay()
         else:  # no graphs, or instrumented (events around the reverse-sweep launch): the same calls, issued eagerly
             self._pre()
             self._build_descriptors()
