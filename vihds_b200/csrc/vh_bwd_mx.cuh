@@ -1,0 +1,407 @@
+// Matrix form of the latency-bound reverse sweep (double-receiver family with constant precisions, midpoint rule):
+// the launch `elbo_bwd_mx_kernel`.  Included by vh_launch.cuh (uses its rings, prologue and epilogue helpers).
+//
+// What bounds the reverse launch at the icml size (7,200 trajectories = 225 warps on 592 schedulers) is the time ONE warp
+// needs per time step for the part that is serial in the adjoint state lambda: in elbo_bwd_ws_kernel the consumer warp
+// issues ~300 instructions per step at IPC 0.37 (`wait` = fixed-latency dependency stalls: a single warp, in order) --
+// 855 cycles per step, 37 of the launch's 62 us (profiles/r02_ws_bwd_icml_*).  Taking instructions that merely accumulate
+// away from it changes nothing (measured: VH_WS_SPLIT), only a shorter dependent chain does.
+//
+// The step adjoint is LINEAR in lambda.  For the midpoint rule x1 = x0 + h f(x0 + h/2 f(x0)):
+//     lambda0 = (I + h A + h^2/2 A B)^T lambda1 + e,      A = df/dx at the mid-point state, B = df/dx at x0,
+// e = the emission (log-likelihood) cotangent at t0.  A, B and e depend on the checkpoint x0 only -- not on lambda -- so the
+// whole matrix N = I + h A + h^2/2 A B is formed AHEAD of the recurrence by producer warps (independent per time step:
+// several of them, round-robin), and the recurrence itself shrinks to one sparse 8 x 8 matrix-vector product: 20
+// multiply-adds, dependent depth 5.  The Jacobian of models/dr_constant.py:77-112 has 20 non-zeros (diagonal; column 0
+// through the growth rate gamma(x0); rows yfp / cfp x columns luxR / lasR through the promoter activities) and the
+// pattern is closed under the product, so N has the same 20.
+//
+// The parameter cotangents (23 accumulators: they need the stage VJPs with the actual lambda) only ACCUMULATE; accumulator
+// warps run the unchanged rk_step_adjoint on (x0, stages, kept intermediates) from the producers' ring and lambda1 from the
+// consumer's ring, one step each, round-robin, and discard its lambda output.
+//
+//   warps 0 .. NP-1     producers     checkpoint (cp.async ring) -> stages, kept intermediates, A, B, N, e, d prec
+//   warp  NP            consumer      lambda <- N^T lambda + e; publishes every lambda1
+//   warps NP+1 ..       accumulators  d constants
+// Rings: [slot][item][lane] in shared memory, one mbarrier pair (full / empty) per slot.
+#pragma once
+
+namespace vh {
+
+#ifndef VH_MX_NP
+#define VH_MX_NP 3
+#endif
+#ifndef VH_MX_NA
+#define VH_MX_NA 2
+#endif
+constexpr int MX_NP = VH_MX_NP, MX_NA = VH_MX_NA;
+constexpr int MX_WARPS = MX_NP + 1 + MX_NA;
+constexpr int MX_D1 = 2 * MX_NP;  // slots of the producers' ring
+constexpr int MX_DL = 2 * MX_NA;  // slots of the consumer's lambda ring
+
+template <class M, class TB>
+struct MxOk {
+  static constexpr bool value = false;
+};
+template <int VER>
+struct MxOk<DrModel<float, VER, 0, false>, TabMidpoint<float>> {  // fp32: the fp64 build needs 247 registers x 192 threads
+  static constexpr bool value = true;
+};
+
+// ---- mbarrier (shared memory, CTA scope) ----------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+// one arrival for the whole warp: every lane's shared-memory writes are ordered before it
+__device__ __forceinline__ void mbar_arrive_warp(unsigned long long* b, int lane) {
+  __syncwarp();
+  if (lane == 0) {
+    unsigned long long state;
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 %0, [%1];"
+                 : "=l"(state)
+                 : "r"((unsigned)__cvta_generic_to_shared(b))
+                 : "memory");
+    (void)state;
+  }
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(b);
+  unsigned done;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// ---- Jacobian of the species right-hand side (DrModel, no extension) at state X with intermediates m -------------------
+template <typename R>
+struct DrJac {
+  R j00;          // d f0 / d x0
+  R c0[8];        // d f_i / d x0, i = 1..7
+  R dg[8];        // d f_i / d x_i, i = 1..7
+  R j26, j27, j36, j37;
+};
+template <class M>
+__device__ __forceinline__ void dr_jacobian(const typename M::real* X, const typename M::Consts& c, const typename M::Mid& m,
+                                            DrJac<typename M::real>& J) {
+  typedef typename M::real R;
+  const R* v = c.v;
+  const R dgam = -(m.gr * c.iK);  // d gamma / d x0
+  J.j00 = m.gam + X[0] * dgam;
+#pragma unroll
+  for (int i = 1; i < 8; ++i) J.c0[i] = -(X[i] * dgam);
+  J.dg[1] = -(m.gam + v[C_drfp]);
+  J.dg[2] = -(m.gam + v[C_dyfp]);
+  J.dg[3] = -(m.gam + v[C_dcfp]);
+  J.dg[4] = -m.gam;
+  J.dg[5] = -m.gam;
+  J.dg[6] = -(m.gam + v[C_dR]);
+  J.dg[7] = -(m.gam + v[C_dS]);
+  // promoter activities P = (e + a + b) / (1 + a + b), a = KGR x6^2 fR, b = KGS x7^2 fS:  dP/da = (1 - P) / (1 + a + b)
+  const R q81 = v[C_cY] * ((R(1) - m.P81) * m.i81), q76 = v[C_cC] * ((R(1) - m.P76) * m.i76);
+  const R s6 = R(2) * X[6] * v[C_fR], s7 = R(2) * X[7] * v[C_fS];
+  J.j26 = q81 * v[C_KGR81] * s6;
+  J.j27 = q81 * v[C_KGS81] * s7;
+  J.j36 = q76 * v[C_KGR76] * s6;
+  J.j37 = q76 * v[C_KGS76] * s7;
+}
+
+// the 20 + 4 numbers a step hands to the recurrence; order = ring item order
+enum {
+  MXN_00 = 0,   // N_00
+  MXN_C0 = 0,   // N_i0 at MXN_C0 + i, i = 1..7
+  MXN_DG = 7,   // N_ii at MXN_DG + i, i = 1..7
+  MXN_26 = 15, MXN_27 = 16, MXN_36 = 17, MXN_37 = 18,
+  MXN_E = 19,   // emission cotangent: e0, e1, e2 (= e4), e3 (= e5)
+  MXN_ITEMS = 23
+};
+
+template <class M, class TB>
+struct MxRing {
+  typedef typename M::real R;
+  typedef WsRing<M, TB> Inner;                             // x0, stage derivatives, kept intermediates: the accumulators' share
+  static constexpr int SLOT = (MXN_ITEMS + Inner::NITEM) * 32;  // elements
+};
+
+template <class M, class TB>
+__global__ void __launch_bounds__(MX_WARPS * 32) elbo_bwd_mx_kernel(const Call<typename M::real> a) {
+  typedef typename M::real R;
+  typedef WsRing<M, TB> Ring;
+  typedef MxRing<M, TB> MR;
+  constexpr int S = M::S;
+  static_assert(S == 8 && !M::DYN, "matrix-form reverse kernel: dr_constant family");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw);
+  unsigned long long* full1 = bars;                    // [MX_D1] producers -> consumer + accumulator
+  unsigned long long* empty1 = bars + MX_D1;           // [MX_D1]
+  unsigned long long* fullL = bars + 2 * MX_D1;        // [MX_DL] consumer -> accumulator
+  unsigned long long* emptyL = bars + 2 * MX_D1 + MX_DL;
+  R* ring = reinterpret_cast<R*>(smem_raw + 8 * (2 * MX_D1 + 2 * MX_DL + 2));
+  pdl_wait();     // see elbo_bwd_ws_kernel
+  pdl_trigger();
+  const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * 32 + lane;
+  const bool active = n0 < a.N;
+  const int n = active ? n0 : a.N - 1;
+  const int b = n / a.IW;
+  const size_t N = a.N;
+  const int T = a.T;
+  R* lring = ring + MX_D1 * MR::SLOT;                                 // [MX_DL][S][32]
+  R* slots = lring + MX_DL * S * 32;                                  // theta by slot | its cotangent: [NSLOT][64]
+  const SlotScratch<R> thv{slots + lane, 64};
+  const SlotScratch<R> gloc{slots + 32 + lane, 64};
+  R* ckbase = slots + M::NSLOT * 64;                                  // [MX_NP][WS_PF + 1][S][32]
+  R* gcsm = ckbase + MX_NP * (WS_PF + 1) * S * 32;                    // [MX_NA][NC][32]
+  R* gpsm = gcsm + MX_NA * M::NC * 32;                                // [MX_NP][4][32]
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MX_D1; ++i) {
+      mbar_init(full1 + i, 1);
+      mbar_init(empty1 + i, 2);  // the consumer and the accumulator of that step
+    }
+    for (int i = 0; i < MX_DL; ++i) {
+      mbar_init(fullL + i, 1);
+      mbar_init(emptyL + i, 1);
+    }
+  }
+  // upstream gradients (fused IWAE or handed in) and theta, as elbo_bwd_ws_kernel
+  const bool iwae = a.iw_b_total > 0;
+  const R gup = iwae ? iwae_upstream_in_kernel(a, n, active, ring) : R(0);
+  const R glq = iwae ? -gup : ((a.g_logq_theta && active) ? a.g_logq_theta[n] : R(0));
+  const R glp = iwae ? gup : ((a.g_logp_theta && active) ? a.g_logp_theta[n] : R(0));
+  for (int s = role; s < M::NSLOT; s += MX_WARPS) {
+    const int src = a.slot_src[s];
+    if (src < 0) thv[s] = src != VH_SLOT_UNUSED ? a.extra[(size_t)(-1 - src) * N + n] : R(0);
+  }
+#pragma unroll 3
+  for (int k = role; k < a.P; k += MX_WARPS) {
+    R lq = R(0), lp = R(0);
+    const R v = a.theta_in ? a.theta_in[(size_t)k * N + n] : sample_column(a, n, b, k, lq, lp, false);
+    const int s = a.col_slot[k];
+    if (s >= 0) thv[s] = v;
+  }
+  __syncthreads();  // theta complete, barriers initialised
+  Rhs<M> f;
+  f.w = nullptr;
+  f.nh = 0;
+  R prec[4], gl[4];
+  {
+    R th[M::NSLOT];
+    R tc[3];
+#pragma unroll
+    for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? thv[s] : R(0);
+    M::treatments(a.treatments + (size_t)b * a.C, tc);
+    M::setup(th, tc, f.c);
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      prec[o] = th[S_prec_x + o];
+      gl[o] = iwae ? gup : ((a.g_logp_species && active) ? a.g_logp_species[(size_t)n * 4 + o] : R(0));
+    }
+  }
+  const size_t slab = (size_t)S * N;
+  const R* obs = a.obs + (size_t)b * 4 * T;
+  const int nit = T - 1;  // time steps; iteration it handles step k = T - 2 - it
+  // emission cotangent at state x against the observations of time index k: e[0..3] (cotangent of x0, x1, x2 = x4, x3 = x5)
+  // and the precision cotangents; vihds/ode.py:84-93 + the Gaussian log-likelihood (training.py:150-160)
+  auto emission = [&](const R* x, int k, R* e, R* gprec) {
+    R xp[4];
+    M::observe(x, xp);
+    R gxp[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const R d = xp[o] - obs[o * T + k];
+      gxp[o] = -(gl[o] * prec[o] * d);
+      gprec[o] += gl[o] * R(0.5) * (vdiv(R(1), prec[o]) - d * d);
+    }
+    e[0] = gxp[0] + gxp[1] * x[1] + gxp[2] * (x[2] + x[4]) + gxp[3] * (x[3] + x[5]);
+    e[1] = gxp[1] * x[0];
+    e[2] = gxp[2] * x[0];
+    e[3] = gxp[3] * x[0];
+  };
+  if (role < MX_NP) {
+    // ---------------- producers ----------------
+    R* ck = ckbase + role * (WS_PF + 1) * S * 32 + lane;
+    R gprec[4] = {R(0), R(0), R(0), R(0)};
+    int itw = role, sw = 0, sr = 0;  // iteration of the next checkpoint copy, staging slots of the next copy / read
+    auto issue = [&]() {
+      if (itw < nit) {
+        const R* xs = a.x_states + (size_t)(T - 2 - itw) * slab + n;
+#pragma unroll
+        for (int q = 0; q < S; ++q) cp_async_elem(ck + (sw * S + q) * 32, xs + (size_t)q * N);
+      }
+      cp_async_commit();
+      itw += MX_NP;
+      sw = sw == WS_PF ? 0 : sw + 1;
+    };
+#pragma unroll
+    for (int d = 0; d < WS_PF; ++d) issue();
+    for (int it = role; it < nit; it += MX_NP) {
+      const int k = T - 2 - it, slot = it % MX_D1, use = it / MX_D1;
+      issue();
+      const R t0 = a.times[k], t1 = a.times[k + 1];
+      const R h = t1 - t0;
+      cp_async_wait<WS_PF>();
+      R x[S];
+#pragma unroll
+      for (int q = 0; q < S; ++q) x[q] = ck[(sr * S + q) * 32];
+      sr = sr == WS_PF ? 0 : sr + 1;
+      typename Ring::SD sd;
+      rk_stages_forward<Rhs<M>, TB>(f, t0, t1, h, x, sd);
+      R Xm[S];
+#pragma unroll
+      for (int q = 0; q < S; ++q) Xm[q] = x[q] + (h * TB::a(1, 0)) * sd.k[0][q];
+      DrJac<R> A, B;
+      dr_jacobian<M>(Xm, f.c, sd.kept[1].m, A);
+      dr_jacobian<M>(x, f.c, sd.kept[0].m, B);
+      // N = I + h A + h^2/2 A B on the common sparsity pattern
+      const R hh = h * h * TB::a(1, 0);
+      R Nv[MXN_ITEMS];
+      Nv[MXN_00] = R(1) + h * A.j00 + hh * (A.j00 * B.j00);
+#pragma unroll
+      for (int i = 1; i < 8; ++i) {
+        R ab = A.c0[i] * B.j00 + A.dg[i] * B.c0[i];
+        if (i == 2) ab += A.j26 * B.c0[6] + A.j27 * B.c0[7];
+        if (i == 3) ab += A.j36 * B.c0[6] + A.j37 * B.c0[7];
+        Nv[MXN_C0 + i] = h * A.c0[i] + hh * ab;
+        Nv[MXN_DG + i] = R(1) + h * A.dg[i] + hh * (A.dg[i] * B.dg[i]);
+      }
+      Nv[MXN_26] = h * A.j26 + hh * (A.dg[2] * B.j26 + A.j26 * B.dg[6]);
+      Nv[MXN_27] = h * A.j27 + hh * (A.dg[2] * B.j27 + A.j27 * B.dg[7]);
+      Nv[MXN_36] = h * A.j36 + hh * (A.dg[3] * B.j36 + A.j36 * B.dg[6]);
+      Nv[MXN_37] = h * A.j37 + hh * (A.dg[3] * B.j37 + A.j37 * B.dg[7]);
+      emission(x, k, Nv + MXN_E, gprec);
+      if (use > 0) mbar_wait(empty1 + slot, (use - 1) & 1);  // both readers have released the slot
+      R* sl = ring + slot * MR::SLOT + lane;
+#pragma unroll
+      for (int i = 0; i < MXN_ITEMS; ++i) sl[i * 32] = Nv[i];
+      Ring::put(ring + slot * MR::SLOT + MXN_ITEMS * 32, lane, x, sd);
+      mbar_arrive_warp(full1 + slot, lane);
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) gpsm[(role * 4 + o) * 32 + lane] = gprec[o];
+  } else if (role == MX_NP) {
+    // ---------------- consumer: lambda <- N^T lambda + e ----------------
+    R lam[S];
+    R gprec[4] = {R(0), R(0), R(0), R(0)};
+    {
+      R x[S], e[4];
+#pragma unroll
+      for (int q = 0; q < S; ++q) x[q] = a.x_states[(size_t)(T - 1) * slab + (size_t)q * N + n];
+      emission(x, T - 1, e, gprec);
+      lam[0] = e[0]; lam[1] = e[1]; lam[2] = e[2]; lam[3] = e[3]; lam[4] = e[2]; lam[5] = e[3];
+      lam[6] = R(0); lam[7] = R(0);
+    }
+    for (int it = 0; it < nit; ++it) {
+      const int slot = it % MX_D1, use = it / MX_D1;
+      const int ls = it % MX_DL, luse = it / MX_DL;
+      // lambda1 of this step for its accumulator
+      if (luse > 0) mbar_wait(emptyL + ls, (luse - 1) & 1);
+#pragma unroll
+      for (int q = 0; q < S; ++q) lring[(ls * S + q) * 32 + lane] = lam[q];
+      mbar_arrive_warp(fullL + ls, lane);
+      mbar_wait(full1 + slot, use & 1);
+      R Nv[MXN_ITEMS];
+      const R* sl = ring + slot * MR::SLOT + lane;
+#pragma unroll
+      for (int i = 0; i < MXN_ITEMS; ++i) Nv[i] = sl[i * 32];
+      mbar_arrive_warp(empty1 + slot, lane);
+      // column 0 gathers all eight components (pairwise: depth 4), the others one or three
+      const R s01 = Nv[MXN_00] * lam[0] + Nv[MXN_C0 + 1] * lam[1];
+      const R s23 = Nv[MXN_C0 + 2] * lam[2] + Nv[MXN_C0 + 3] * lam[3];
+      const R s45 = Nv[MXN_C0 + 4] * lam[4] + Nv[MXN_C0 + 5] * lam[5];
+      const R s67 = Nv[MXN_C0 + 6] * lam[6] + Nv[MXN_C0 + 7] * lam[7];
+      const R l6 = Nv[MXN_DG + 6] * lam[6] + (Nv[MXN_26] * lam[2] + Nv[MXN_36] * lam[3]);
+      const R l7 = Nv[MXN_DG + 7] * lam[7] + (Nv[MXN_27] * lam[2] + Nv[MXN_37] * lam[3]);
+      lam[0] = ((s01 + s23) + (s45 + s67)) + Nv[MXN_E + 0];
+      lam[1] = Nv[MXN_DG + 1] * lam[1] + Nv[MXN_E + 1];
+      lam[2] = Nv[MXN_DG + 2] * lam[2] + Nv[MXN_E + 2];
+      lam[3] = Nv[MXN_DG + 3] * lam[3] + Nv[MXN_E + 3];
+      lam[4] = Nv[MXN_DG + 4] * lam[4] + Nv[MXN_E + 2];
+      lam[5] = Nv[MXN_DG + 5] * lam[5] + Nv[MXN_E + 3];
+      lam[6] = l6;
+      lam[7] = l7;
+    }
+    // chain rule back to theta (as elbo_bwd_ws_kernel); the constants' cotangents come from the accumulators
+    named_bar_sync_n<MX_WARPS * 32>(1);  // producers' d prec and accumulators' d constants are in shared memory
+    typename M::Consts gc;
+#pragma unroll
+    for (int i = 0; i < M::NC; ++i) {
+      R v = R(0);
+#pragma unroll
+      for (int q = 0; q < MX_NA; ++q) v += gcsm[(q * M::NC + i) * 32 + lane];
+      gc.v[i] = v;
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int p = 0; p < MX_NP; ++p) gprec[o] += gpsm[(p * 4 + o) * 32 + lane];
+    R gth[M::NSLOT];
+#pragma unroll
+    for (int s = 0; s < M::NSLOT; ++s) gth[s] = R(0);
+    {
+      R th[M::NSLOT];
+      R tc[3];
+#pragma unroll
+      for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? thv[s] : R(0);
+      M::treatments(a.treatments + (size_t)b * a.C, tc);
+      M::init_state_vjp(lam, gth);
+      M::setup_vjp(th, tc, f.c, gc, gth);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gprec[o];
+    }
+#pragma unroll
+    for (int s = 0; s < M::NSLOT; ++s) gloc[s] = M::uses(s) ? gth[s] : R(0);
+  } else {
+    // ---------------- accumulators: parameter cotangents of the stage VJPs ----------------
+    const int q = role - MX_NP - 1;
+    typename M::Consts gc;
+#pragma unroll
+    for (int i = 0; i < M::NC; ++i) gc.v[i] = R(0);
+    NoGW<R> nogw;
+    for (int it = q; it < nit; it += MX_NA) {
+      const int k = T - 2 - it, slot = it % MX_D1, use = it / MX_D1;
+      const int ls = it % MX_DL, luse = it / MX_DL;
+      const R t0 = a.times[k], t1 = a.times[k + 1];
+      R x[S], lam[S];
+      typename Ring::SD sd;
+      mbar_wait(full1 + slot, use & 1);
+      Ring::get(ring + slot * MR::SLOT + MXN_ITEMS * 32, lane, x, sd);
+      mbar_arrive_warp(empty1 + slot, lane);
+      mbar_wait(fullL + ls, luse & 1);
+#pragma unroll
+      for (int j = 0; j < S; ++j) lam[j] = lring[(ls * S + j) * 32 + lane];
+      mbar_arrive_warp(emptyL + ls, lane);
+      rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, t1 - t0, x, sd, lam, gc, nogw);  // its lambda output is not used
+    }
+#pragma unroll
+    for (int i = 0; i < M::NC; ++i) gcsm[(q * M::NC + i) * 32 + lane] = gc.v[i];
+  }
+  if (role != MX_NP) named_bar_sync_n<MX_WARPS * 32>(1);
+  __syncthreads();  // gloc complete
+  WarpSegRed<R> red(a.d_q_mu, a.d_q_prec, a.P, b, active);
+#pragma unroll 3
+  for (int k = role; k < a.P; k += MX_WARPS) {
+    const int s = a.col_slot[k];
+    R dmu = R(0), dprec = R(0);
+    if (active) column_vjp(a, n, b, k, s >= 0 ? gloc[s] : R(0), glq, glp, dmu, dprec);
+    red(b, k, dmu, dprec, active);
+  }
+  if (a.d_extra && active) {
+    for (int s = role; s < M::NSLOT; s += MX_WARPS) {
+      const int src = a.slot_src[s];
+      if (src < 0 && src != VH_SLOT_UNUSED) a.d_extra[(size_t)(-1 - src) * N + n] = gloc[s];
+    }
+  }
+}
+
+template <class M, class TB>
+inline size_t mx_smem_bytes() {
+  typedef typename M::real R;
+  return 8 * (2 * MX_D1 + 2 * MX_DL + 2) +
+         sizeof(R) * ((size_t)MX_D1 * MxRing<M, TB>::SLOT + (size_t)MX_DL * M::S * 32 + (size_t)M::NSLOT * 64 +
+                      (size_t)MX_NP * (WS_PF + 1) * M::S * 32 + (size_t)MX_NA * M::NC * 32 + (size_t)MX_NP * 4 * 32);
+}
+
+}  // namespace vh

@@ -12,6 +12,12 @@
 #include "vh_lane.cuh"
 #include "vh_pdl.cuh"
 
+// 1: accumulator warp in elbo_bwd_ws_kernel for the constant-precision models (measured: 65 us instead of 62 us at the icml
+// size -- the instructions taken off the consumer warp were filling its dependency stalls; kept for the record, off)
+#ifndef VH_WS_SPLIT
+#define VH_WS_SPLIT 0
+#endif
+
 namespace vh {
 
 void set_error(const char* fmt, ...);
@@ -205,6 +211,10 @@ __global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+template <int NT>
+__device__ __forceinline__ void named_bar_sync_n(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
+template <int NT>
+__device__ __forceinline__ void named_bar_arrive_n(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
 
 template <class M, class TB>
 struct WsRing {
@@ -243,6 +253,12 @@ struct WsRing {
       for (int j = 0; j < KN; ++j) m[j] = slot[(it++) * 32 + lane];
     }
   }
+};
+
+// models whose reverse step is split over a consumer and an accumulator warp (see elbo_bwd_ws_kernel)
+template <class M>
+struct WsSplit {
+  static constexpr bool value = !M::DYN && VH_WS_SPLIT;
 };
 
 // WS_WARPS warps per CTA share one group of 32 trajectories: warp 0 = producer, warp 1 = consumer, the others sleep on
@@ -373,6 +389,17 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
   typedef WgradRing<R, M::NIN> WG;
   R* wsm = ring + 2 * Ring::SLOT + M::NSLOT * 64 + (WS_PF + 1) * S * 32;
   R* wgbuf = wsm + ((NW + 3) & ~3);
+  // Constant-precision models: the parameter cotangents (23 accumulators for dr_constant, ~50 of the consumer's ~360
+  // instructions per step and VJP) only ACCUMULATE -- they are not part of the recurrence in lambda.  A third warp (the
+  // "accumulator", otherwise asleep until the epilogue) reads the same ring slots as the consumer, takes the cotangents
+  // of the stage derivatives from the consumer through a second two-slot ring, and keeps those accumulators; the
+  // consumer's step shrinks to the state cotangents (rk_step_adjoint_x / rk_step_adjoint_c, vh_traj.cuh).
+  constexpr bool SPLIT = WsSplit<M>::value;
+  constexpr int RD = SPLIT ? 96 : 64;                 // threads on the full / empty barriers of the main ring
+  constexpr int GN = TB::s * S;                       // items per slot of the consumer -> accumulator ring
+  R* gring = wgbuf + 2 * (M::NIN + 8) * 32;           // [2][GN][32]
+  R* gcsm = gring + 2 * GN * 32;                      // [NC][32]: the accumulator's result, read by the consumer's epilogue
+  enum { G_FULL0 = 7, G_EMPTY0 = 9, GC_READY = 11 };  // ids 7..10 are the weight-gradient ring's in the DYN kernels
   if (M::DYN) {
     for (int i = threadIdx.x; i < NW; i += blockDim.x) wsm[i] = a.weights[i];
   }
@@ -395,8 +422,8 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
     if (s >= 0) thv[s] = v;
   }
   named_bar_sync_all(PROLOGUE);
-  if (role < 2) {
-    // both roles need the RHS constants
+  if (role < 2 || (SPLIT && role == 2)) {
+    // every role of the recurrence needs the RHS constants
     Rhs<M> f;
     f.w = M::DYN ? wsm : nullptr;
     f.nh = 0;  // the warp-specialised form keeps the no-hidden-layer net only (its weight-gradient warp is sized for it)
@@ -450,14 +477,14 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
         const R tp = ld_early(a.times + kp);
         typename Ring::SD sd;
         rk_stages_forward<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd);
-        if (it >= 2) named_bar_sync(EMPTY0 + slot);  // the consumer has released this slot
+        if (it >= 2) named_bar_sync_n<RD>(EMPTY0 + slot);  // the reader(s) have released this slot
         Ring::put(ring + slot * Ring::SLOT, lane, x, sd);
         __threadfence_block();
-        named_bar_arrive(FULL0 + slot);
+        named_bar_arrive_n<RD>(FULL0 + slot);
         t1 = t0;
         t0 = tp;
       }
-    } else {
+    } else if (role == 1) {
       // ---------------- consumer: everything that is serial in lambda ----------------
       R gl[4], gprec[4];
 #pragma unroll
@@ -495,13 +522,26 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
         if (k + 1 < T) {
           const int it = T - 2 - k, slot = it & 1;
           typename Ring::SD sd;
-          named_bar_sync(FULL0 + slot);
+          named_bar_sync_n<RD>(FULL0 + slot);
           Ring::get(ring + slot * Ring::SLOT, lane, x, sd);
           if (k >= 2) {  // slot will be refilled with step k-2; the last two fills are never waited for
             __threadfence_block();
-            named_bar_arrive(EMPTY0 + slot);
+            named_bar_arrive_n<RD>(EMPTY0 + slot);
           }
-          if (M::DYN)
+          if constexpr (SPLIT) {
+            // the cotangent of every stage derivative goes to the accumulator warp as soon as it is final
+            R* gs = gring + slot * GN * 32 + lane;
+            auto pub = [&](int i, const R* g) {
+              if (i == TB::s - 1 && it >= 2) named_bar_sync(G_EMPTY0 + slot);  // the accumulator has read iteration it - 2
+#pragma unroll
+              for (int q = 0; q < S; ++q) gs[(i * S + q) * 32] = g[q];
+              if (i == 0) {
+                __threadfence_block();
+                named_bar_arrive(G_FULL0 + slot);
+              }
+            };
+            rk_step_adjoint_x<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd, lam, pub);
+          } else if (M::DYN)
             rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd, lam, gc, sgw);
           else
             rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd, lam, gc, nogw);
@@ -549,6 +589,11 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
         for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? thv[s] : R(0);
         M::treatments(a.treatments + (size_t)b * a.C, tc);
         M::init_state_vjp(lam, gth);
+        if constexpr (SPLIT) {
+          named_bar_sync(GC_READY);  // the accumulator warp has finished
+#pragma unroll
+          for (int i = 0; i < M::NC; ++i) gc.v[i] = gcsm[i * 32 + lane];
+        }
         M::setup_vjp(th, tc, f.c, gc, gth);
         if (!M::DYN) {
 #pragma unroll
@@ -557,8 +602,46 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
       }
 #pragma unroll
       for (int s = 0; s < M::NSLOT; ++s) gloc[s] = M::uses(s) ? gth[s] : R(0);
-    }  // consumer
-  }    // producer / consumer
+    } else if constexpr (SPLIT) {
+      // ---------------- accumulator: parameter cotangents of every stage VJP ----------------
+      typename M::Consts gc;
+#pragma unroll
+      for (int i = 0; i < M::NC; ++i) gc.v[i] = R(0);
+      R x[S];
+      R t1 = a.times[T - 1], t0 = a.times[T > 1 ? T - 2 : 0];
+      for (int k = T - 2; k >= 0; --k) {
+        const int it = T - 2 - k, slot = it & 1;
+        const R tp = ld_early(a.times + (k > 0 ? k - 1 : 0));
+        typename Ring::SD sd;
+        named_bar_sync_n<RD>(FULL0 + slot);
+        Ring::get(ring + slot * Ring::SLOT, lane, x, sd);
+        if (k >= 2) {
+          __threadfence_block();
+          named_bar_arrive_n<RD>(EMPTY0 + slot);
+        }
+        R gk[TB::s][S];
+        named_bar_sync(G_FULL0 + slot);
+        {
+          const R* gs = gring + slot * GN * 32 + lane;
+#pragma unroll
+          for (int i = 0; i < TB::s; ++i)
+#pragma unroll
+            for (int q = 0; q < S; ++q) gk[i][q] = gs[(i * S + q) * 32];
+        }
+        if (k >= 2) {  // the consumer waits for this before it writes iteration it + 2
+          __threadfence_block();
+          named_bar_arrive(G_EMPTY0 + slot);
+        }
+        rk_step_adjoint_c<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x, sd, gk, gc);
+        t1 = t0;
+        t0 = tp;
+      }
+#pragma unroll
+      for (int i = 0; i < M::NC; ++i) gcsm[i * 32 + lane] = gc.v[i];
+      __threadfence_block();
+      named_bar_arrive(GC_READY);
+    }  // consumer / accumulator
+  }    // producer / consumer / accumulator
   if (M::DYN && role == 2) {
     // ---------------- weight-gradient warp: acc[k] += outer product of every NeuralPrecisions VJP ----------------
     constexpr int NIN = M::NIN, H = 4 * NIN + 4;
@@ -617,6 +700,10 @@ __global__ void __launch_bounds__(WS_WARPS * 32) elbo_bwd_ws_kernel(const Call<t
     }
   }
 }
+
+}  // namespace vh
+#include "vh_bwd_mx.cuh"
+namespace vh {
 
 inline int pick_block(int N) {
   // small batches are latency-bound: spread warps over as many SMs as possible (148 SMs x 4 schedulers)
@@ -694,13 +781,29 @@ struct BwdLauncher {
     const int mode = (!m || !*m) ? -1 : atoi(m);
     return mode >= 0 ? mode != 0 : block == 32;
   }
+  // VIHDS_BWD_MX=0|1 (read per call): the matrix form of the latency-bound reverse kernel (vh_bwd_mx.cuh) where it exists
+  static bool use_mx() {
+    const char* m = getenv("VIHDS_BWD_MX");
+    return !(m && *m == '0');
+  }
   template <class M, class TB>
   void launch_bwd_variant(bool ws, int grid, int block, size_t smem) {
+    if constexpr (MxOk<M, TB>::value) {
+      // training-shaped calls only: observations present, no upstream gradients on the trajectories themselves
+      if (ws && use_mx() && a.obs && !a.g_x_states && !a.g_x_predict && a.T >= 2) {
+        const size_t sm = mx_smem_bytes<M, TB>();
+        if (sm > 48 * 1024)
+          cudaFuncSetAttribute(elbo_bwd_mx_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        launch_maybe_pdl(elbo_bwd_mx_kernel<M, TB>, dim3((a.N + 31) / 32), dim3(MX_WARPS * 32), sm, stream, outputs_cleared, a);
+        return;
+      }
+    }
     if (ws) {
       // hand-off ring | slot scratch | checkpoint staging ring
       // | NeuralPrecisions weights + hand-off ring of the weight-gradient warp
       const size_t ring = sizeof(R) * (2 * WsRing<M, TB>::SLOT + (size_t)M::NSLOT * 64 + (size_t)(WS_PF + 1) * M::S * 32 +
-                                       (size_t)((NetInfo<M>::NW + 3) & ~3) + 2 * (M::NIN + 8) * 32);
+                                       (size_t)((NetInfo<M>::NW + 3) & ~3) + 2 * (M::NIN + 8) * 32 +
+                                       (WsSplit<M>::value ? 2 * TB::s * M::S * 32 + M::NC * 32 : 0));
       if (ring > 48 * 1024)
         cudaFuncSetAttribute(elbo_bwd_ws_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring);
       launch_maybe_pdl(elbo_bwd_ws_kernel<M, TB>, dim3((a.N + 31) / 32), dim3(WS_WARPS * 32), ring, stream, outputs_cleared, a);

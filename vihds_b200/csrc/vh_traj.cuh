@@ -310,6 +310,82 @@ VH_HD void rk_step_adjoint(const F& f, typename F::real t0, typename F::real t1,
   }
 }
 
+// The adjoint of one step SPLIT over two executors (warp-specialised reverse kernel, constant-precision models): the part
+// that is serial in lam (state cotangents only) and the parameter cotangents, which only ACCUMULATE.  Both call the same
+// vjp_kept; each discards one half of its results, and with everything inlined the compiler drops the instructions that
+// feed only the discarded half (no per-model code).  rk_step_adjoint_x hands the cotangent of every stage derivative,
+// gk[i] -- final at the moment stage i's VJP runs -- to `pub(i, gk[i])`; rk_step_adjoint_c takes them back.
+template <class F, class TB, typename Pub>
+VH_HD void rk_step_adjoint_x(const F& f, typename F::real t0, typename F::real t1, typename F::real h,
+                             const typename F::real* x, const StageData<F, TB>& sd, typename F::real* lam, Pub& pub) {
+  typedef typename F::real R;
+  constexpr int S = F::S;
+  constexpr int s = TB::s;
+  NoGW<R> nosink;
+  typename F::Grad unused;
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(unused.v) / sizeof(R)); ++i) unused.v[i] = R(0);
+  R gk[s][S];
+#pragma unroll
+  for (int i = 0; i < s; ++i)
+#pragma unroll
+    for (int q = 0; q < S; ++q) gk[i][q] = (h * TB::b(i)) * lam[q];
+#pragma unroll
+  for (int i = s - 1; i >= 0; --i) {
+    R X[S], gX[S];
+#pragma unroll
+    for (int q = 0; q < S; ++q) {
+      X[q] = x[q];
+      gX[q] = R(0);
+    }
+#pragma unroll
+    for (int j = 0; j < i; ++j)
+      if (TB::a(i, j) != R(0)) {
+        const R ha = h * TB::a(i, j);
+#pragma unroll
+        for (int q = 0; q < S; ++q) X[q] += ha * sd.k[j][q];
+      }
+    pub(i, gk[i]);
+    f.vjp_kept(stage_time<TB, R>(i, t0, t1), X, sd.kept[i], gk[i], gX, unused, nosink);
+#pragma unroll
+    for (int q = 0; q < S; ++q) lam[q] += gX[q];
+#pragma unroll
+    for (int j = 0; j < i; ++j)
+      if (TB::a(i, j) != R(0)) {
+        const R ha = h * TB::a(i, j);
+#pragma unroll
+        for (int q = 0; q < S; ++q) gk[j][q] += ha * gX[q];
+      }
+  }
+}
+
+template <class F, class TB>
+VH_HD void rk_step_adjoint_c(const F& f, typename F::real t0, typename F::real t1, typename F::real h,
+                             const typename F::real* x, const StageData<F, TB>& sd,
+                             const typename F::real (*gk)[F::S], typename F::Grad& gc) {
+  typedef typename F::real R;
+  constexpr int S = F::S;
+  constexpr int s = TB::s;
+  NoGW<R> nosink;
+#pragma unroll
+  for (int i = s - 1; i >= 0; --i) {
+    R X[S], unused[S];
+#pragma unroll
+    for (int q = 0; q < S; ++q) {
+      X[q] = x[q];
+      unused[q] = R(0);
+    }
+#pragma unroll
+    for (int j = 0; j < i; ++j)
+      if (TB::a(i, j) != R(0)) {
+        const R ha = h * TB::a(i, j);
+#pragma unroll
+        for (int q = 0; q < S; ++q) X[q] += ha * sd.k[j][q];
+      }
+    f.vjp_kept(stage_time<TB, R>(i, t0, t1), X, sd.kept[i], gk[i], unused, gc, nosink);
+  }
+}
+
 // lam: in = dL/dx(t1), out = dL/dx(t0);  x = state at t0;  gc/gw accumulate parameter cotangents
 template <class F, class TB, typename GW>
 VH_HD void rk_step_vjp(const F& f, typename F::real t0, typename F::real t1, typename F::real h,
