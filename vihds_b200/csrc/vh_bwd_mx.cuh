@@ -29,14 +29,17 @@
 namespace vh {
 
 #ifndef VH_MX_NP
-#define VH_MX_NP 3
+#define VH_MX_NP 4
 #endif
 #ifndef VH_MX_NA
-#define VH_MX_NA 2
+#define VH_MX_NA 3
 #endif
 constexpr int MX_NP = VH_MX_NP, MX_NA = VH_MX_NA;
 constexpr int MX_WARPS = MX_NP + 1 + MX_NA;
-constexpr int MX_D1 = 2 * MX_NP;  // slots of the producers' ring
+// two CTAs per SM must stay resident (225 CTAs on 148 SMs at the icml size): register budget per thread, in units of 8;
+// warps are allocated in pairs (measured: 7 warps x 144 registers left room for ONE CTA per SM)
+constexpr int MX_MAXREG = (65536 / (2 * ((MX_WARPS + 1) / 2 * 2) * 32)) / 8 * 8;
+constexpr int MX_D1 = MX_NP + 2;  // slots of the producers' ring (7.4 KB each: two CTAs must fit one SM)
 constexpr int MX_DL = 2 * MX_NA;  // slots of the consumer's lambda ring
 
 template <class M, class TB>
@@ -64,15 +67,28 @@ __device__ __forceinline__ void mbar_arrive_warp(unsigned long long* b, int lane
     (void)state;
   }
 }
+// VH_MX_SPIN 1: poll with test_wait (returns at once); 0: try_wait (the hardware may suspend the warp before it looks again).
+// Measured at the icml size: 56.5 us spinning, 53.0 us with try_wait.
+#ifndef VH_MX_SPIN
+#define VH_MX_SPIN 0
+#endif
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
   const unsigned addr = (unsigned)__cvta_generic_to_shared(b);
   unsigned done;
   do {
+#if VH_MX_SPIN
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+#else
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+#endif
   } while (!done);
 }
 
@@ -116,18 +132,20 @@ enum {
   MXN_DG = 7,   // N_ii at MXN_DG + i, i = 1..7
   MXN_26 = 15, MXN_27 = 16, MXN_36 = 17, MXN_37 = 18,
   MXN_E = 19,   // emission cotangent: e0, e1, e2 (= e4), e3 (= e5)
-  MXN_ITEMS = 23
+  MXN_ITEMS = 23,
+  MXN_PAD = 24  // the accumulators' share of a slot starts on a vector boundary
 };
 
 template <class M, class TB>
 struct MxRing {
   typedef typename M::real R;
   typedef WsRing<M, TB> Inner;                             // x0, stage derivatives, kept intermediates: the accumulators' share
-  static constexpr int SLOT = (MXN_ITEMS + Inner::NITEM) * 32;  // elements
+  static constexpr int NITEM = MXN_PAD + Inner::NITEM;
+  static constexpr int SLOT = RingVec<R>::slot_elems(NITEM);  // elements
 };
 
 template <class M, class TB>
-__global__ void __launch_bounds__(MX_WARPS * 32) elbo_bwd_mx_kernel(const Call<typename M::real> a) {
+__global__ void __maxnreg__(MX_MAXREG) elbo_bwd_mx_kernel(const Call<typename M::real> a) {
   typedef typename M::real R;
   typedef WsRing<M, TB> Ring;
   typedef MxRing<M, TB> MR;
@@ -205,15 +223,22 @@ __global__ void __launch_bounds__(MX_WARPS * 32) elbo_bwd_mx_kernel(const Call<t
   const int nit = T - 1;  // time steps; iteration it handles step k = T - 2 - it
   // emission cotangent at state x against the observations of time index k: e[0..3] (cotangent of x0, x1, x2 = x4, x3 = x5)
   // and the precision cotangents; vihds/ode.py:84-93 + the Gaussian log-likelihood (training.py:150-160)
-  auto emission = [&](const R* x, int k, R* e, R* gprec) {
+  R glp_o[4], hgl[4], iprec[4];  // gl * prec, gl / 2, 1 / prec: per-trajectory constants of the emission cotangent
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    glp_o[o] = gl[o] * prec[o];
+    hgl[o] = gl[o] * R(0.5);
+    iprec[o] = R(1) / prec[o];
+  }
+  auto emission = [&](const R* x, const R* ob, R* e, R* gprec) {
     R xp[4];
     M::observe(x, xp);
     R gxp[4];
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
-      const R d = xp[o] - obs[o * T + k];
-      gxp[o] = -(gl[o] * prec[o] * d);
-      gprec[o] += gl[o] * R(0.5) * (vdiv(R(1), prec[o]) - d * d);
+      const R d = xp[o] - ob[o];
+      gxp[o] = -(glp_o[o] * d);
+      gprec[o] += hgl[o] * (iprec[o] - d * d);
     }
     e[0] = gxp[0] + gxp[1] * x[1] + gxp[2] * (x[2] + x[4]) + gxp[3] * (x[3] + x[5]);
     e[1] = gxp[1] * x[0];
@@ -237,10 +262,24 @@ __global__ void __launch_bounds__(MX_WARPS * 32) elbo_bwd_mx_kernel(const Call<t
     };
 #pragma unroll
     for (int d = 0; d < WS_PF; ++d) issue();
+    // grid times and observations of the step after this one are fetched one (own) iteration ahead: as plain loads at
+    // their point of use they held ~45 % of the producers' stall samples (long scoreboard)
+    R t0 = R(0), t1 = R(0), ob[4] = {R(0), R(0), R(0), R(0)};
+    if (role < nit) {
+      const int k = T - 2 - role;
+      t0 = a.times[k];
+      t1 = a.times[k + 1];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) ob[o] = obs[o * T + k];
+    }
     for (int it = role; it < nit; it += MX_NP) {
       const int k = T - 2 - it, slot = it % MX_D1, use = it / MX_D1;
       issue();
-      const R t0 = a.times[k], t1 = a.times[k + 1];
+      const int kn = k >= MX_NP ? k - MX_NP : 0;
+      const R t0n = ld_early(a.times + kn), t1n = ld_early(a.times + kn + 1);
+      R obn[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) obn[o] = ld_early(obs + o * T + kn);
       const R h = t1 - t0;
       cp_async_wait<WS_PF>();
       R x[S];
@@ -271,13 +310,21 @@ __global__ void __launch_bounds__(MX_WARPS * 32) elbo_bwd_mx_kernel(const Call<t
       Nv[MXN_27] = h * A.j27 + hh * (A.dg[2] * B.j27 + A.j27 * B.dg[7]);
       Nv[MXN_36] = h * A.j36 + hh * (A.dg[3] * B.j36 + A.j36 * B.dg[6]);
       Nv[MXN_37] = h * A.j37 + hh * (A.dg[3] * B.j37 + A.j37 * B.dg[7]);
-      emission(x, k, Nv + MXN_E, gprec);
+      emission(x, ob, Nv + MXN_E, gprec);
       if (use > 0) mbar_wait(empty1 + slot, (use - 1) & 1);  // both readers have released the slot
-      R* sl = ring + slot * MR::SLOT + lane;
+      {
+        R buf[MR::NITEM];
 #pragma unroll
-      for (int i = 0; i < MXN_ITEMS; ++i) sl[i * 32] = Nv[i];
-      Ring::put(ring + slot * MR::SLOT + MXN_ITEMS * 32, lane, x, sd);
+        for (int i = 0; i < MXN_PAD; ++i) buf[i] = i < MXN_ITEMS ? Nv[i] : R(0);
+        R(&inner)[Ring::NITEM] = *reinterpret_cast<R(*)[Ring::NITEM]>(buf + MXN_PAD);
+        Ring::pack(x, sd, inner);
+        RingVec<R>::store(ring + slot * MR::SLOT, lane, buf);
+      }
       mbar_arrive_warp(full1 + slot, lane);
+      t0 = t0n;
+      t1 = t1n;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) ob[o] = obn[o];
     }
 #pragma unroll
     for (int o = 0; o < 4; ++o) gpsm[(role * 4 + o) * 32 + lane] = gprec[o];
@@ -286,10 +333,12 @@ __global__ void __launch_bounds__(MX_WARPS * 32) elbo_bwd_mx_kernel(const Call<t
     R lam[S];
     R gprec[4] = {R(0), R(0), R(0), R(0)};
     {
-      R x[S], e[4];
+      R x[S], e[4], ob[4];
 #pragma unroll
       for (int q = 0; q < S; ++q) x[q] = a.x_states[(size_t)(T - 1) * slab + (size_t)q * N + n];
-      emission(x, T - 1, e, gprec);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) ob[o] = obs[o * T + T - 1];
+      emission(x, ob, e, gprec);
       lam[0] = e[0]; lam[1] = e[1]; lam[2] = e[2]; lam[3] = e[3]; lam[4] = e[2]; lam[5] = e[3];
       lam[6] = R(0); lam[7] = R(0);
     }
@@ -298,14 +347,11 @@ __global__ void __launch_bounds__(MX_WARPS * 32) elbo_bwd_mx_kernel(const Call<t
       const int ls = it % MX_DL, luse = it / MX_DL;
       // lambda1 of this step for its accumulator
       if (luse > 0) mbar_wait(emptyL + ls, (luse - 1) & 1);
-#pragma unroll
-      for (int q = 0; q < S; ++q) lring[(ls * S + q) * 32 + lane] = lam[q];
+      RingVec<R>::store(lring + ls * S * 32, lane, lam);
       mbar_arrive_warp(fullL + ls, lane);
       mbar_wait(full1 + slot, use & 1);
       R Nv[MXN_ITEMS];
-      const R* sl = ring + slot * MR::SLOT + lane;
-#pragma unroll
-      for (int i = 0; i < MXN_ITEMS; ++i) Nv[i] = sl[i * 32];
+      RingVec<R>::load(ring + slot * MR::SLOT, lane, 0, Nv);
       mbar_arrive_warp(empty1 + slot, lane);
       // column 0 gathers all eight components (pairwise: depth 4), the others one or three
       const R s01 = Nv[MXN_00] * lam[0] + Nv[MXN_C0 + 1] * lam[1];
@@ -360,20 +406,31 @@ __global__ void __launch_bounds__(MX_WARPS * 32) elbo_bwd_mx_kernel(const Call<t
 #pragma unroll
     for (int i = 0; i < M::NC; ++i) gc.v[i] = R(0);
     NoGW<R> nogw;
+    R t0 = R(0), t1 = R(0);
+    if (q < nit) {
+      t0 = a.times[T - 2 - q];
+      t1 = a.times[T - 1 - q];
+    }
     for (int it = q; it < nit; it += MX_NA) {
       const int k = T - 2 - it, slot = it % MX_D1, use = it / MX_D1;
       const int ls = it % MX_DL, luse = it / MX_DL;
-      const R t0 = a.times[k], t1 = a.times[k + 1];
+      const int kn = k >= MX_NA ? k - MX_NA : 0;
+      const R t0n = ld_early(a.times + kn), t1n = ld_early(a.times + kn + 1);
       R x[S], lam[S];
       typename Ring::SD sd;
       mbar_wait(full1 + slot, use & 1);
-      Ring::get(ring + slot * MR::SLOT + MXN_ITEMS * 32, lane, x, sd);
+      {
+        R buf[Ring::NITEM];
+        RingVec<R>::load(ring + slot * MR::SLOT, lane, MXN_PAD, buf);
+        Ring::unpack(buf, x, sd);
+      }
       mbar_arrive_warp(empty1 + slot, lane);
       mbar_wait(fullL + ls, luse & 1);
-#pragma unroll
-      for (int j = 0; j < S; ++j) lam[j] = lring[(ls * S + j) * 32 + lane];
+      RingVec<R>::load(lring + ls * S * 32, lane, 0, lam);
       mbar_arrive_warp(emptyL + ls, lane);
       rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, t1 - t0, x, sd, lam, gc, nogw);  // its lambda output is not used
+      t0 = t0n;
+      t1 = t1n;
     }
 #pragma unroll
     for (int i = 0; i < M::NC; ++i) gcsm[(q * M::NC + i) * 32 + lane] = gc.v[i];

@@ -216,42 +216,90 @@ __device__ __forceinline__ void named_bar_sync_n(int id) { asm volatile("bar.syn
 template <int NT>
 __device__ __forceinline__ void named_bar_arrive_n(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
 
+// Ring slots are arrays of 16-byte vectors, [vector][lane]: item i of a lane sits in vector i / V, element i % V
+// (V = 4 fp32 / 2 fp64).  One 128-bit shared-memory access moves V items (conflict-free: a quarter warp per wavefront);
+// as 32-bit accesses the hand-off was 36 + 36 instructions per step and the warps queued on the load/store unit.
+template <typename R>
+struct RingVec {
+  static constexpr int V = 16 / sizeof(R);
+  struct alignas(16) Vec {
+    R v[V];
+  };
+  static constexpr int vectors(int items) { return (items + V - 1) / V; }
+  // elements a slot of `items` items occupies
+  static constexpr int slot_elems(int items) { return vectors(items) * V * 32; }
+  template <int N>
+  __device__ static void store(R* slot, int lane, const R (&buf)[N]) {
+    Vec* s = reinterpret_cast<Vec*>(slot) + lane;
+#pragma unroll
+    for (int g = 0; g < vectors(N); ++g) {
+      Vec q;
+#pragma unroll
+      for (int e = 0; e < V; ++e) q.v[e] = g * V + e < N ? buf[g * V + e] : R(0);
+      s[g * 32] = q;
+    }
+  }
+  // items [first, first + N) of the slot; `first` must be a multiple of V
+  template <int N>
+  __device__ static void load(const R* slot, int lane, int first, R (&buf)[N]) {
+    const Vec* s = reinterpret_cast<const Vec*>(slot) + lane + (first / V) * 32;
+#pragma unroll
+    for (int g = 0; g < vectors(N); ++g) {
+      const Vec q = s[g * 32];
+#pragma unroll
+      for (int e = 0; e < V; ++e)
+        if (g * V + e < N) buf[g * V + e] = q.v[e];
+    }
+  }
+};
+
 template <class M, class TB>
 struct WsRing {
   typedef typename M::real R;
   typedef StageData<Rhs<M>, TB> SD;
   static constexpr int KN = sizeof(typename Rhs<M>::Kept) / sizeof(R);  // species intermediates (+ NeuralPrecisions activations)
   static constexpr int NITEM = M::S + SD::nk * M::S + TB::s * KN;
-  static constexpr int SLOT = NITEM * 32;  // elements per ring slot
-  __device__ static void put(R* slot, int lane, const R* x, const SD& sd) {
+  static constexpr int SLOT = RingVec<R>::slot_elems(NITEM);  // elements per ring slot
+  // flat item order: x | stage derivatives | kept intermediates of every stage
+  __device__ static void pack(const R* x, const SD& sd, R (&buf)[NITEM]) {
     int it = 0;
 #pragma unroll
-    for (int q = 0; q < M::S; ++q) slot[(it++) * 32 + lane] = x[q];
+    for (int q = 0; q < M::S; ++q) buf[it++] = x[q];
 #pragma unroll
     for (int i = 0; i < SD::nk; ++i)
 #pragma unroll
-      for (int q = 0; q < M::S; ++q) slot[(it++) * 32 + lane] = sd.k[i][q];
+      for (int q = 0; q < M::S; ++q) buf[it++] = sd.k[i][q];
 #pragma unroll
     for (int i = 0; i < TB::s; ++i) {
       const R* m = reinterpret_cast<const R*>(&sd.kept[i]);
 #pragma unroll
-      for (int j = 0; j < KN; ++j) slot[(it++) * 32 + lane] = m[j];
+      for (int j = 0; j < KN; ++j) buf[it++] = m[j];
     }
   }
-  __device__ static void get(const R* slot, int lane, R* x, SD& sd) {
+  __device__ static void unpack(const R (&buf)[NITEM], R* x, SD& sd) {
     int it = 0;
 #pragma unroll
-    for (int q = 0; q < M::S; ++q) x[q] = slot[(it++) * 32 + lane];
+    for (int q = 0; q < M::S; ++q) x[q] = buf[it++];
 #pragma unroll
     for (int i = 0; i < SD::nk; ++i)
 #pragma unroll
-      for (int q = 0; q < M::S; ++q) sd.k[i][q] = slot[(it++) * 32 + lane];
+      for (int q = 0; q < M::S; ++q) sd.k[i][q] = buf[it++];
 #pragma unroll
     for (int i = 0; i < TB::s; ++i) {
       R* m = reinterpret_cast<R*>(&sd.kept[i]);
 #pragma unroll
-      for (int j = 0; j < KN; ++j) m[j] = slot[(it++) * 32 + lane];
+      for (int j = 0; j < KN; ++j) m[j] = buf[it++];
     }
+  }
+  __device__ static void put(R* slot, int lane, const R* x, const SD& sd) {
+    R buf[NITEM];
+    pack(x, sd, buf);
+    RingVec<R>::store(slot, lane, buf);
+  }
+  __device__ static void get(const R* slot, int lane, R* x, SD& sd) {
+    R buf[NITEM];
+    RingVec<R>::load(slot, lane, 0, buf);
+    unpack(buf, x, sd);
   }
 };
 
