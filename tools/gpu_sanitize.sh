@@ -10,5 +10,5 @@ run() {
   timeout 1200 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_driver.py $which > $log 2>&1
   echo "$tool $which: rc=$? $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY|SANITIZE_DRIVER_DONE' $log | tr '\n' ' ')"
 }
-for which in dr_latency relay_precisions blackbox_mma step; do run racecheck $which; done
-for which in dr_latency dr_throughput relay_precisions hidden_precisions blackbox_mma blackbox_scalar exchange step; do run memcheck $which; done
+for which in dr_latency dr_ws relay_precisions blackbox_mma step; do run racecheck $which; done
+for which in dr_latency dr_ws dr_throughput relay_precisions hidden_precisions blackbox_mma blackbox_scalar exchange step; do run memcheck $which; done

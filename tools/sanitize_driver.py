@@ -20,8 +20,12 @@ def case(name, t=20):
 
 
 def main(which):
-    if "dr_latency" in which:  # team prologue forward, producer / consumer reverse sweep
+    if "dr_latency" in which:  # team prologue forward; matrix-form reverse sweep (mbarrier rings, vh_bwd_mx.cuh)
         run_case_on_gpu(case("dr_constant_icml_midpoint_f32_iw8"))
+    if "dr_ws" in which:  # the producer / consumer reverse sweep (named-barrier ring) the matrix form replaced for this model
+        os.environ["VIHDS_BWD_MX"] = "0"
+        run_case_on_gpu(case("dr_constant_icml_midpoint_f32_iw8"))
+        del os.environ["VIHDS_BWD_MX"]
     if "dr_throughput" in which:
         os.environ["VIHDS_FWD_TEAM"], os.environ["VIHDS_BWD_WS"] = "0", "0"
         run_case_on_gpu(case("dr_constant_icml_midpoint_f32_iw8"))

@@ -40,7 +40,7 @@ constexpr int MX_WARPS = MX_NP + 1 + MX_NA;
 // warps are allocated in pairs (measured: 7 warps x 144 registers left room for ONE CTA per SM)
 constexpr int MX_MAXREG = (65536 / (2 * ((MX_WARPS + 1) / 2 * 2) * 32)) / 8 * 8;
 constexpr int MX_D1 = MX_NP + 2;  // slots of the producers' ring (7.4 KB each: two CTAs must fit one SM)
-constexpr int MX_DL = 2 * MX_NA;  // slots of the consumer's lambda ring
+constexpr int MX_DL = MX_D1;       // slots of the consumer's lambda ring (same count: the consumer's loop is unrolled over it)
 
 template <class M, class TB>
 struct MxOk {
@@ -151,6 +151,7 @@ __global__ void __maxnreg__(MX_MAXREG) elbo_bwd_mx_kernel(const Call<typename M:
   typedef MxRing<M, TB> MR;
   constexpr int S = M::S;
   static_assert(S == 8 && !M::DYN, "matrix-form reverse kernel: dr_constant family");
+  static_assert(MX_NP <= MX_D1 && MX_NA <= MX_D1 && MX_DL == MX_D1, "ring bookkeeping below");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem_raw);
   unsigned long long* full1 = bars;                    // [MX_D1] producers -> consumer + accumulator
@@ -206,15 +207,31 @@ __global__ void __maxnreg__(MX_MAXREG) elbo_bwd_mx_kernel(const Call<typename M:
   f.nh = 0;
   R prec[4], gl[4];
   {
-    R th[M::NSLOT];
-    R tc[3];
+    // the RHS constants (six powf in the Hill fractions) are formed by ONE warp and handed to the others through shared
+    // memory: computed by all eight warps they were 8 % of the launch's instructions, all at the same moment
+    static_assert(sizeof(typename M::Consts) / sizeof(R) <= MX_NA * M::NC, "constants are staged in the accumulators' area");
+    constexpr int NCW = sizeof(typename M::Consts) / sizeof(R);
+    if (role == 0) {
+      R th[M::NSLOT];
+      R tc[3];
 #pragma unroll
-    for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? thv[s] : R(0);
-    M::treatments(a.treatments + (size_t)b * a.C, tc);
-    M::setup(th, tc, f.c);
+      for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? thv[s] : R(0);
+      M::treatments(a.treatments + (size_t)b * a.C, tc);
+      M::setup(th, tc, f.c);
+      const R* cv = reinterpret_cast<const R*>(&f.c);
+#pragma unroll
+      for (int i = 0; i < NCW; ++i) gcsm[i * 32 + lane] = cv[i];
+    }
+    __syncthreads();
+    if (role != 0) {
+      R* cv = reinterpret_cast<R*>(&f.c);
+#pragma unroll
+      for (int i = 0; i < NCW; ++i) cv[i] = gcsm[i * 32 + lane];
+    }
+    __syncthreads();  // gcsm is the accumulators' again
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
-      prec[o] = th[S_prec_x + o];
+      prec[o] = thv[S_prec_x + o];
       gl[o] = iwae ? gup : ((a.g_logp_species && active) ? a.g_logp_species[(size_t)n * 4 + o] : R(0));
     }
   }
@@ -272,8 +289,9 @@ __global__ void __maxnreg__(MX_MAXREG) elbo_bwd_mx_kernel(const Call<typename M:
 #pragma unroll
       for (int o = 0; o < 4; ++o) ob[o] = obs[o * T + k];
     }
+    int slot = role % MX_D1, use = role / MX_D1;
     for (int it = role; it < nit; it += MX_NP) {
-      const int k = T - 2 - it, slot = it % MX_D1, use = it / MX_D1;
+      const int k = T - 2 - it;
       issue();
       const int kn = k >= MX_NP ? k - MX_NP : 0;
       const R t0n = ld_early(a.times + kn), t1n = ld_early(a.times + kn + 1);
@@ -325,6 +343,11 @@ __global__ void __maxnreg__(MX_MAXREG) elbo_bwd_mx_kernel(const Call<typename M:
       t1 = t1n;
 #pragma unroll
       for (int o = 0; o < 4; ++o) ob[o] = obn[o];
+      slot += MX_NP;
+      if (slot >= MX_D1) {
+        slot -= MX_D1;
+        ++use;
+      }
     }
 #pragma unroll
     for (int o = 0; o < 4; ++o) gpsm[(role * 4 + o) * 32 + lane] = gprec[o];
@@ -342,9 +365,14 @@ __global__ void __maxnreg__(MX_MAXREG) elbo_bwd_mx_kernel(const Call<typename M:
       lam[0] = e[0]; lam[1] = e[1]; lam[2] = e[2]; lam[3] = e[3]; lam[4] = e[2]; lam[5] = e[3];
       lam[6] = R(0); lam[7] = R(0);
     }
-    for (int it = 0; it < nit; ++it) {
-      const int slot = it % MX_D1, use = it / MX_D1;
-      const int ls = it % MX_DL, luse = it / MX_DL;
+    // unrolled over the ring: slot numbers and shared-memory addresses are immediates, one backward branch per MX_D1
+    // steps (the branch and the index arithmetic were ~30 % of this warp's samples)
+    for (int it0 = 0, use = 0; it0 < nit; it0 += MX_D1, ++use)
+#pragma unroll
+    for (int slot = 0; slot < MX_D1; ++slot) {
+      const int it = it0 + slot;
+      if (it >= nit) break;
+      const int ls = slot, luse = use;
       // lambda1 of this step for its accumulator
       if (luse > 0) mbar_wait(emptyL + ls, (luse - 1) & 1);
       RingVec<R>::store(lring + ls * S * 32, lane, lam);
@@ -393,7 +421,7 @@ __global__ void __maxnreg__(MX_MAXREG) elbo_bwd_mx_kernel(const Call<typename M:
       for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? thv[s] : R(0);
       M::treatments(a.treatments + (size_t)b * a.C, tc);
       M::init_state_vjp(lam, gth);
-      M::setup_vjp(th, tc, f.c, gc, gth);
+      M::setup_vjp(th, tc, f.c, gc, gth, 4 | 1);  // the LasR Hill fraction's share: first accumulator warp, below
 #pragma unroll
       for (int o = 0; o < 4; ++o) gth[S_prec_x + o] += gprec[o];
     }
@@ -411,9 +439,10 @@ __global__ void __maxnreg__(MX_MAXREG) elbo_bwd_mx_kernel(const Call<typename M:
       t0 = a.times[T - 2 - q];
       t1 = a.times[T - 1 - q];
     }
+    int slot = q % MX_D1, use = q / MX_D1;
     for (int it = q; it < nit; it += MX_NA) {
-      const int k = T - 2 - it, slot = it % MX_D1, use = it / MX_D1;
-      const int ls = it % MX_DL, luse = it / MX_DL;
+      const int k = T - 2 - it;
+      const int ls = slot, luse = use;
       const int kn = k >= MX_NA ? k - MX_NA : 0;
       const R t0n = ld_early(a.times + kn), t1n = ld_early(a.times + kn + 1);
       R x[S], lam[S];
@@ -431,24 +460,81 @@ __global__ void __maxnreg__(MX_MAXREG) elbo_bwd_mx_kernel(const Call<typename M:
       rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, t1 - t0, x, sd, lam, gc, nogw);  // its lambda output is not used
       t0 = t0n;
       t1 = t1n;
+      slot += MX_NA;
+      if (slot >= MX_D1) {
+        slot -= MX_D1;
+        ++use;
+      }
     }
 #pragma unroll
     for (int i = 0; i < M::NC; ++i) gcsm[(q * M::NC + i) * 32 + lane] = gc.v[i];
   }
+  // this warp's columns of the chain-rule epilogue: their inputs are fetched NOW, while the consumer warp is still busy
+  // with the chain rule of the constants (nine dependent-latency loads per column otherwise sit behind the barrier)
+  constexpr int CPW = 6;  // columns per warp held in registers (P <= CPW * (MX_WARPS - 1) = 42; more: plain path)
+  const bool pre = a.P <= CPW * (MX_WARPS - 1);
+  ColumnIn<R> cin[CPW];
+  int cslot[CPW];
+  const int cw = role < MX_NP ? role : role - 1;  // the consumer takes no columns in this form
+  if (pre && role != MX_NP) {
+#pragma unroll
+    for (int j = 0; j < CPW; ++j) {
+      const int k = cw + j * (MX_WARPS - 1);
+      if (k < a.P) {
+        column_load(a, n, b, k, cin[j]);
+        cslot[j] = a.col_slot[k];
+      }
+    }
+  }
   if (role != MX_NP) named_bar_sync_n<MX_WARPS * 32>(1);
-  __syncthreads();  // gloc complete
+  // second half of the constants' chain rule (the LasR Hill fraction: six powf, three logf) on the first accumulator warp,
+  // next to the consumer's half; its slot cotangents go to gloc2 and are added where the columns read them
+  R* gloc2 = ring + lane;  // [NSLOT][32]: the rings are idle from here on
+  if (role == MX_NP + 1) {
+    typename M::Consts gc;
+#pragma unroll
+    for (int i = 0; i < M::NC; ++i) {
+      R v = R(0);
+#pragma unroll
+      for (int q = 0; q < MX_NA; ++q) v += gcsm[(q * M::NC + i) * 32 + lane];
+      gc.v[i] = v;
+    }
+    R gth[M::NSLOT], th[M::NSLOT], tc[3];
+#pragma unroll
+    for (int s = 0; s < M::NSLOT; ++s) {
+      gth[s] = R(0);
+      th[s] = M::uses(s) ? thv[s] : R(0);
+    }
+    M::treatments(a.treatments + (size_t)b * a.C, tc);
+    M::setup_vjp(th, tc, f.c, gc, gth, 2);
+#pragma unroll
+    for (int s = 0; s < M::NSLOT; ++s) gloc2[s * 32] = gth[s];
+  }
+  __syncthreads();  // gloc, gloc2 complete
   WarpSegRed<R> red(a.d_q_mu, a.d_q_prec, a.P, b, active);
+  if (pre) {
+#pragma unroll
+    for (int j = 0; j < CPW; ++j) {
+      const int k = cw + j * (MX_WARPS - 1);
+      if (role != MX_NP && k < a.P) {
+        R dmu = R(0), dprec = R(0);
+        if (active) column_vjp_from(cin[j], cslot[j] >= 0 ? gloc[cslot[j]] + gloc2[cslot[j] * 32] : R(0), glq, glp, dmu, dprec);
+        red(b, k, dmu, dprec, active);
+      }
+    }
+  } else {
 #pragma unroll 3
-  for (int k = role; k < a.P; k += MX_WARPS) {
-    const int s = a.col_slot[k];
-    R dmu = R(0), dprec = R(0);
-    if (active) column_vjp(a, n, b, k, s >= 0 ? gloc[s] : R(0), glq, glp, dmu, dprec);
-    red(b, k, dmu, dprec, active);
+    for (int k = role; k < a.P; k += MX_WARPS) {
+      const int s = a.col_slot[k];
+      R dmu = R(0), dprec = R(0);
+      if (active) column_vjp(a, n, b, k, s >= 0 ? gloc[s] + gloc2[s * 32] : R(0), glq, glp, dmu, dprec);
+      red(b, k, dmu, dprec, active);
+    }
   }
   if (a.d_extra && active) {
     for (int s = role; s < M::NSLOT; s += MX_WARPS) {
       const int src = a.slot_src[s];
-      if (src < 0 && src != VH_SLOT_UNUSED) a.d_extra[(size_t)(-1 - src) * N + n] = gloc[s];
+      if (src < 0 && src != VH_SLOT_UNUSED) a.d_extra[(size_t)(-1 - src) * N + n] = gloc[s] + gloc2[s * 32];
     }
   }
 }

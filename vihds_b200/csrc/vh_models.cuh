@@ -195,10 +195,14 @@ struct DrModel {
     gKb = gB * c12;
   }
 
-  // gc: cotangent of the constants  ->  gth: cotangent of the theta slots (accumulated)
-  VH_HD static void setup_vjp(const R* th, const R* tc, const Consts& c, const Consts& gc, R* gth) {
+  // gc: cotangent of the constants  ->  gth: cotangent of the theta slots (accumulated).
+  // parts (compile-time constant at every call site): the two Hill fractions carry most of the cost (six powf + three logf
+  // each) and are independent of each other and of the rest, so a kernel may give them to different warps:
+  // 1 = the LuxR fraction (fR), 2 = the LasR fraction (fS), 4 = everything else; 7 = all.
+  VH_HD static void setup_vjp(const R* th, const R* tc, const Consts& c, const Consts& gc, R* gth, int parts = 7) {
     const R c6 = tc[0], c12 = tc[1];
     const R* g = gc.v;
+    if (parts & 4) {
     gth[S_r] += g[C_r] * clampmask(th[S_r], R(0), R(4));
     gth[S_K] += g[C_K] * clampmask(th[S_K], R(0), R(4));
     gth[S_tlag] += g[C_tlag];
@@ -222,27 +226,40 @@ struct DrModel {
     gth[S_a480] += g[C_p5] * rc;
     gth[S_aR] += g[C_p6] * rc;
     gth[S_aS] += g[C_p7] * rc;
+    gth[S_rc] += grc;
+    }  // parts & 4
     const R nR = clampv(th[S_nR], R(0.5), R(3)), nS = clampv(th[S_nS], R(0.5), R(3));
-    R gnR, gnS;
+    R gnR = R(0), gnS = R(0);
     if (VERSION == 1) {
       const R lb = R(1e-12), ub = R(1);
       R ga, gb;
-      hill_vjp(clampv(th[S_KR6], lb, ub), clampv(th[S_KR12], lb, ub), nR, c6, c12, c.v[C_fR], g[C_fR], ga, gb, gnR);
-      gth[S_KR6] += ga * clampmask(th[S_KR6], lb, ub);
-      gth[S_KR12] += gb * clampmask(th[S_KR12], lb, ub);
-      hill_vjp(clampv(th[S_KS6], lb, ub), clampv(th[S_KS12], lb, ub), nS, c6, c12, c.v[C_fS], g[C_fS], ga, gb, gnS);
-      gth[S_KS6] += ga * clampmask(th[S_KS6], lb, ub);
-      gth[S_KS12] += gb * clampmask(th[S_KS12], lb, ub);
+      if (parts & 1) {
+        hill_vjp(clampv(th[S_KR6], lb, ub), clampv(th[S_KR12], lb, ub), nR, c6, c12, c.v[C_fR], g[C_fR], ga, gb, gnR);
+        gth[S_KR6] += ga * clampmask(th[S_KR6], lb, ub);
+        gth[S_KR12] += gb * clampmask(th[S_KR12], lb, ub);
+      }
+      if (parts & 2) {
+        hill_vjp(clampv(th[S_KS6], lb, ub), clampv(th[S_KS12], lb, ub), nS, c6, c12, c.v[C_fS], g[C_fS], ga, gb, gnS);
+        gth[S_KS6] += ga * clampmask(th[S_KS6], lb, ub);
+        gth[S_KS12] += gb * clampmask(th[S_KS12], lb, ub);
+      }
     } else {
       const R eS6 = clampv(th[S_eS6], R(1e-12), R(1)), eR12 = clampv(th[S_eR12], R(1e-12), R(1));
       const R E = eR12 * c12, F = eS6 * c6;
-      gnR = g[C_fR] * (vpow(c6, nR) * vlog(c6) + vpow(E, nR) * vlog(E));
-      gnS = g[C_fS] * (vpow(F, nS) * vlog(F) + vpow(c12, nS) * vlog(c12));
-      gth[S_eR12] += g[C_fR] * nR * vpow(E, nR - R(1)) * c12 * clampmask(th[S_eR12], R(1e-12), R(1));
-      gth[S_eS6] += g[C_fS] * nS * vpow(F, nS - R(1)) * c6 * clampmask(th[S_eS6], R(1e-12), R(1));
+      if (parts & 1) {
+        gnR = g[C_fR] * (vpow(c6, nR) * vlog(c6) + vpow(E, nR) * vlog(E));
+        gth[S_eR12] += g[C_fR] * nR * vpow(E, nR - R(1)) * c12 * clampmask(th[S_eR12], R(1e-12), R(1));
+      }
+      if (parts & 2) {
+        gnS = g[C_fS] * (vpow(F, nS) * vlog(F) + vpow(c12, nS) * vlog(c12));
+        gth[S_eS6] += g[C_fS] * nS * vpow(F, nS - R(1)) * c6 * clampmask(th[S_eS6], R(1e-12), R(1));
+      }
     }
-    gth[S_nR] += gnR * clampmask(th[S_nR], R(0.5), R(3));
-    gth[S_nS] += gnS * clampmask(th[S_nS], R(0.5), R(3));
+    if (parts & 1) gth[S_nR] += gnR * clampmask(th[S_nR], R(0.5), R(3));
+    if (parts & 2) gth[S_nS] += gnS * clampmask(th[S_nS], R(0.5), R(3));
+    if (!(parts & 4)) return;
+    R grc = R(0);
+    const R rc = th[S_rc];
     if (RELAY) {
       gth[S_dluxI] += g[C_dluxI] * clampmask(th[S_dluxI], R(1e-12), R(5));
       gth[S_dlasI] += g[C_dlasI] * clampmask(th[S_dlasI], R(1e-12), R(5));

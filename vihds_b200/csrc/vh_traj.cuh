@@ -527,6 +527,75 @@ VH_HD void load_theta(const Call<typename M::real>& a, int n, int b, typename M:
   for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? loc[s] : R(0);
 }
 
+// column_vjp in two halves: everything it reads from global memory (nine loads per column, the one of u strided by P), and
+// the arithmetic.  The latency-bound reverse kernels issue the loads of all their columns while the warps are still waiting
+// for the lambda recurrence to finish -- the cotangent gth is the only late input.
+template <typename R>
+struct ColumnIn {
+  int kind;
+  R mu, prec, uu, lo, hi, th_in, pm, pp, gth_up;
+  bool have_th;
+};
+template <typename R>
+VH_HD void column_load(const Call<R>& a, int n, int b, int k, ColumnIn<R>& c) {
+  c.kind = a.kind[k];
+  c.gth_up = a.g_theta ? a.g_theta[(size_t)k * a.N + n] : R(0);
+  c.mu = a.q_mu[b * a.P + k];
+  c.prec = a.q_prec[b * a.P + k];
+  c.uu = a.u[(size_t)n * a.P + k];
+  c.lo = a.clip_lo[k];
+  c.hi = a.clip_hi[k];
+  c.have_th = a.theta_in != nullptr;
+  c.th_in = c.have_th ? a.theta_in[(size_t)k * a.N + n] : R(0);
+  c.pm = a.p_mu[k];
+  c.pp = a.p_prec[k];
+}
+template <typename R>
+VH_HD void column_vjp_from(const ColumnIn<R>& c, R gth, R glq, R glp, R& dmu, R& dprec) {
+  dmu = R(0);
+  dprec = R(0);
+  const int kind = c.kind;
+  gth += c.gth_up;
+  const R mu = c.mu;
+  if (kind == VH_KIND_CONSTANT) {
+    dmu = gth;
+    return;
+  }
+  const R prec = c.prec;
+  const R sigma = R(1) / vsqrt(prec);
+  const R uu = c.uu;
+  const R lo = c.lo, hi = c.hi;
+  R raw, th;
+  bool have = false;
+  if (c.have_th) {
+    th = c.th_in;
+    raw = th;
+    have = th > lo && th < hi;
+  }
+  if (!have) {
+    const R sv = mu + sigma * uu;
+    raw = kind == VH_KIND_LOGNORMAL ? vexp(sv) : sv;
+    th = clampv(raw, lo, hi);
+  }
+  const R pm = c.pm, pp = c.pp;
+  R x, gx_to_th;
+  if (kind == VH_KIND_LOGNORMAL) {
+    x = vlog(th + R(1e-12));
+    gx_to_th = R(1) / (th + R(1e-12));
+  } else {
+    x = th;
+    gx_to_th = R(1);
+  }
+  const R jac = kind == VH_KIND_LOGNORMAL ? R(1) : R(0);
+  const R dq = mu - x, dp = pm - x;
+  const R gx = glq * (prec * dq - jac) + glp * (pp * dp - jac);
+  const R gtot = gth + gx * gx_to_th;
+  const R graw = gtot * clampmask(raw, lo, hi);
+  const R gs = kind == VH_KIND_LOGNORMAL ? graw * raw : graw;
+  dmu = gs - glq * prec * dq;
+  dprec = -R(0.5) * gs * uu * sigma / prec + glq * (R(0.5) / (prec + R(1e-12)) - R(0.5) * dq * dq);
+}
+
 // cotangent of one sampled column -> (d mu, d prec) of q for this trajectory
 template <typename R>
 VH_HD void column_vjp(const Call<R>& a, int n, int b, int k, R gth, R glq, R glp, R& dmu, R& dprec) {
