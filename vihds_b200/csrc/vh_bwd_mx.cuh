@@ -55,10 +55,19 @@ struct MxOk<DrModel<float, VER, 0, false>, TabMidpoint<float>> {  // fp32: the f
 __device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
 }
-// one arrival for the whole warp: every lane's shared-memory writes are ordered before it
+// VH_MX_ARRIVE_ALL 1: every lane arrives for itself (barrier counts are per lane; each lane's release covers its own
+// shared-memory accesses -- the form compute-sanitizer's racecheck can follow); 0: __syncwarp() + one arrival by lane 0
+// (ordered through the warp barrier and the cumulativity of the release).
+#ifndef VH_MX_ARRIVE_ALL
+#define VH_MX_ARRIVE_ALL 1
+#endif
+constexpr int MBAR_PER_WARP = VH_MX_ARRIVE_ALL ? 32 : 1;
 __device__ __forceinline__ void mbar_arrive_warp(unsigned long long* b, int lane) {
+#if !VH_MX_ARRIVE_ALL
   __syncwarp();
-  if (lane == 0) {
+  if (lane == 0)
+#endif
+  {
     unsigned long long state;
     asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 %0, [%1];"
                  : "=l"(state)
@@ -177,12 +186,12 @@ __global__ void __maxnreg__(MX_MAXREG) elbo_bwd_mx_kernel(const Call<typename M:
   R* gpsm = gcsm + MX_NA * M::NC * 32;                                // [MX_NP][4][32]
   if (threadIdx.x == 0) {
     for (int i = 0; i < MX_D1; ++i) {
-      mbar_init(full1 + i, 1);
-      mbar_init(empty1 + i, 2);  // the consumer and the accumulator of that step
+      mbar_init(full1 + i, MBAR_PER_WARP);
+      mbar_init(empty1 + i, 2 * MBAR_PER_WARP);  // the consumer and the accumulator of that step
     }
     for (int i = 0; i < MX_DL; ++i) {
-      mbar_init(fullL + i, 1);
-      mbar_init(emptyL + i, 1);
+      mbar_init(fullL + i, MBAR_PER_WARP);
+      mbar_init(emptyL + i, MBAR_PER_WARP);
     }
   }
   // upstream gradients (fused IWAE or handed in) and theta, as elbo_bwd_ws_kernel
