@@ -28,6 +28,8 @@
 
 namespace vh {
 
+// warps per role (8 warps at 128 registers keep two CTAs per SM): 4 + 3 and 5 + 2 measure the same (46.7 / 46.2 us at the
+// icml size), 3 + 2 in six warps 48 us
 #ifndef VH_MX_NP
 #define VH_MX_NP 4
 #endif
