@@ -53,8 +53,9 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // guard: this rank's cost of the step (or NULL).  A NaN cost anywhere means a NaN gradient sum everywhere: every rank
 // publishes a "bad" bit with its flags, every CTA ORs the bits of all ranks and all of them skip the update together (the
 // reference stops before optimizer.step(), vihds/training.py:331-333); state[3] / step[2] count the skipped calls.
-// A wait that exceeds timeout_ns marks the exchange as timed out (sticky) and the CTA skips its part of the update; once
-// the flag is set every later call returns at once, so the peers time out as well and every host finds the flag.
+// A wait that exceeds timeout_ns marks the exchange as timed out (sticky) and NO block of this rank applies the update (the
+// blocks vote before they touch the parameters); once the flag is set every later call returns at once, so the peers time
+// out as well and every host finds the flag.
 //
 // Per CTA: push the slice to every rank's inbox -> system fence -> one flag per peer -> wait for the same CTA of every peer
 // -> sum the inboxes + Adam on the slice.  (Round 1 had ONE flag per rank, published by the last CTA to finish pushing: a
@@ -141,6 +142,24 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(size_t n, size_t n_
     }
   }
   __syncthreads();
+  // All or nothing on this rank: a block applies its slice only when EVERY block of the grid has received its peers'
+  // flags (local vote on the ticket counter; the grid is resident).  A block that timed out has set the sticky flag
+  // instead of voting, which releases the others without an update.
+  if (threadIdx.x == 0) {
+    if (!(s_skip & 2)) {
+      __threadfence();
+      atomicAdd((unsigned long long*)(state + 1), 1ULL);
+      const unsigned long long t0 = global_ns();
+      while (*(volatile long long*)(state + 1) < (long long)gridDim.x) {
+        if (*(volatile long long*)(state + 2) != 0 || global_ns() - t0 > timeout_ns) {
+          state[2] = 1;
+          s_skip |= 2;
+          break;
+        }
+      }
+    }
+  }
+  __syncthreads();
   const int skip = s_skip;
   if (!skip) {
     const double lr = hyper[0], b1d = hyper[1], b2d = hyper[2];
@@ -167,7 +186,7 @@ __global__ void __launch_bounds__(256) adam_allreduce_kernel(size_t n, size_t n_
   if (threadIdx.x == 0) {
     __threadfence();
     const unsigned long long ticket = atomicAdd((unsigned long long*)(state + 1), 1ULL);
-    if (ticket == (unsigned long long)gridDim.x - 1) {
+    if (ticket == 2ULL * gridDim.x - 1) {  // votes + finishers (never reached after a time-out: the exchange is dead then)
       state[1] = 0;
       state[0] = (long long)(epoch + 1);
       if (skip == 0)
