@@ -91,6 +91,7 @@ def test_cuda_matches_reference_golden(name, form, monkeypatch):
         if not (str(case["model"]).startswith("dr_constant") and "precisions" not in str(case["model"]) and str(case["solver"]) == "midpoint" and str(case["dtype"]) == "float32"):
             pytest.skip("same kernels as the default form")
         monkeypatch.setenv("VIHDS_BWD_MX", "0")
+        monkeypatch.setenv("VIHDS_FWD_SCRIBE", "0")  # ... and the one-warp time loop of the team forward kernel
     if form == "throughput":
         if str(case["model"]) == "dr_blackbox":
             pytest.skip("the black-box kernels have one form per implementation (tests/test_gpu_bb_mma.py compares those)")

@@ -115,8 +115,58 @@ struct BwdBounds {
 #ifndef VH_FWD_LANE_DEFAULT
 #define VH_FWD_LANE_DEFAULT 0
 #endif
+// named barriers (two warps unless a count is given) and 16-byte ring slots: shared by the team forward kernel and the
+// warp-specialised reverse kernels below
+__device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
+template <int NT>
+__device__ __forceinline__ void named_bar_sync_n(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
+template <int NT>
+__device__ __forceinline__ void named_bar_arrive_n(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
+
+// Ring slots are arrays of 16-byte vectors, [vector][lane]: item i of a lane sits in vector i / V, element i % V
+// (V = 4 fp32 / 2 fp64).  One 128-bit shared-memory access moves V items (conflict-free: a quarter warp per wavefront);
+// as 32-bit accesses the hand-off was 36 + 36 instructions per step and the warps queued on the load/store unit.
+template <typename R>
+struct RingVec {
+  static constexpr int V = 16 / sizeof(R);
+  struct alignas(16) Vec {
+    R v[V];
+  };
+  static constexpr int vectors(int items) { return (items + V - 1) / V; }
+  // elements a slot of `items` items occupies
+  static constexpr int slot_elems(int items) { return vectors(items) * V * 32; }
+  template <int N>
+  __device__ static void store(R* slot, int lane, const R (&buf)[N]) {
+    Vec* s = reinterpret_cast<Vec*>(slot) + lane;
+#pragma unroll
+    for (int g = 0; g < vectors(N); ++g) {
+      Vec q;
+#pragma unroll
+      for (int e = 0; e < V; ++e) q.v[e] = g * V + e < N ? buf[g * V + e] : R(0);
+      s[g * 32] = q;
+    }
+  }
+  // items [first, first + N) of the slot; `first` must be a multiple of V
+  template <int N>
+  __device__ static void load(const R* slot, int lane, int first, R (&buf)[N]) {
+    const Vec* s = reinterpret_cast<const Vec*>(slot) + lane + (first / V) * 32;
+#pragma unroll
+    for (int g = 0; g < vectors(N); ++g) {
+      const Vec q = s[g * 32];
+#pragma unroll
+      for (int e = 0; e < V; ++e)
+        if (g * V + e < N) buf[g * V + e] = q.v[e];
+    }
+  }
+};
+
 constexpr int FWD_TEAM = VH_FWD_TEAM;
-template <class M, class TB>
+// SCRIBE: after the prologue warp 1 stays as the "scribe" of the time loop.  Warp 0 only integrates (one RK step per time
+// point) and hands every state x_k over through a two-slot shared-memory ring; the scribe stores the trace, applies the
+// observation map, accumulates the Gaussian log-likelihood and fetches the observations.  That takes ~55 of the ~210
+// instructions per step off the warp whose in-order instruction stream IS the launch time at this size.
+template <class M, class TB, bool SCRIBE>
 __global__ void __launch_bounds__(FWD_TEAM * 32) elbo_fwd_team_kernel(const Call<typename M::real> a) {
   typedef typename M::real R;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -127,8 +177,12 @@ __global__ void __launch_bounds__(FWD_TEAM * 32) elbo_fwd_team_kernel(const Call
   const bool active = n0 < a.N;
   const int n = active ? n0 : a.N - 1;
   const int b = n / a.IW;
-  const SlotScratch<R> loc{sm + lane, 32};
-  R* part = sm + M::NSLOT * 32;       // [2][FWD_TEAM][32]
+  constexpr int S = M::S, NS = M::NS;
+  constexpr int XSLOT = RingVec<R>::slot_elems(S);
+  R* xring = sm;  // [2][XSLOT] (scribe form), 16-byte aligned
+  R* slots = sm + (SCRIBE ? 2 * XSLOT : 0);
+  const SlotScratch<R> loc{slots + lane, 32};
+  R* part = slots + M::NSLOT * 32;    // [2][FWD_TEAM][32]
   R* wsm = part + 2 * FWD_TEAM * 32;  // NeuralPrecisions weights (dynamic-precision models)
   if (M::DYN) {
     for (int i = threadIdx.x; i < a.nw; i += blockDim.x) wsm[i] = a.weights[i];
@@ -147,18 +201,126 @@ __global__ void __launch_bounds__(FWD_TEAM * 32) elbo_fwd_team_kernel(const Call
   part[role * 32 + lane] = lq;
   part[(FWD_TEAM + role) * 32 + lane] = lp;
   __syncthreads();
-  if (role != 0 || !active) return;
-  lq = R(0);
-  lp = R(0);
+  if constexpr (!SCRIBE) {
+    if (role != 0 || !active) return;
+    lq = R(0);
+    lp = R(0);
 #pragma unroll
-  for (int r = 0; r < FWD_TEAM; ++r) {
-    lq += part[r * 32 + lane];
-    lp += part[(FWD_TEAM + r) * 32 + lane];
+    for (int r = 0; r < FWD_TEAM; ++r) {
+      lq += part[r * 32 + lane];
+      lp += part[(FWD_TEAM + r) * 32 + lane];
+    }
+    R th[M::NSLOT];
+#pragma unroll
+    for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? loc[s] : R(0);
+    traj_forward_from<M, TB>(a, n, M::DYN ? wsm : nullptr, th, lq, lp);
+  } else {
+    if (role > 1) return;
+    // whole warps from here on (the named barriers count threads); lanes past the batch shadow its last trajectory
+    enum { FULL0 = 1, EMPTY0 = 3 };
+    const size_t N = a.N;
+    const int T = a.T;
+    if (role == 0) {
+      // ---------------- integrator ----------------
+      lq = R(0);
+      lp = R(0);
+#pragma unroll
+      for (int r = 0; r < FWD_TEAM; ++r) {
+        lq += part[r * 32 + lane];
+        lp += part[(FWD_TEAM + r) * 32 + lane];
+      }
+      Rhs<M> f;
+      f.w = M::DYN ? wsm : nullptr;
+      f.nh = a.n_hidden;
+      R x[S];
+      {
+        R th[M::NSLOT];
+        R tc[3];
+#pragma unroll
+        for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? loc[s] : R(0);
+        M::treatments(a.treatments + (size_t)b * a.C, tc);
+        M::setup(th, tc, f.c);
+        M::init_state(th, tc, x);
+      }
+      const R h0 = a.times[1] - a.times[0];
+      R t0 = a.times[0], t1 = a.times[1];
+      for (int k = 0; k < T; ++k) {
+        const int slot = k & 1;
+        const R t2 = ld_early(a.times + (k + 2 < T ? k + 2 : T - 1));
+        if (k >= 2) named_bar_sync(EMPTY0 + slot);  // the scribe has taken x_{k-2} out of this slot
+        RingVec<R>::store(xring + slot * XSLOT, lane, x);
+        __threadfence_block();
+        named_bar_arrive(FULL0 + slot);
+        if (k + 1 < T) rk_step<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x);
+        t0 = t1;
+        t1 = t2;
+      }
+      if (active) {
+        if (a.logp_theta) a.logp_theta[n] = lp;
+        if (a.logq_theta) a.logq_theta[n] = lq;
+      }
+    } else {
+      // ---------------- scribe: trace, observation map, log-likelihood (vihds/ode.py:84-93, training.py:24-44) ----------------
+      R prec[4], lprec[4], ll[4];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        prec[o] = M::DYN ? R(1) : loc[S_prec_x + o];
+        lprec[o] = M::DYN ? R(0) : vlog(prec[o]);
+        ll[o] = R(0);
+      }
+      const R* obs = a.obs ? a.obs + (size_t)b * 4 * T : nullptr;
+      R* xs = (a.x_states && active) ? a.x_states + n : nullptr;
+      R* xpr = (a.x_predict && active) ? a.x_predict + n : nullptr;
+      R ob[4] = {R(0), R(0), R(0), R(0)};
+      if (obs) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) ob[o] = obs[o * T];
+      }
+      for (int k = 0; k < T; ++k) {
+        const int slot = k & 1;
+        R obn[4] = {R(0), R(0), R(0), R(0)};
+        const int kn = k + 1 < T ? k + 1 : k;
+        if (obs) {
+#pragma unroll
+          for (int o = 0; o < 4; ++o) obn[o] = ld_early(obs + o * T + kn);
+        }
+        R x[S];
+        named_bar_sync(FULL0 + slot);
+        RingVec<R>::load(xring + slot * XSLOT, lane, 0, x);
+        if (k + 2 < T) {
+          __threadfence_block();
+          named_bar_arrive(EMPTY0 + slot);
+        }
+        if (xs) {
+#pragma unroll
+          for (int q = 0; q < S; ++q) xs[(size_t)q * N] = x[q];
+          xs += (size_t)S * N;
+        }
+        R xp[4];
+        M::observe(x, xp);
+        if (xpr) {
+#pragma unroll
+          for (int o = 0; o < 4; ++o) xpr[(size_t)o * N] = xp[o];
+          xpr += (size_t)4 * N;
+        }
+        if (obs) {
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const R pr = M::DYN ? x[NS + o] : prec[o];
+            const R lpr = M::DYN ? vlog(pr) : lprec[o];
+            const R d = xp[o] - ob[o];
+            ll[o] = loglik_add(ll[o], pr, lpr, d);
+          }
+        }
+#pragma unroll
+        for (int o = 0; o < 4; ++o) ob[o] = obn[o];
+      }
+      if (a.logp_species && active) {
+#pragma unroll
+        for (int o = 0; o < 4; ++o) a.logp_species[(size_t)n * 4 + o] = ll[o];
+      }
+    }
   }
-  R th[M::NSLOT];
-#pragma unroll
-  for (int s = 0; s < M::NSLOT; ++s) th[s] = M::uses(s) ? loc[s] : R(0);
-  traj_forward_from<M, TB>(a, n, M::DYN ? wsm : nullptr, th, lq, lp);
 }
 
 template <class M, class TB>
@@ -209,49 +371,6 @@ __global__ void __launch_bounds__(128, BwdBounds<M>::min_blocks) elbo_bwd_kernel
 // [item][lane] (conflict-free).  fp32 / fp64.  Dynamic-precision models: the NeuralPrecisions weights sit in shared
 // memory too, and a third warp accumulates their gradient (WgradRing).
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void named_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
-template <int NT>
-__device__ __forceinline__ void named_bar_sync_n(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
-template <int NT>
-__device__ __forceinline__ void named_bar_arrive_n(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
-
-// Ring slots are arrays of 16-byte vectors, [vector][lane]: item i of a lane sits in vector i / V, element i % V
-// (V = 4 fp32 / 2 fp64).  One 128-bit shared-memory access moves V items (conflict-free: a quarter warp per wavefront);
-// as 32-bit accesses the hand-off was 36 + 36 instructions per step and the warps queued on the load/store unit.
-template <typename R>
-struct RingVec {
-  static constexpr int V = 16 / sizeof(R);
-  struct alignas(16) Vec {
-    R v[V];
-  };
-  static constexpr int vectors(int items) { return (items + V - 1) / V; }
-  // elements a slot of `items` items occupies
-  static constexpr int slot_elems(int items) { return vectors(items) * V * 32; }
-  template <int N>
-  __device__ static void store(R* slot, int lane, const R (&buf)[N]) {
-    Vec* s = reinterpret_cast<Vec*>(slot) + lane;
-#pragma unroll
-    for (int g = 0; g < vectors(N); ++g) {
-      Vec q;
-#pragma unroll
-      for (int e = 0; e < V; ++e) q.v[e] = g * V + e < N ? buf[g * V + e] : R(0);
-      s[g * 32] = q;
-    }
-  }
-  // items [first, first + N) of the slot; `first` must be a multiple of V
-  template <int N>
-  __device__ static void load(const R* slot, int lane, int first, R (&buf)[N]) {
-    const Vec* s = reinterpret_cast<const Vec*>(slot) + lane + (first / V) * 32;
-#pragma unroll
-    for (int g = 0; g < vectors(N); ++g) {
-      const Vec q = s[g * 32];
-#pragma unroll
-      for (int e = 0; e < V; ++e)
-        if (g * V + e < N) buf[g * V + e] = q.v[e];
-    }
-  }
-};
 
 template <class M, class TB>
 struct WsRing {
@@ -798,10 +917,20 @@ struct FwdLauncher {
     }
     if (use_team<M>(block)) {
       // slot values | partial log-probs | NeuralPrecisions weights
-      const size_t tsm = sizeof(R) * ((size_t)M::NSLOT * 32 + 2 * FWD_TEAM * 32 + a.nw);
-      if (tsm > 48 * 1024)
-        cudaFuncSetAttribute(elbo_fwd_team_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-      elbo_fwd_team_kernel<M, TB><<<(a.N + 31) / 32, FWD_TEAM * 32, tsm, stream>>>(a);
+      // VIHDS_FWD_SCRIBE=0|1 (read per call): second warp of the time loop (see elbo_fwd_team_kernel); default on
+      const char* sc = getenv("VIHDS_FWD_SCRIBE");
+      const bool scribe = !(sc && *sc == '0') && a.T >= 2;
+      const size_t tsm = sizeof(R) * ((scribe ? 2 * (size_t)RingVec<R>::slot_elems(M::S) : 0) + (size_t)M::NSLOT * 32 +
+                                      2 * FWD_TEAM * 32 + a.nw);
+      if (scribe) {
+        if (tsm > 48 * 1024)
+          cudaFuncSetAttribute(elbo_fwd_team_kernel<M, TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        elbo_fwd_team_kernel<M, TB, true><<<(a.N + 31) / 32, FWD_TEAM * 32, tsm, stream>>>(a);
+      } else {
+        if (tsm > 48 * 1024)
+          cudaFuncSetAttribute(elbo_fwd_team_kernel<M, TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
+        elbo_fwd_team_kernel<M, TB, false><<<(a.N + 31) / 32, FWD_TEAM * 32, tsm, stream>>>(a);
+      }
     } else {
       if (smem > 48 * 1024)
         cudaFuncSetAttribute(elbo_fwd_kernel<M, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

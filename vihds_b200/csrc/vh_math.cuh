@@ -103,6 +103,30 @@ VH_HD R sigmoid(R z) {
   return sigmoid_impl(z);
 }
 
+// Arithmetic whose rounding must not depend on the surrounding code: the emission (observation map + Gaussian
+// log-likelihood) is compiled into several kernels -- the throughput form, the one-warp latency form and the scribe warp of
+// the team kernel -- and a batch must give bit-identical per-sample terms whichever of them runs it
+// (tests/test_gpu_properties.py: batch-composition invariance).  vmul_rn is a product the compiler may not contract into a
+// following add / subtract; vfma is an explicit fused multiply-add.
+VH_HD float vmul_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  volatile float r = a * b;
+  return r;
+#endif
+}
+VH_HD double vmul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(a, b);
+#else
+  volatile double r = a * b;
+  return r;
+#endif
+}
+VH_HD float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+VH_HD double vfma(double a, double b, double c) { return fma(a, b, c); }
+
 // torch.clamp semantics: NaN propagates (both comparisons false); gradient passes on the CLOSED interval.
 template <typename R>
 VH_HD R clampv(R x, R lo, R hi) {
@@ -115,6 +139,8 @@ VH_HD R clampmask(R x, R lo, R hi) {
 
 template <typename R>
 struct Lim;
+template <typename R>
+VH_HD R loglik_add(R ll, R pr, R lpr, R d);
 template <>
 struct Lim<float> {
   static constexpr float log2pi = 1.8378770664093453f;
@@ -123,5 +149,13 @@ template <>
 struct Lim<double> {
   static constexpr double log2pi = 1.8378770664093453;
 };
+
+// ll + log N(d; 0, 1 / pr) with a pinned operation order (see vmul_rn above)
+template <typename R>
+VH_HD R loglik_add(R ll, R pr, R lpr, R d) {
+  const R q = vmul_rn(pr, d);
+  const R e = vfma(q, d, Lim<R>::log2pi - lpr);
+  return vfma(R(-0.5), e, ll);
+}
 
 }  // namespace vh

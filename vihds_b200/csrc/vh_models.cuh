@@ -481,9 +481,9 @@ struct DrModel {
   // observe, vihds/ode.py:84-93
   VH_HD static void observe(const R* x, R* xp) {
     xp[0] = x[0];
-    xp[1] = x[0] * x[1];
-    xp[2] = x[0] * (x[2] + x[4]);
-    xp[3] = x[0] * (x[3] + x[5]);
+    xp[1] = vmul_rn(x[0], x[1]);
+    xp[2] = vmul_rn(x[0], x[2] + x[4]);
+    xp[3] = vmul_rn(x[0], x[3] + x[5]);
   }
   VH_HD static void observe_vjp(const R* x, const R* gxp, R* gx) {
     gx[0] += gxp[0] + gxp[1] * x[1] + gxp[2] * (x[2] + x[4]) + gxp[3] * (x[3] + x[5]);
@@ -679,16 +679,16 @@ struct GrowthModel {
   // prpr: vihds/ode.py:84-93 (default observe); auto: models/auto_constant.py:81-89; inducer: inducer_constant.py:102-110
   VH_HD static void observe(const R* x, R* xp) {
     xp[0] = x[0];
-    xp[1] = x[0] * x[1];
+    xp[1] = vmul_rn(x[0], x[1]);
     if (PRPR) {
-      xp[2] = x[0] * (x[2] + x[4]);
-      xp[3] = x[0] * (x[3] + x[5]);
+      xp[2] = vmul_rn(x[0], x[2] + x[4]);
+      xp[3] = vmul_rn(x[0], x[3] + x[5]);
     } else if (IND) {
-      xp[2] = x[0] * (x[2] + x[3]);
-      xp[3] = x[0] * x[4];
+      xp[2] = vmul_rn(x[0], x[2] + x[3]);
+      xp[3] = vmul_rn(x[0], x[4]);
     } else {
-      xp[2] = x[0] * x[2];
-      xp[3] = x[0] * x[3];
+      xp[2] = vmul_rn(x[0], x[2]);
+      xp[3] = vmul_rn(x[0], x[3]);
     }
   }
   VH_HD static void observe_vjp(const R* x, const R* gxp, R* gx) {

@@ -712,7 +712,7 @@ VH_HD void traj_forward_from(const Call<typename M::real>& a, int n, const typen
         const R pr = M::DYN ? x[NS + o] : prec[o];
         const R lpr = M::DYN ? vlog(pr) : lprec[o];
         const R d = xp[o] - ob[o];
-        ll[o] += R(-0.5) * (Lim<R>::log2pi - lpr + pr * d * d);
+        ll[o] = loglik_add(ll[o], pr, lpr, d);
       }
     }
     if (k + 1 < T) rk_step<Rhs<M>, TB>(f, t0, t1, TB::const_h ? h0 : (t1 - t0), x);
