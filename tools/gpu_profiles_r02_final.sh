@@ -4,6 +4,7 @@
 # ODE kernels of the headline workload, compute-sanitizer over every kernel family.
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE_OK')" 2>&1 | tail -2
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -4 | tee gpurun_out/r02f_pytest_gpu.txt
 timeout 600 python bench.py --steps 100 --warmup 5 2>gpurun_out/r02f_bench.err | tail -1 > gpurun_out/r02f_bench_1gpu.json
 timeout 300 python bench.py --impl reference --steps 8 --warmup 2 2>>gpurun_out/r02f_bench.err | tail -1 > gpurun_out/r02f_bench_reference_arm.json

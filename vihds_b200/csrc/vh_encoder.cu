@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(ENC_THREADS) enc_fwd_kernel(const EncDims d, c
   const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
   const int b0 = blockIdx.x * G;
   const int ngr = min(G, d.B - b0);
+  pdl_trigger();  // the ODE forward launch may become resident; it waits for this grid before it reads the q tables
   const int ncw = d.F * d.NS * d.K;
   const int nfree = 2 * (d.nl + d.ng);
   // staged copies (d.stage): hidden-layer weights + bias, head weights + biases

@@ -171,6 +171,9 @@ __global__ void __launch_bounds__(FWD_TEAM * 32) elbo_fwd_team_kernel(const Call
   typedef typename M::real R;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   R* sm = reinterpret_cast<R*>(smem_raw);
+  // launched under the tail of the encoder forward when that is the preceding kernel of the stream (vh_pdl.cuh); everything
+  // below reads its q tables
+  pdl_wait();
   pdl_trigger();  // the reverse launch may become resident now; it blocks in pdl_wait() until this grid has completed
   const int role = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * 32 + lane;
@@ -925,11 +928,11 @@ struct FwdLauncher {
       if (scribe) {
         if (tsm > 48 * 1024)
           cudaFuncSetAttribute(elbo_fwd_team_kernel<M, TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-        elbo_fwd_team_kernel<M, TB, true><<<(a.N + 31) / 32, FWD_TEAM * 32, tsm, stream>>>(a);
+        launch_maybe_pdl(elbo_fwd_team_kernel<M, TB, true>, dim3((a.N + 31) / 32), dim3(FWD_TEAM * 32), tsm, stream, true, a);
       } else {
         if (tsm > 48 * 1024)
           cudaFuncSetAttribute(elbo_fwd_team_kernel<M, TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm);
-        elbo_fwd_team_kernel<M, TB, false><<<(a.N + 31) / 32, FWD_TEAM * 32, tsm, stream>>>(a);
+        launch_maybe_pdl(elbo_fwd_team_kernel<M, TB, false>, dim3((a.N + 31) / 32), dim3(FWD_TEAM * 32), tsm, stream, true, a);
       }
     } else {
       if (smem > 48 * 1024)
