@@ -250,6 +250,9 @@ int vh_copy_async(void* dst, const void* src, size_t bytes, void* stream);
  *                           it synchronises and stop. */
 #define VH_PEER_MAX_WORLD 16
 size_t vh_peer_buffer_bytes(int dtype, size_t n, int world);
+/* diagnostics: %globaltimer stamps (ns) of thread block 0 of the last exchange launch on the current device: start, after
+ * griddepcontrol.wait, pushed, published, peers' flags seen, vote passed, update applied, (unused) */
+int vh_peer_debug_times(unsigned long long* out8);
 int vh_peer_buffer_create(size_t bytes, void** dev_ptr, void* handle64);
 int vh_peer_buffer_open(const void* handle64, void** dev_ptr);
 int vh_peer_buffer_close(void* dev_ptr);
