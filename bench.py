@@ -484,13 +484,20 @@ def run_workload(name, a, rank, local_rank, world, device, pg, primary):
     note = ("latency-bound at this size: %d trajectories = %d warps on 148 SMs x 4 schedulers" % (N, (N + 31) // 32)
             if N < 148 * 4 * 32 * 4 else "FP32-issue-bound: ~440 instructions per 32 B of trace") + " (DESIGN.md section 5)"
     res["kernels"] = {"elbo_fwd_us": fwd_us, "elbo_bwd_us": bwd_us, "elbo_bwd_in_step_us": bwd_in_step_us}
+    # which form of the white-box kernels this batch takes (vh_launch.cuh: pick_block / use_ws / MxOk)
+    latency = N <= 148 * 4 * 32
+    hidden = bool(getattr(gs.prob, "dynamic_precisions", False) and gs.prob.net.get("n_hidden", 0) > 0)
+    mx = (latency and name.startswith("dr_constant") and "precisions" not in name and settings.params.solver == "midpoint"
+          and settings.dtype == torch.float32 and os.environ.get("VIHDS_BWD_MX", "1") != "0")
+    bwd_name = "bbm_bwd_kernel" if bb else ("elbo_bwd_mx_kernel" if mx else ("elbo_bwd_ws_kernel" if latency and not hidden else "elbo_bwd_kernel"))
+    fwd_name = "bbm_fwd_kernel" if bb else ("elbo_fwd_team_kernel" if latency else "elbo_fwd_kernel")
     res["roofline"] = {
-        "kernel": "%s (discrete-adjoint reverse sweep, the dominant launch)" % ("bbm_bwd_kernel" if bb else "elbo_bwd_kernel"),
+        "kernel": "%s (discrete-adjoint reverse sweep, the dominant launch)" % bwd_name,
         "bound": "hbm", "achieved": bytes_bwd / (bwd_in_step_us * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
         "frac": bytes_bwd / (bwd_in_step_us * 1e-6) / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": peak_src, "algorithmic_bytes": bytes_bwd, "launch_us": bwd_in_step_us, "note": note}
     res["roofline_fwd"] = {
-        "kernel": "bbm_fwd_kernel" if bb else "elbo_fwd_kernel", "bound": "hbm", "achieved": bytes_fwd / (fwd_us * 1e-6) / 1e9,
+        "kernel": fwd_name, "bound": "hbm", "achieved": bytes_fwd / (fwd_us * 1e-6) / 1e9,
         "peak": peak, "unit": "GB/s", "frac": bytes_fwd / (fwd_us * 1e-6) / 1e9 / peak, "algorithmic_bytes": bytes_fwd,
         "launch_us": fwd_us}
     res["config"] = workload_config(name, B, IW, T, S, P, settings.params.solver, world)
