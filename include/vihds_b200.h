@@ -227,6 +227,9 @@ int vh_adam_step_dev(int dtype, size_t n, void* param, void* grad, void* exp_avg
  * weights: `.to(device)` in vihds/training.py:326-329, vae.py:22-24) without a tensor library in between.  Host memory
  * should be pinned. */
 int vh_copy_async(void* dst, const void* src, size_t bytes, void* stream);
+/* cudaMemsetAsync(dst, 0, bytes): the `optimizer.zero_grad()` of training.py:333 for the reverse launch's accumulators
+ * (vh_bwd_io.outputs_cleared) as a memset node of the captured step instead of a fill kernel */
+int vh_zero_async(void* dst, size_t bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Multi-GPU exchange step fused with the optimiser (no counterpart in the single-device reference; it takes the place

@@ -101,6 +101,7 @@ def load():
                                  C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p]
     lib.vh_adam_step_dev.argtypes = [C.c_int, C.c_size_t] + [C.c_void_p] * 6 + [C.c_int, C.c_void_p, C.c_void_p]
     lib.vh_copy_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.vh_zero_async.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
     lib.vh_peer_buffer_bytes.restype = C.c_size_t
     lib.vh_peer_buffer_bytes.argtypes = [C.c_int, C.c_size_t, C.c_int]
     lib.vh_peer_buffer_create.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]

@@ -526,6 +526,19 @@ int vh_adam_step_dev(int dtype, size_t n, void* param, void* grad, void* exp_avg
   return check_launch("adam_dev_kernel");
 }
 
+int vh_zero_async(void* dst, size_t bytes, void* stream) {
+  if (!dst) {
+    set_error("vh_zero_async: null pointer");
+    return VH_ERR_INVALID;
+  }
+  cudaError_t e = cudaMemsetAsync(dst, 0, bytes, (cudaStream_t)stream);
+  if (e != cudaSuccess) {
+    set_error("vh_zero_async(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    return VH_ERR_CUDA;
+  }
+  return VH_OK;
+}
+
 int vh_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
   if (!dst || !src) {
     set_error("vh_copy_async: null pointer");

@@ -317,9 +317,9 @@ class GraphedStep(object):
             # outputs the reverse launch accumulates into, cleared HERE (a parallel branch of the captured graph) instead of
             # by a memset node between the forward and the reverse kernel: vh_bwd_io.outputs_cleared
             if self.outputs_cleared:
-                self.buf.d_q_cost.zero_()
-                if self.d_weights is not None:
-                    self.d_weights.zero_()
+                for t in (self.buf.d_q_cost, self.d_weights):
+                    if t is not None:
+                        L.check(lib.vh_zero_async(t.data_ptr(), t.numel() * t.element_size(), _stream()))
         if fork:
             with torch.cuda.stream(self._side):
                 if not self._global_devices_loaded:
