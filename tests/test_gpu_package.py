@@ -328,10 +328,12 @@ def test_fused_encoder_large_batch_paths(B):
         assert _rel(a.cpu().numpy(), b.cpu().numpy()) < 5e-5, tuple(p.shape)
 
 
-def test_step_from_host_equals_step():
+@pytest.mark.parametrize("one_graph", ["1", "0"])
+def test_step_from_host_equals_step(one_graph, monkeypatch):
     """The end-to-end entry (host buffers; two input sets filled on a copy stream, alternating) takes the same steps as
     load_* + step().  Every step has its own batch contents and u, the calls are issued back to back without a
     synchronisation, and a ``step()`` in the middle of the stream (mode "mixed") computes on the set in use."""
+    monkeypatch.setenv("VIHDS_ONE_GRAPH", one_graph)  # "0": the two-graph form of the step everywhere
     case = load_case("dr_constant_icml_midpoint_f32_iw8")
     batch = batch_from_case(case)
     B, IW, P = case["u"].shape
