@@ -6,6 +6,7 @@
 
 #include "../../vihds_b200/csrc/vh_dispatch.cuh"
 #include "../../vihds_b200/csrc/vh_bb.cuh"
+#include "../../vihds_b200/csrc/vh_mx_math.cuh"
 
 namespace {
 using namespace vh;
@@ -139,4 +140,39 @@ extern "C" const char* hc_build_error(const vh_problem* p, const vh_fwd_io* io) 
 extern "C" const char* hc_slot_name(int model, int s) {
   if (vh::model_is_dyn(model) && s >= vh::S_prec_x && s <= vh::S_prec_cfp) return vh::kDrDynPrecNames[s - vh::S_prec_x];
   return vh::kDrSlotNames[s];
+}
+
+// One midpoint step of the adjoint two ways (fp64): rk_step_adjoint on the kept stage data -- the code every reverse kernel
+// runs -- and the matrix form of vh_bwd_mx.cuh, lambda0 = (I + h A + h^2/2 A B)^T lambda1.  th: DR_NSLOT slot values,
+// tc: {C6, C12, Ara}, x: state at t0, lam1: cotangent at t1.  Outputs: lam_ref[8], lam_mx[8].
+template <int VER>
+static void mx_step_t(const double* th, const double* tc, const double* x, const double* lam1, double t0, double t1,
+                      double* lam_ref, double* lam_mx) {
+  typedef DrModel<double, VER, 0, false> M;
+  typedef TabMidpoint<double> TB;
+  Rhs<M> f;
+  f.w = nullptr;
+  f.nh = 0;
+  M::setup(th, tc, f.c);
+  const double h = t1 - t0;
+  StageData<Rhs<M>, TB> sd;
+  rk_stages_forward<Rhs<M>, TB>(f, t0, t1, h, x, sd);
+  typename M::Consts gc;
+  for (int i = 0; i < M::NC; ++i) gc.v[i] = 0.0;
+  NoGW<double> nogw;
+  for (int q = 0; q < 8; ++q) lam_ref[q] = lam1[q];
+  rk_step_adjoint<Rhs<M>, TB>(f, t0, t1, h, x, sd, lam_ref, gc, nogw);
+  double Xm[8], Nv[MXN_ITEMS];
+  for (int q = 0; q < 8; ++q) Xm[q] = x[q] + (h * TB::a(1, 0)) * sd.k[0][q];
+  mx_step_matrix<M>(x, Xm, f.c, sd.kept[0].m, sd.kept[1].m, h, TB::a(1, 0), Nv);
+  for (int i = 0; i < 4; ++i) Nv[MXN_E + i] = 0.0;
+  for (int q = 0; q < 8; ++q) lam_mx[q] = lam1[q];
+  mx_apply(Nv, lam_mx);
+}
+extern "C" void hc_mx_step(int version, const double* th, const double* tc, const double* x, const double* lam1, double t0,
+                           double t1, double* lam_ref, double* lam_mx) {
+  if (version == 2)
+    mx_step_t<2>(th, tc, x, lam1, t0, t1, lam_ref, lam_mx);
+  else
+    mx_step_t<1>(th, tc, x, lam1, t0, t1, lam_ref, lam_mx);
 }

@@ -104,3 +104,32 @@ def test_host_math_matches_reference(hc, name):
         dW, db = H.offset_layer_grads(case, bkeep["d_extra"])
         assert _rel(dW, case["gw:ode_model.offset_layer.weight"]) < gtol
         assert _rel(db, case["gw:ode_model.offset_layer.bias"]) < gtol
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_matrix_form_of_the_midpoint_adjoint_equals_the_vjp_form(version):
+    """vh_mx_math.cuh (what elbo_bwd_mx_kernel's producers and consumer compute) against rk_step_adjoint (what every other
+    reverse kernel computes) on random states, parameters and cotangents, in fp64 on the host: the two are the same linear
+    map, lambda0 = (I + h A + h^2/2 A B)^T lambda1."""
+    import ctypes as C
+
+    lib = H.build_hostcheck()
+    dp = C.POINTER(C.c_double)
+    lib.hc_mx_step.argtypes = [C.c_int, dp, dp, dp, dp, C.c_double, C.c_double, dp, dp]
+    lib.hc_mx_step.restype = None
+    rng = np.random.RandomState(7 + version)
+    nslot = lib.hc_num_slots()
+    worst = 0.0
+    for trial in range(50):
+        th = np.ascontiguousarray(rng.uniform(0.05, 2.5, size=nslot))
+        tc = np.ascontiguousarray(rng.uniform(0.1, 20.0, size=3))
+        x = np.ascontiguousarray(rng.uniform(0.01, 3.0, size=8))
+        lam1 = np.ascontiguousarray(rng.randn(8))
+        t0 = float(rng.uniform(0.0, 10.0))
+        t1 = t0 + float(rng.uniform(0.05, 0.4))
+        ref, mx = np.zeros(8), np.zeros(8)
+        lib.hc_mx_step(version, th.ctypes.data_as(dp), tc.ctypes.data_as(dp), x.ctypes.data_as(dp), lam1.ctypes.data_as(dp),
+                       t0, t1, ref.ctypes.data_as(dp), mx.ctypes.data_as(dp))
+        assert np.all(np.isfinite(ref))
+        worst = max(worst, float(np.max(np.abs(ref - mx)) / max(1e-300, np.max(np.abs(ref)))))
+    assert worst < 1e-12, worst

@@ -25,6 +25,7 @@
 //   warps NP+1 ..       accumulators  d constants
 // Rings: [slot][item][lane] in shared memory, one mbarrier pair (full / empty) per slot.
 #pragma once
+#include "vh_mx_math.cuh"
 
 namespace vh {
 
@@ -102,50 +103,6 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
 #endif
   } while (!done);
 }
-
-// ---- Jacobian of the species right-hand side (DrModel, no extension) at state X with intermediates m -------------------
-template <typename R>
-struct DrJac {
-  R j00;          // d f0 / d x0
-  R c0[8];        // d f_i / d x0, i = 1..7
-  R dg[8];        // d f_i / d x_i, i = 1..7
-  R j26, j27, j36, j37;
-};
-template <class M>
-__device__ __forceinline__ void dr_jacobian(const typename M::real* X, const typename M::Consts& c, const typename M::Mid& m,
-                                            DrJac<typename M::real>& J) {
-  typedef typename M::real R;
-  const R* v = c.v;
-  const R dgam = -(m.gr * c.iK);  // d gamma / d x0
-  J.j00 = m.gam + X[0] * dgam;
-#pragma unroll
-  for (int i = 1; i < 8; ++i) J.c0[i] = -(X[i] * dgam);
-  J.dg[1] = -(m.gam + v[C_drfp]);
-  J.dg[2] = -(m.gam + v[C_dyfp]);
-  J.dg[3] = -(m.gam + v[C_dcfp]);
-  J.dg[4] = -m.gam;
-  J.dg[5] = -m.gam;
-  J.dg[6] = -(m.gam + v[C_dR]);
-  J.dg[7] = -(m.gam + v[C_dS]);
-  // promoter activities P = (e + a + b) / (1 + a + b), a = KGR x6^2 fR, b = KGS x7^2 fS:  dP/da = (1 - P) / (1 + a + b)
-  const R q81 = v[C_cY] * ((R(1) - m.P81) * m.i81), q76 = v[C_cC] * ((R(1) - m.P76) * m.i76);
-  const R s6 = R(2) * X[6] * v[C_fR], s7 = R(2) * X[7] * v[C_fS];
-  J.j26 = q81 * v[C_KGR81] * s6;
-  J.j27 = q81 * v[C_KGS81] * s7;
-  J.j36 = q76 * v[C_KGR76] * s6;
-  J.j37 = q76 * v[C_KGS76] * s7;
-}
-
-// the 20 + 4 numbers a step hands to the recurrence; order = ring item order
-enum {
-  MXN_00 = 0,   // N_00
-  MXN_C0 = 0,   // N_i0 at MXN_C0 + i, i = 1..7
-  MXN_DG = 7,   // N_ii at MXN_DG + i, i = 1..7
-  MXN_26 = 15, MXN_27 = 16, MXN_36 = 17, MXN_37 = 18,
-  MXN_E = 19,   // emission cotangent: e0, e1, e2 (= e4), e3 (= e5)
-  MXN_ITEMS = 23,
-  MXN_PAD = 24  // the accumulators' share of a slot starts on a vector boundary
-};
 
 template <class M, class TB>
 struct MxRing {
@@ -320,25 +277,8 @@ __global__ void __maxnreg__(MX_MAXREG) elbo_bwd_mx_kernel(const Call<typename M:
       R Xm[S];
 #pragma unroll
       for (int q = 0; q < S; ++q) Xm[q] = x[q] + (h * TB::a(1, 0)) * sd.k[0][q];
-      DrJac<R> A, B;
-      dr_jacobian<M>(Xm, f.c, sd.kept[1].m, A);
-      dr_jacobian<M>(x, f.c, sd.kept[0].m, B);
-      // N = I + h A + h^2/2 A B on the common sparsity pattern
-      const R hh = h * h * TB::a(1, 0);
       R Nv[MXN_ITEMS];
-      Nv[MXN_00] = R(1) + h * A.j00 + hh * (A.j00 * B.j00);
-#pragma unroll
-      for (int i = 1; i < 8; ++i) {
-        R ab = A.c0[i] * B.j00 + A.dg[i] * B.c0[i];
-        if (i == 2) ab += A.j26 * B.c0[6] + A.j27 * B.c0[7];
-        if (i == 3) ab += A.j36 * B.c0[6] + A.j37 * B.c0[7];
-        Nv[MXN_C0 + i] = h * A.c0[i] + hh * ab;
-        Nv[MXN_DG + i] = R(1) + h * A.dg[i] + hh * (A.dg[i] * B.dg[i]);
-      }
-      Nv[MXN_26] = h * A.j26 + hh * (A.dg[2] * B.j26 + A.j26 * B.dg[6]);
-      Nv[MXN_27] = h * A.j27 + hh * (A.dg[2] * B.j27 + A.j27 * B.dg[7]);
-      Nv[MXN_36] = h * A.j36 + hh * (A.dg[3] * B.j36 + A.j36 * B.dg[6]);
-      Nv[MXN_37] = h * A.j37 + hh * (A.dg[3] * B.j37 + A.j37 * B.dg[7]);
+      mx_step_matrix<M>(x, Xm, f.c, sd.kept[0].m, sd.kept[1].m, h, TB::a(1, 0), Nv);
       emission(x, ob, Nv + MXN_E, gprec);
       if (use > 0) mbar_wait(empty1 + slot, (use - 1) & 1);  // both readers have released the slot
       {
@@ -392,21 +332,7 @@ __global__ void __maxnreg__(MX_MAXREG) elbo_bwd_mx_kernel(const Call<typename M:
       R Nv[MXN_ITEMS];
       RingVec<R>::load(ring + slot * MR::SLOT, lane, 0, Nv);
       mbar_arrive_warp(empty1 + slot, lane);
-      // column 0 gathers all eight components (pairwise: depth 4), the others one or three
-      const R s01 = Nv[MXN_00] * lam[0] + Nv[MXN_C0 + 1] * lam[1];
-      const R s23 = Nv[MXN_C0 + 2] * lam[2] + Nv[MXN_C0 + 3] * lam[3];
-      const R s45 = Nv[MXN_C0 + 4] * lam[4] + Nv[MXN_C0 + 5] * lam[5];
-      const R s67 = Nv[MXN_C0 + 6] * lam[6] + Nv[MXN_C0 + 7] * lam[7];
-      const R l6 = Nv[MXN_DG + 6] * lam[6] + (Nv[MXN_26] * lam[2] + Nv[MXN_36] * lam[3]);
-      const R l7 = Nv[MXN_DG + 7] * lam[7] + (Nv[MXN_27] * lam[2] + Nv[MXN_37] * lam[3]);
-      lam[0] = ((s01 + s23) + (s45 + s67)) + Nv[MXN_E + 0];
-      lam[1] = Nv[MXN_DG + 1] * lam[1] + Nv[MXN_E + 1];
-      lam[2] = Nv[MXN_DG + 2] * lam[2] + Nv[MXN_E + 2];
-      lam[3] = Nv[MXN_DG + 3] * lam[3] + Nv[MXN_E + 3];
-      lam[4] = Nv[MXN_DG + 4] * lam[4] + Nv[MXN_E + 2];
-      lam[5] = Nv[MXN_DG + 5] * lam[5] + Nv[MXN_E + 3];
-      lam[6] = l6;
-      lam[7] = l7;
+      mx_apply(Nv, lam);
     }
     // chain rule back to theta (as elbo_bwd_ws_kernel); the constants' cotangents come from the accumulators
     named_bar_sync_n<MX_WARPS * 32>(1);  // producers' d prec and accumulators' d constants are in shared memory
